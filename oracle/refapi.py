@@ -1,0 +1,250 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes binding of oracle/_ref/libref_mtrack.so (the unmodified reference
+mtracklib compiled by oracle/build_ref.py).  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / reference arm may import this module; the product never does."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_ref", "libref_mtrack.so")
+EXE = os.path.join(HERE, "_ref", "ref_rebvo")
+
+# struct KeyLine, include/mtracklib/edge_finder.h:45-91 (168 bytes)
+KEYLINE = np.dtype({
+    "names": ["p_inx", "m_m", "u_m", "n_m", "score", "c_p", "rho", "s_rho", "rho_nr", "s_rho_nr",
+              "rho0", "s_rho0", "p_m", "p_m_0", "m_id", "m_id_f", "m_id_kf", "m_num", "m_m0", "n_m0",
+              "p_id", "n_id", "net_id", "stereo_m_id", "stereo_rho", "stereo_s_rho"],
+    "formats": ["i4", ("f4", 2), ("f4", 2), "f4", "f4", ("f4", 2), "f8", "f8", "f8", "f8", "f8", "f8",
+                ("f4", 2), ("f4", 2), "i4", "i4", "i4", "i4", ("f4", 2), "f8", "i4", "i4", "i4", "i4",
+                "f8", "f8"],
+    "offsets": [0, 4, 12, 20, 24, 28, 40, 48, 56, 64, 72, 80, 88, 96, 104, 108, 112, 116, 120, 128,
+                136, 140, 144, 148, 152, 160],
+    "itemsize": 168})
+
+_lib = None
+
+
+def _blas_dir():
+    import glob
+    import importlib.util
+    spec = importlib.util.find_spec("cv2")
+    return os.path.join(os.path.dirname(os.path.dirname(spec.origin)), "opencv_python_headless.libs")
+
+
+def _preload():
+    import glob
+    d = _blas_dir()
+    for pat in ("libquadmath*", "libgfortran*", "libopenblas*"):
+        for f in sorted(glob.glob(os.path.join(d, pat))):
+            C.CDLL(f, mode=C.RTLD_GLOBAL)
+
+
+def available():
+    return os.path.exists(LIB)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _preload()
+        _lib = C.CDLL(LIB)
+        L = _lib
+        L.ref_map_create.restype = C.c_void_p
+        L.ref_map_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                     C.c_double, C.c_double]
+        L.ref_quantile.restype = C.c_double
+        L.ref_minimizer_rv.restype = C.c_double
+        L.ref_try_vel_rot.restype = C.c_double
+        L.ref_rescale.restype = C.c_double
+        assert L.ref_sizeof_keyline() == KEYLINE.itemsize
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class RefMap:
+    """One ring slot of the reference: sspace + edge_tracker + global_tracker (rebvo.cpp:297-312)."""
+
+    def __init__(self, w, h, ppx, ppy, zfx, zfy, sigma0, ksigma):
+        self.w, self.h = w, h
+        self.L = lib()
+        self.h_ = C.c_void_p(self.L.ref_map_create(w, h, ppx, ppy, zfx, zfy, sigma0, ksigma))
+
+    def __del__(self):
+        if getattr(self, "h_", None):
+            self.L.ref_map_destroy(self.h_)
+            self.h_ = None
+
+    def rgb2bw(self, rgb):
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        self.L.ref_rgb2bw(self.h_, _p(rgb))
+
+    def set_gray(self, g):
+        g = np.ascontiguousarray(g, np.float32)
+        self.L.ref_set_gray(self.h_, _p(g))
+
+    def build(self):
+        self.L.ref_build(self.h_)
+
+    def plane(self, which):
+        idx = {"img0": 0, "img1": 1, "dog": 2, "dx": 3, "dy": 4, "gray": 5}[which]
+        out = np.empty((self.h, self.w), np.float32)
+        self.L.ref_get_plane(self.h_, idx, _p(out))
+        return out
+
+    def detect(self, plane_fit, pos_neg, dog_thresh, kl_max, tresh, l_kl_num, kl_ref, gain, tmax, tmin):
+        t = C.c_double(tresh)
+        l = C.c_int(l_kl_num)
+        kn = self.L.ref_detect(self.h_, plane_fit, C.c_double(pos_neg), C.c_double(dog_thresh), kl_max,
+                               C.byref(t), C.byref(l), kl_ref, C.c_double(gain), C.c_double(tmax),
+                               C.c_double(tmin))
+        return kn, t.value, l.value
+
+    def reestimate(self, knum, n):
+        o = C.c_float(0)
+        r = self.L.ref_reestimate(self.h_, knum, n, C.byref(o))
+        return r, o.value
+
+    def knum(self):
+        return self.L.ref_knum(self.h_)
+
+    def keylines(self):
+        out = np.zeros(self.knum(), KEYLINE)
+        self.L.ref_get_keylines(self.h_, _p(out))
+        return out
+
+    def set_keylines(self, kl):
+        kl = np.ascontiguousarray(kl, KEYLINE)
+        self.L.ref_set_keylines(self.h_, _p(kl), len(kl))
+
+    def mask(self):
+        out = np.empty((self.h, self.w), np.int32)
+        self.L.ref_get_mask(self.h_, _p(out))
+        return out
+
+    def set_mask(self, mask, kn):
+        mask = np.ascontiguousarray(mask, np.int32)
+        self.L.ref_set_mask(self.h_, _p(mask), kn)
+
+    def quantile(self, smin, smax, perc, n):
+        return self.L.ref_quantile(self.h_, C.c_double(smin), C.c_double(smax), C.c_double(perc), n)
+
+    def build_field(self, radius, min_mod):
+        self.L.ref_build_field(self.h_, radius, C.c_float(min_mod))
+
+    def field(self):
+        out = np.empty((self.h, self.w, 2), np.int32)
+        self.L.ref_get_field(self.h_, _p(out))
+        return out
+
+    def minimizer_rv(self, old, V, W, match_thresh, iter_max, init_type, reweight, max_s_rho,
+                     match_num_thresh, init_iter):
+        V = np.array(V, np.float64)
+        W = np.array(W, np.float64)
+        RV = np.eye(3) * 1e50
+        RW = np.eye(3) * 1e50
+        WX = np.zeros((6, 6))
+        e1, e2 = C.c_double(0), C.c_double(0)
+        F = self.L.ref_minimizer_rv(self.h_, old.h_, _p(V), _p(W), _p(RV), _p(RW), C.c_double(match_thresh),
+                                    iter_max, init_type, C.c_double(reweight), C.byref(e1), C.byref(e2),
+                                    C.c_double(max_s_rho), C.c_uint(match_num_thresh),
+                                    C.c_double(init_iter), _p(WX))
+        return dict(F=F, V=V, W=W, RVel=RV, RW0=RW, W_X=WX, rel_err=e1.value, rel_err_score=e2.value)
+
+    def try_vel_rot(self, old, X, reweight, procjf, match_thresh, s_rho_min, match_num_thresh, k_huber,
+                    res_in):
+        X = np.array(X, np.float64)
+        pnum = (old.knum() + 3) & ~3
+        res_in = np.ascontiguousarray(res_in, np.float64)
+        assert len(res_in) == pnum
+        res_out = np.full(pnum, np.nan)
+        JtJ = np.zeros((6, 6))
+        JtF = np.zeros(6)
+        s = self.L.ref_try_vel_rot(self.h_, old.h_, _p(X), int(reweight), int(procjf),
+                                   C.c_double(match_thresh), C.c_double(s_rho_min),
+                                   C.c_uint(match_num_thresh), C.c_double(k_huber), _p(res_in),
+                                   _p(res_out), _p(JtJ), _p(JtF))
+        return s, JtJ, JtF, res_out
+
+    def forward_match(self, new):
+        return self.L.ref_forward_match(self.h_, new.h_)
+
+    def rotate(self, R):
+        R = np.ascontiguousarray(R, np.float64)
+        self.L.ref_rotate(self.h_, _p(R))
+
+    def directed_matching(self, old, V, RVel, BackRot, thr_mod, thr_ang, max_radius, loc_unc):
+        V = np.ascontiguousarray(V, np.float64)
+        RVel = np.ascontiguousarray(RVel, np.float64)
+        BackRot = np.ascontiguousarray(BackRot, np.float64)
+        kf = C.c_int(0)
+        return self.L.ref_directed_matching(self.h_, old.h_, _p(V), _p(RVel), _p(BackRot), C.byref(kf),
+                                            C.c_double(thr_mod), C.c_double(thr_ang),
+                                            C.c_double(max_radius), C.c_double(loc_unc))
+
+    def num_matches(self):
+        return self.L.ref_num_matches(self.h_)
+
+    def regularize(self, thresh):
+        return self.L.ref_regularize(self.h_, C.c_double(thresh))
+
+    def ekf(self, V, RVel, RW0, qabs, qrel, loc_unc):
+        V = np.ascontiguousarray(V, np.float64)
+        RVel = np.ascontiguousarray(RVel, np.float64)
+        RW0 = np.ascontiguousarray(RW0, np.float64)
+        self.L.ref_ekf(self.h_, _p(V), _p(RVel), _p(RW0), C.c_double(qabs), C.c_double(qrel),
+                       C.c_double(loc_unc))
+
+    def rescale(self, s_rho_min, match_num_min, re_escale):
+        rkp = C.c_double(0)
+        kp = self.L.ref_rescale(self.h_, C.byref(rkp), C.c_double(s_rho_min), C.c_uint(match_num_min),
+                                int(re_escale))
+        return kp, rkp.value
+
+
+def so3_exp(w):
+    w = np.ascontiguousarray(w, np.float64)
+    R = np.zeros((3, 3))
+    lib().ref_so3_exp(_p(w), _p(R))
+    return R
+
+
+def so3_ln(R):
+    R = np.ascontiguousarray(R, np.float64)
+    w = np.zeros(3)
+    lib().ref_so3_ln(_p(R), _p(w))
+    return w
+
+
+OUTREC = np.dtype([("t", "f8"), ("Pos", "f8", 3), ("PoseLie", "f8", 3), ("Pose", "f8", 9), ("Vel", "f8", 3),
+                   ("RotLie", "f8", 3), ("dtp0", "f8"), ("dtp1", "f8"), ("K", "f8"), ("Kp", "f8"),
+                   ("s_rho_p", "f8"), ("kn", "i4"), ("matches", "i4"), ("est_ok", "i4"), ("pad", "i4")])
+
+
+def run_full_rebvo(frames_file, out_file, params=None, timeout=600):
+    """Level B: run the reference's whole 3-thread REBVO on a raw frame file (oracle/ref_driver.cpp)."""
+    import json
+    import resource
+    import subprocess
+
+    def pre():
+        # finite, large stack: the reference keeps O(27*8*K) byte VLAs on thread stacks
+        resource.setrlimit(resource.RLIMIT_STACK, (1000000 * 1024, resource.RLIM_INFINITY))
+
+    args = [EXE, frames_file, out_file] + ["%s=%r" % (k, v) for k, v in (params or {}).items()]
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = _blas_dir() + ":" + env.get("LD_LIBRARY_PATH", "")
+    env.setdefault("OPENBLAS_NUM_THREADS", "1")
+    r = subprocess.run(args, capture_output=True, text=True, timeout=timeout, preexec_fn=pre, env=env)
+    if r.returncode != 0:
+        raise RuntimeError("ref_rebvo failed: %s\n%s" % (r.returncode, r.stderr[-2000:]))
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    info = json.loads(line)
+    with open(out_file, "rb") as f:
+        n, sz = np.frombuffer(f.read(8), np.int32)
+        assert sz == OUTREC.itemsize, (sz, OUTREC.itemsize)
+        rec = np.frombuffer(f.read(), OUTREC, count=n)
+    return info, rec
