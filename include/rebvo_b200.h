@@ -1,0 +1,207 @@
+/* rebvo_b200.h -- C ABI of librebvo_b200.so: the B200 (sm_100a) implementation of REBVO's per-frame
+ * edge pipeline (DoG edge detector + keyline extraction, edge-map tracker / SE(3) minimiser, per-keyline
+ * inverse-depth EKF).
+ *
+ * The reference (JuanTarrio/rebvo) has no FFI: its hot path is a set of C++ classes called directly by
+ * REBVO::FirstThr (src/rebvo/rebvo_first_t.cpp:259-272) and REBVO::SecondThread
+ * (src/rebvo/rebvo_second_t.cpp:172-487).  Each entry point below replaces one of those calls; the
+ * comment on each cites the reference method it stands for.  Host shim classes with the reference's own
+ * names/signatures (include/rebvo_b200_shim.hpp) forward to these functions, see INTEGRATION.md.
+ *
+ * Conventions: every function returns 0 on success, a negative rb_status otherwise, and never throws.
+ * A CUDA failure is sticky per context (rb_last_error()).  Pointers are plain host pointers unless the
+ * name says dev.  Images are row-major without stride (Image<T>, include/VideoLib/image.h:42-217).
+ * All calls on one context are ordered on the context's CUDA stream; functions that return values to
+ * host memory synchronise that stream before returning.
+ */
+#ifndef REBVO_B200_H
+#define REBVO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rb_ctx rb_ctx; /* device, stream, camera model, DoG filter plan, scratch */
+typedef struct rb_map rb_map; /* one ring slot: sspace + edge_tracker + global_tracker (rebvo.cpp:297-312) */
+typedef struct rb_pipeline rb_pipeline; /* FirstThr + SecondThread per-frame flow, device resident */
+
+enum rb_status {
+    RB_OK = 0,
+    RB_ERR_CUDA = -1,
+    RB_ERR_ARG = -2,
+    RB_ERR_NO_DEVICE = -3,
+    RB_ERR_STATE = -4
+};
+
+/* struct KeyLine (include/mtracklib/edge_finder.h:45-91): 168-byte AoS record produced for host
+ * consumers by rb_map_sync_host_keylines(); field names and offsets are the reference's. */
+typedef struct rb_keyline {
+    int32_t p_inx;
+    float m_m[2], u_m[2], n_m, score, c_p[2];
+    int32_t _pad0;
+    double rho, s_rho, rho_nr, s_rho_nr, rho0, s_rho0;
+    float p_m[2], p_m_0[2];
+    int32_t m_id, m_id_f, m_id_kf, m_num;
+    float m_m0[2];
+    double n_m0;
+    int32_t p_id, n_id, net_id, stereo_m_id;
+    double stereo_rho, stereo_s_rho;
+} rb_keyline;
+
+/* cam_model (include/UtilLib/cam_model.h:32-50): pinhole part used by the hot path */
+typedef struct rb_camera {
+    int32_t w, h;
+    float ppx, ppy, zfx, zfy;
+} rb_camera;
+
+/* arguments of edge_finder::detect (edge_finder.cpp:342-365) */
+typedef struct rb_detect_params {
+    int32_t plane_fit_size; /* DetectorPlaneFitSize (only 2 is supported: 5x5 window) */
+    double pos_neg_thresh;  /* DetectorPosNegThresh */
+    double dog_thresh;      /* DetectorDoGThresh */
+    int32_t kl_max;         /* MaxPoints */
+    int32_t kl_ref;         /* ReferencePoints */
+    double gain;            /* DetectorAutoGain (0 = fixed threshold) */
+    double thresh_max, thresh_min;
+} rb_detect_params;
+
+/* the REBVOParameters subset (include/rebvo/rebvo.h:64-235) the edge pipeline reads */
+typedef struct rb_params {
+    rb_camera cam;
+    double Sigma0, KSigma;
+    rb_detect_params det;
+    double DetectorThresh;
+    int32_t TrackPoints;
+    int32_t QCutOffNumBins;
+    double QCutOffQuantile;
+    int32_t SearchRange;
+    int32_t TrackerIterNum, TrackerInitIterNum, TrackerInitType;
+    double TrackerMatchThresh;
+    double LocationUncertaintyMatch, MatchThreshModule, MatchThreshAngle;
+    double ReweigthDistance;
+    uint32_t MatchNumThresh;
+    int32_t MatchThreshold; /* GlobalMatchThreshold */
+    double RegularizeThresh, ReshapeQAbsolute, ReshapeQRelative, LocationUncertainty;
+    double DoReScaling;
+    double config_fps;
+    int32_t kl_capacity; /* KEYLINE_MAX of the build (<= 50000) */
+} rb_params;
+
+/* NavData subset + per-frame scalars REBVO hands to the output callback (rebvo.h:292-351) */
+typedef struct rb_nav {
+    double t, dt;
+    double Rot[9], RotLie[3], Vel[3];
+    double Pose[9], PoseLie[3], Pos[3];
+    double V[3], W[3]; /* raw minimiser output (translation, rotation) */
+    double K, Kp, RKp, s_rho_p;
+    double score;   /* Minimizer_RV return value */
+    int32_t kn;     /* keylines in this edge map */
+    int32_t matches; /* directed_matching() return */
+    int32_t fwd_matches;
+    int32_t estimation_ok;
+    float thresh;   /* detector threshold used for this frame */
+    float retuned_thresh;
+} rb_nav;
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int rb_ctx_create(rb_ctx **out, int device, const rb_camera *cam, double sigma0, double ksigma,
+                  int kl_capacity);
+void rb_ctx_destroy(rb_ctx *c);
+const char *rb_last_error(const rb_ctx *c);
+int rb_ctx_sync(rb_ctx *c);
+/* iigauss::iigauss box plan (iigauss.cpp:43-81): out_d[6] = box widths filter0[3], filter1[3];
+ * out_sigma_r[2] = achieved sigmas */
+int rb_ctx_box_plan(const rb_ctx *c, int *out_d, double *out_sigma_r);
+/* kernels launched on this context so far (bench.py's gpu_launches) */
+int64_t rb_ctx_launch_count(const rb_ctx *c);
+
+/* ---- edge map (ring slot) ---------------------------------------------------------------------- */
+int rb_map_create(rb_ctx *c, rb_map **out);
+void rb_map_destroy(rb_map *m);
+
+/* Image<float>::ConvertRGB2BW (image.h:197-203) after the H2D copy of the RGB24 frame */
+int rb_map_upload_rgb(rb_map *m, const uint8_t *rgb);
+int rb_map_upload_gray(rb_map *m, const float *gray);
+/* sspace::build (sspace.cpp:52-60): bit-exact float32 integral-image DoG */
+int rb_map_dog_build(rb_map *m);
+/* which: 0 Img(0), 1 Img(1), 2 ImgDOG, 3 ImgDx, 4 ImgDy, 5 gray.  Img(1), dx, dy are materialised on
+ * demand (the detector computes them on the fly). */
+int rb_map_get_plane(rb_map *m, int which, float *out);
+/* edge_finder::detect (edge_finder.cpp:342-365): UpdateThresh + build_mask + join_edges.
+ * tresh / l_kl_num are the caller-held feedback state of FirstThr (rebvo_first_t.cpp:92-94). */
+int rb_map_detect(rb_map *m, const rb_detect_params *p, double *tresh, int *l_kl_num, int *kn_out);
+/* edge_finder::reEstimateThresh (edge_finder.cpp:373-405) */
+int rb_map_reestimate_thresh(rb_map *m, int knum, int nbins, float *out_thresh);
+int rb_map_knum(rb_map *m, int *kn);
+/* AoS mirror for host consumers (callback / net packer): kn records of 168 bytes */
+int rb_map_sync_host_keylines(rb_map *m, rb_keyline *dst, int capacity, int *kn);
+/* test / checkpoint path: load an edge map (keylines + mask) produced elsewhere */
+int rb_map_load_keylines(rb_map *m, const rb_keyline *src, int kn, const int32_t *mask);
+int rb_map_get_mask(rb_map *m, int32_t *out);
+
+/* edge_tracker::EstimateQuantile (edge_tracker.cpp:1148-1186) */
+int rb_map_quantile(rb_map *m, double s_rho_min, double s_rho_max, double percentile, int nbins,
+                    double *out);
+/* global_tracker::build_field (global_tracker.cpp:61-105) on this map's own keylines */
+int rb_map_build_field(rb_map *m, int radius, float min_mod);
+/* out: w*h pairs {dist, ikl} as the reference's gt_field_data (global_tracker.h:33-36) */
+int rb_map_get_field(rb_map *m, int32_t *out);
+/* one global_tracker::TryVelRot<double,ReWeight,ProcJF,false> evaluation (global_tracker.cpp:285-543).
+ * fmap holds the field (new map), old is the map being moved.  res_in / res_out: K0 doubles (may be
+ * NULL when !reweight / not wanted). */
+int rb_try_vel_rot(rb_map *fmap, rb_map *old, const double X[6], int reweight, int procjf,
+                   double match_thresh, double s_rho_min, uint32_t match_num_thresh, double k_huber,
+                   const double *res_in, double *res_out, double JtJ[36], double JtF[6], double *score);
+/* global_tracker::Minimizer_RV<double,false> (global_tracker.cpp:578-819), device-resident LM loop */
+int rb_minimizer_rv(rb_map *fmap, rb_map *old, double V[3], double W[3], double RVel[9], double RW0[9],
+                    double match_thresh, int iter_max, int init_type, double reweight_distance,
+                    double *rel_error, double *rel_error_score, double max_s_rho,
+                    uint32_t match_num_thresh, int init_iter, double W_X[36], double *score);
+/* edge_tracker::FordwardMatch (edge_tracker.cpp:380-436): old -> new along m_id_f */
+int rb_forward_match(rb_map *old, rb_map *neu, int *nmatch);
+/* edge_tracker::rotate_keylines (edge_tracker.cpp:42-76) */
+int rb_map_rotate_keylines(rb_map *m, const double R[9]);
+/* edge_tracker::directed_matching (edge_tracker.cpp:302-374) */
+int rb_directed_matching(rb_map *neu, rb_map *old, const double Vel[3], const double RVel[9],
+                         const double BackRot[9], double min_thr_mod, double min_thr_ang,
+                         double max_radius, double loc_uncertainty, int *nmatch);
+/* edge_tracker::Regularize_1_iter (edge_tracker.cpp:87-148) */
+int rb_map_regularize(rb_map *m, double thresh, int *r_num);
+/* edge_tracker::UpdateInverseDepthKalman -> ...ARLU (edge_tracker.cpp:695-724, 954-1055) */
+int rb_map_ekf_update(rb_map *m, const double vel[3], double reshape_q_abs, double loc_uncertainty);
+/* edge_tracker::EstimateReScalingOpt (edge_tracker.cpp:1104-1140) */
+int rb_map_rescale_opt(rb_map *m, double s_rho_min, uint32_t match_num_min, int re_escale,
+                       double *Kp, double *RKp);
+/* global_tracker's FrameCount (global_tracker.cpp:356,816) of this slot */
+int rb_map_set_frame_count(rb_map *m, uint32_t fc);
+
+/* ---- whole per-frame flow ------------------------------------------------------------------------
+ * REBVO::FirstThr detector stage + REBVO::SecondThread tracker/mapper stage (ImuMode=0) with all
+ * state (edge-map ring, threshold feedback, V/W/P_V, pose) resident on the device. */
+int rb_pipeline_create(rb_pipeline **out, int device, const rb_params *p, int max_batch);
+void rb_pipeline_destroy(rb_pipeline *pl);
+const char *rb_pipeline_last_error(const rb_pipeline *pl);
+/* Push n frames (host RGB24, n*w*h*3 bytes; timestamps ts[n]).  Detection of the n frames runs
+ * batched, tracking runs frame by frame in order; nav_out[n] receives one record per frame (the first
+ * frame ever pushed only initialises the ring: estimation_ok = 0).  Synchronous. */
+int rb_pipeline_push(rb_pipeline *pl, const uint8_t *rgb, const double *ts, int n, rb_nav *nav_out);
+/* same with frames already resident in device memory (device pointer) */
+int rb_pipeline_push_dev(rb_pipeline *pl, const uint8_t *rgb_dev, const double *ts, int n,
+                         rb_nav *nav_out);
+/* REBVO::Reset (rebvo_second_t.cpp:609-620) */
+int rb_pipeline_reset(rb_pipeline *pl);
+/* newest / previous edge map of the ring (valid until the next push) */
+rb_map *rb_pipeline_map(rb_pipeline *pl, int age);
+int64_t rb_pipeline_launch_count(const rb_pipeline *pl);
+/* CUDA-event time (ms) of the last push split by stage: [0] h2d+gray, [1] DoG, [2] detect,
+ * [3] tracker (field + minimiser), [4] mapper, [5] total */
+int rb_pipeline_stage_ms(const rb_pipeline *pl, float out[6]);
+/* opaque stream handle (cudaStream_t) the pipeline launches on, for CUDA-event timing by the caller */
+void *rb_pipeline_stream(rb_pipeline *pl);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REBVO_B200_H */

@@ -1,0 +1,282 @@
+// dog.cu -- scale space: bit-exact float32 integral-image box blurs, DoG and gradient.
+//
+// Replaces sspace::build (src/mtracklib/sspace.cpp:52-85) = 2 x iigauss::smooth (iigauss.cpp:91-101),
+// each 3 x { iimage::load (iimage.cpp:53-71) ; iimage::average (iimage.cpp:86-128) }.
+//
+// Parity constraint: the reference's integral images are float32 and exceed
+// 2^24, so every add must happen in the reference's order: each row left->right, then each column
+// top->bottom.  The kernels therefore keep one sequential chain per row / per column and get their
+// parallelism from rows x columns x images of a batch; the library is compiled with -fmad=false so no
+// mul+add is ever contracted.
+//
+// Pass structure per box stage (B images x 2 filters in one launch):
+//   k_rowscan<AVG> : S(x,y)  = sum_{i<=x} avg(I_prev)(i,y)   warp per 32-row band, smem-transposed tiles
+//   k_colscan      : I(x,y)  = sum_{j<=y} S(x,j)              thread per 4 columns, float4 streams
+// and a final k_blur_dog that evaluates the last box of both filters, Img(0) and the DoG.
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------------
+// iimage::average for one pixel (iimage.cpp:86-128).  The nine regions of the reference collapse to:
+// taps A=I(xr,yb) B=I(xl,yb) C=I(xr,yt) D=I(xl,yt) with xr=min(x+d2,w-1), yb=min(y+d2,h-1), xl=x-d2-1,
+// yt=y-d2-1; a tap whose xl / yt is negative is absent; the subtraction order is A-B-C+D except in the
+// bottom band (y >= h-d2) where the reference writes A-C-B+D; the factor is a=1.0/(d*d) in the centre
+// region and the per-pixel reciprocal box area of iimage::build_average (iimage.cpp:134-179) elsewhere.
+__device__ __forceinline__ float box_avg(const float *__restrict__ I, int x, int y, int w, int h, int d,
+                                         int d2, float a) {
+    const bool left = x < d2 + 1, right = x >= w - d2;
+    const bool top = y < d2 + 1, bottom = y >= h - d2;
+    const int xr = right ? w - 1 : x + d2;
+    const int yb = bottom ? h - 1 : y + d2;
+    const int xl = x - d2 - 1, yt = y - d2 - 1;
+    float r = I[yb * w + xr];
+    if (!(left | right | top | bottom)) {
+        r = r - I[yb * w + xl];
+        r = r - I[yt * w + xr];
+        r = r + I[yt * w + xl];
+        return r * a;
+    }
+    if (bottom) {
+        if (!top) r = r - I[yt * w + xr];           // A - C
+        if (!left) r = r - I[yb * w + xl];          //   - B
+        if (!top && !left) r = r + I[yt * w + xl];  //   + D
+    } else {
+        if (!left) r = r - I[yb * w + xl];          // A - B
+        if (!top) r = r - I[yt * w + xr];           //   - C
+        if (!top && !left) r = r + I[yt * w + xl];  //   + D
+    }
+    // build_average: div = (float)(1.0 / (double)(float)(cx*cy)), cx/cy = clipped box extents
+    const int cx = left ? x + d2 + 1 : (right ? w - x + d2 : d);
+    const int cy = top ? y + d2 + 1 : (bottom ? h - y + d2 : d);
+    const float area = (float)(cx * cy);
+    const float div = (float)(1.0 / (double)area);
+    return r * div;
+}
+
+// Image<float>::ConvertRGB2BW (image.h:197-203): b+g+r as float, 4 pixels per thread
+__global__ void __launch_bounds__(256) k_rgb2gray(const uint32_t *__restrict__ rgb,
+                                                  float4 *__restrict__ gray, size_t n4) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    uint32_t a = rgb[3 * i], b = rgb[3 * i + 1], c = rgb[3 * i + 2];
+    // bytes: a = p0.0 p0.1 p0.2 p1.0 | b = p1.1 p1.2 p2.0 p2.1 | c = p2.2 p3.0 p3.1 p3.2
+    float4 o;
+    o.x = (float)((a & 0xff) + ((a >> 8) & 0xff) + ((a >> 16) & 0xff));
+    o.y = (float)((a >> 24) + (b & 0xff) + ((b >> 8) & 0xff));
+    o.z = (float)(((b >> 16) & 0xff) + (b >> 24) + (c & 0xff));
+    o.w = (float)(((c >> 8) & 0xff) + ((c >> 16) & 0xff) + (c >> 24));
+    gray[i] = o;
+}
+
+// Row pass: warp per band of 32 rows of one image.  Tiles of 32x32 are produced coalesced (optionally
+// through box_avg of the previous integral image), transposed through shared memory so that each lane
+// owns one row, scanned sequentially (the reference's add order), and stored coalesced.
+template <bool AVG>
+__global__ void __launch_bounds__(128) k_rowscan(const float *__restrict__ in, float *__restrict__ out,
+                                                 int w, int h, int nimg, int in_mod, int nper, int d_f0,
+                                                 int d_f1) {
+    __shared__ float tile[4][32][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * 4 + warp;
+    const int bands = (h + 31) >> 5;
+    const int img = gw / bands, band = gw - img * bands;
+    if (img >= nimg) return;
+    const size_t N = (size_t)w * h;
+    const float *__restrict__ I = in + (size_t)(img % in_mod) * N;
+    float *__restrict__ O = out + (size_t)img * N;
+    const int d = (img / nper) ? d_f1 : d_f0;
+    const int d2 = d / 2;
+    const float a = (float)(1.0 / (double)(d * d));
+    const int y0 = band * 32;
+    float v[32];
+    float carry = 0.f;
+
+#define LOAD_TILE(X0)                                                           \
+    {                                                                           \
+        const int x = (X0) + lane;                                              \
+        _Pragma("unroll") for (int r = 0; r < 32; r++) {                        \
+            const int y = y0 + r;                                               \
+            float t = 0.f;                                                      \
+            if (y < h && x < w) t = AVG ? box_avg(I, x, y, w, h, d, d2, a) : I[(size_t)y * w + x]; \
+            v[r] = t;                                                           \
+        }                                                                       \
+    }
+    LOAD_TILE(0);
+    for (int x0 = 0; x0 < w; x0 += 32) {
+#pragma unroll
+        for (int r = 0; r < 32; r++) tile[warp][r][lane] = v[r];
+        __syncwarp();
+        if (x0 + 32 < w) LOAD_TILE(x0 + 32);  // next tile's loads overlap the dependent add chain
+        float *row = tile[warp][lane];
+#pragma unroll
+        for (int cidx = 0; cidx < 32; cidx++) {
+            carry = carry + row[cidx];  // I(x,y) = I(x-1,y) + in(x,y), iimage.cpp:56-60
+            row[cidx] = carry;
+        }
+        __syncwarp();
+        const int x = x0 + lane;
+        if (x < w) {
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                const int y = y0 + r;
+                if (y < h) O[(size_t)y * w + x] = tile[warp][r][lane];
+            }
+        }
+        __syncwarp();
+    }
+#undef LOAD_TILE
+}
+
+// Column pass: thread per 4 adjacent columns; I(x,y) += I(x,y-1) top->bottom (iimage.cpp:62-66)
+__global__ void __launch_bounds__(64) k_colscan(const float4 *__restrict__ in, float4 *__restrict__ out,
+                                                int w4, int h, int nimg) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int img = idx / w4, cx = idx - img * w4;
+    if (img >= nimg) return;
+    const float4 *__restrict__ I = in + (size_t)img * w4 * h + cx;
+    float4 *__restrict__ O = out + (size_t)img * w4 * h + cx;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int U = 16;
+    for (int y = 0; y < h; y += U) {
+        float4 v[U];
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            if (y + k < h) v[k] = __ldcs(&I[(size_t)(y + k) * w4]);
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            if (y + k < h) {
+                acc.x = v[k].x + acc.x;
+                acc.y = v[k].y + acc.y;
+                acc.z = v[k].z + acc.z;
+                acc.w = v[k].w + acc.w;
+                O[(size_t)(y + k) * w4] = acc;
+            }
+    }
+}
+
+// Last box of both filters + sspace::build_dog (sspace.cpp:63-70): img0, dog = img1 - img0
+__global__ void __launch_bounds__(256) k_blur_dog(const float *__restrict__ I, float *__restrict__ img0,
+                                                  float *__restrict__ dog, float *__restrict__ img1_opt,
+                                                  int w, int h, int B, int d0, int d1) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int b = blockIdx.z;
+    if (x >= w) return;
+    const size_t N = (size_t)w * h;
+    const float a0 = (float)(1.0 / (double)(d0 * d0)), a1 = (float)(1.0 / (double)(d1 * d1));
+    const float v0 = box_avg(I + (size_t)b * N, x, y, w, h, d0, d0 / 2, a0);
+    const float v1 = box_avg(I + (size_t)(B + b) * N, x, y, w, h, d1, d1 / 2, a1);
+    const size_t o = (size_t)b * N + (size_t)y * w + x;
+    img0[o] = v0;
+    dog[o] = v1 - v0;
+    if (img1_opt) img1_opt[(size_t)y * w + x] = v1;
+}
+
+// sspace::calc_gradient (sspace.cpp:75-85), materialised only for the debug accessor; borders = 0
+__global__ void k_gradient(const float *__restrict__ img0, float *__restrict__ dx, float *__restrict__ dy,
+                           int w, int h) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= w) return;
+    float gx = 0.f, gy = 0.f;
+    if (x >= 1 && x < w - 1 && y >= 1 && y < h - 1) {
+        gx = img0[y * w + x + 1] - img0[y * w + x - 1];
+        gy = img0[(y + 1) * w + x] - img0[(y - 1) * w + x];
+    }
+    dx[y * w + x] = gx;
+    dy[y * w + x] = gy;
+}
+
+// ---------------------------------------------------------------------------------------------------
+int rb_dogws_alloc(rb_ctx *c, DogWS *ws, int B) {
+    memset(ws, 0, sizeof(*ws));
+    ws->B = B;
+    const size_t N = c->N;
+    RB_CUDA(cudaMalloc(&ws->rgb, (size_t)B * 3 * N));
+    RB_CUDA(cudaMalloc(&ws->gray, (size_t)B * N * 4));
+    RB_CUDA(cudaMalloc(&ws->S, (size_t)2 * B * N * 4));
+    RB_CUDA(cudaMalloc(&ws->I0, (size_t)B * N * 4));
+    RB_CUDA(cudaMalloc(&ws->I, (size_t)2 * B * N * 4));
+    RB_CUDA(cudaMalloc(&ws->img0, (size_t)B * N * 4));
+    RB_CUDA(cudaMalloc(&ws->dog, (size_t)B * N * 4));
+    RB_CUDA(cudaMalloc(&ws->aux, (size_t)3 * N * 4));
+    return RB_OK;
+}
+
+void rb_dogws_free(DogWS *ws) {
+    cudaFree(ws->rgb);
+    cudaFree(ws->gray);
+    cudaFree(ws->S);
+    cudaFree(ws->I0);
+    cudaFree(ws->I);
+    cudaFree(ws->img0);
+    cudaFree(ws->dog);
+    cudaFree(ws->aux);
+    memset(ws, 0, sizeof(*ws));
+}
+
+int rb_dog_gray(rb_ctx *c, DogWS *ws, int nimg) {
+    const size_t n4 = (size_t)nimg * c->N / 4;
+    k_rgb2gray<<<(unsigned)((n4 + 255) / 256), 256, 0, c->stream>>>((const uint32_t *)ws->rgb,
+                                                                   (float4 *)ws->gray, n4);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+static int rowscan(rb_ctx *c, bool avg, const float *in, float *out, int nimg, int in_mod, int nper,
+                   int d0, int d1) {
+    const int bands = (c->h + 31) / 32;
+    const int warps = nimg * bands;
+    const int blocks = rb_div_up(warps, 4);
+    if (avg)
+        k_rowscan<true><<<blocks, 128, 0, c->stream>>>(in, out, c->w, c->h, nimg, in_mod, nper, d0, d1);
+    else
+        k_rowscan<false><<<blocks, 128, 0, c->stream>>>(in, out, c->w, c->h, nimg, in_mod, nper, d0, d1);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+static int colscan(rb_ctx *c, const float *in, float *out, int nimg) {
+    const int w4 = c->w / 4;
+    const int threads = nimg * w4;
+    k_colscan<<<rb_div_up(threads, 64), 64, 0, c->stream>>>((const float4 *)in, (float4 *)out, w4, c->h,
+                                                           nimg);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+// sspace::build for nimg images of the workspace (gray already present)
+int rb_dog_build_batch(rb_ctx *c, DogWS *ws, int nimg) {
+    if (nimg < 1 || nimg > ws->B) return RB_ERR_ARG;
+    const BoxPlan &p = c->plan;
+    int r;
+    // iimage::load(in): identical for both filters -> computed once
+    if ((r = rowscan(c, false, ws->gray, ws->S, nimg, nimg, nimg, 1, 1))) return r;
+    if ((r = colscan(c, ws->S, ws->I0, nimg))) return r;
+    // box 0 of both filters reads the shared integral; image index = filter * nimg + b
+    if ((r = rowscan(c, true, ws->I0, ws->S, 2 * nimg, nimg, nimg, p.d[0][0], p.d[1][0]))) return r;
+    if ((r = colscan(c, ws->S, ws->I, 2 * nimg))) return r;
+    // box 1
+    if ((r = rowscan(c, true, ws->I, ws->S, 2 * nimg, 2 * nimg, nimg, p.d[0][1], p.d[1][1]))) return r;
+    if ((r = colscan(c, ws->S, ws->I, 2 * nimg))) return r;
+    // box 2 + DoG.  Filter f of image b lives at I[(f*nimg + b)*N]
+    dim3 grid(rb_div_up(c->w, 256), c->h, nimg);
+    k_blur_dog<<<grid, 256, 0, c->stream>>>(ws->I, ws->img0, ws->dog, nullptr, c->w, c->h, nimg,
+                                            p.d[0][2], p.d[1][2]);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+// Img(1), dx, dy of image `img` into ws->aux (debug accessor; needs ws->I from the last build with
+// the same nimg = ws_last_nimg, passed through B of the call: only valid for nimg == 1 workspaces)
+int rb_dog_aux_planes(rb_ctx *c, DogWS *ws, int img) {
+    if (ws->B != 1 || img != 0) return RB_ERR_ARG;
+    const BoxPlan &p = c->plan;
+    dim3 grid(rb_div_up(c->w, 256), c->h, 1);
+    k_blur_dog<<<grid, 256, 0, c->stream>>>(ws->I, ws->img0, ws->dog, ws->aux, c->w, c->h, 1, p.d[0][2],
+                                            p.d[1][2]);
+    RB_LAUNCH_CHECK();
+    k_gradient<<<grid, 256, 0, c->stream>>>(ws->img0, ws->aux + c->N, ws->aux + 2 * (size_t)c->N, c->w,
+                                            c->h);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}

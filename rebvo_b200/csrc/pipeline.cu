@@ -1,0 +1,383 @@
+// pipeline.cu -- the per-frame flow of REBVO with every piece of state resident on the device:
+//   detector stage  = REBVO::FirstThr   (src/rebvo/rebvo_first_t.cpp:259-272)
+//   tracker/mapper  = REBVO::SecondThread, ImuMode=0 branch (src/rebvo/rebvo_second_t.cpp:128-629)
+// The host only enqueues kernels: threshold feedback, LM driver, NaN / match-count decisions, pose
+// integration and the NavData record are all computed by 1-thread kernels from device state, so a batch of
+// frames costs one H2D copy, one stream of launches and one D2H copy of the nav records.
+#include <math.h>
+#include <new>
+
+#include "common.cuh"
+#include "lm.cuh"
+#include "tracker.cuh"
+
+int rb_map_alloc(rb_ctx *c, rb_map **out, bool with_ws);
+
+// SecondThread locals (rebvo_second_t.cpp:57-66, 167-169)
+struct FrameState {
+    double V[3], W[3], Pos[3];
+    double R[9], Pose[9];
+    double P_V[9], P_W[9];
+    double Kp, K, P_Kp;
+    double VW[6];       // minimiser priors (V, W of the previous frame)
+    double R0[9];       // forward rotation exp(W)
+    DMatchArgs dm;
+    int do_match, do_map, est_ok;
+    int klm_num;
+    int n_frame;
+    int pad;
+};
+
+struct rb_pipeline {
+    rb_ctx *c;
+    rb_params p;
+    int max_batch;
+    DogWS ws;
+    rb_map *maps[2];
+    DetChain *chain;      // device
+    FrameState *fs;       // device
+    rb_nav *nav_dev;
+    rb_nav *nav_pin;
+    uint8_t *rgb_pin;     // optional pinned staging (unused when the caller's buffer is pinned)
+    long long n_pushed;   // frames pushed so far
+    double t_prev;
+    cudaEvent_t ev[4];
+    float stage_ms[6];
+};
+
+static void set_eye(double *M, double v) {
+    for (int i = 0; i < 9; i++) M[i] = 0;
+    M[0] = M[4] = M[8] = v;
+}
+
+__device__ void d_eye(double *M, double v) {
+    for (int i = 0; i < 9; i++) M[i] = 0;
+    M[0] = M[4] = M[8] = v;
+}
+
+// start of the SecondThread loop body (:167-169) + minimiser priors
+__global__ void k_frame_pre(FrameState *fs) {
+    d_eye(fs->P_V, 1e50);
+    d_eye(fs->P_W, 1e50);
+    d_eye(fs->R, 1);
+    for (int i = 0; i < 3; i++) {
+        fs->VW[i] = fs->V[i];
+        fs->VW[3 + i] = fs->W[i];
+    }
+    fs->est_ok = 1;
+    fs->do_match = 0;
+    fs->do_map = 0;
+    fs->klm_num = 0;
+}
+
+// after Minimizer_RV (:346-398): outputs, R0 = exp(W), R.T() = R0*R.T(), NaN guard, directed-matching args
+__global__ void k_frame_post_min(FrameState *fs, const TrackState *ts) {
+    const LMState &lm = ts->lm;
+    for (int i = 0; i < 3; i++) {
+        fs->V[i] = lm.Vel[i];
+        fs->W[i] = lm.W0[i];
+    }
+    for (int i = 0; i < 9; i++) {
+        fs->P_V[i] = lm.RVel[i];
+        fs->P_W[i] = lm.RW0[i];
+    }
+    so3_exp(fs->W, fs->R0);                 // SO3<> R0(W)
+    double Rt[9], RtT[9];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) RtT[r * 3 + c] = fs->R[c * 3 + r];
+    mat3_mul(fs->R0, RtT, Rt);              // R.T() = R0*R.T()
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) fs->R[r * 3 + c] = Rt[c * 3 + r];
+    bool nan = false;
+    for (int i = 0; i < 3; i++) nan = nan || isnan(fs->V[i]) || isnan(fs->W[i]);
+    if (nan) {                              // :387-398
+        d_eye(fs->P_V, 1e50);
+        for (int i = 0; i < 3; i++) fs->V[i] = 0;
+        fs->Kp = 1;
+        fs->P_Kp = 1e50;
+        fs->est_ok = 0;
+        fs->do_match = 0;
+    } else {
+        fs->do_match = 1;
+        // directed_matching prologue (edge_tracker.cpp:324-325): Vel=BackRot*Vel; RVel=BackRot*RVel*BackRot.T()
+        mat3_vec(fs->R, fs->V, fs->dm.Vel);
+        double t[9];
+        mat3_mul(fs->R, fs->P_V, t);
+        mat3_mul_bt(t, fs->R, fs->dm.RVel);
+        for (int i = 0; i < 9; i++) fs->dm.BackRot[i] = fs->R[i];
+    }
+}
+
+// after directed_matching (:410-423)
+__global__ void k_frame_post_match(FrameState *fs, const MapState *nst, int match_threshold) {
+    if (!fs->do_match) {
+        fs->do_map = 0;
+        return;
+    }
+    fs->klm_num = nst->nmatch;
+    if (fs->klm_num < match_threshold) {
+        d_eye(fs->P_V, 1e50);
+        for (int i = 0; i < 3; i++) fs->V[i] = 0;
+        fs->Kp = 1;
+        fs->P_Kp = 10;
+        fs->est_ok = 0;
+        fs->do_map = 0;
+    } else {
+        fs->do_map = 1;
+    }
+}
+
+// pose integration + NavData (:545-585)
+__global__ void k_frame_finish(FrameState *fs, const MapState *nst, const MapState *ost, const TrackState *ts,
+                               rb_nav *nav, double t, double dt_frame) {
+    if (fs->do_map) {
+        fs->Kp = nst->Kp;      // Kp=EstimateReScalingOpt(P_Kp,...)
+        fs->P_Kp = nst->RKp;
+    }
+    const double K = fs->K;
+    double Pose[9];
+    mat3_mul(fs->Pose, fs->R, Pose);          // Pose=Pose*R
+    for (int i = 0; i < 9; i++) fs->Pose[i] = Pose[i];
+    double nP[9], pv[3];
+    for (int i = 0; i < 9; i++) nP[i] = -Pose[i];
+    mat3_vec(nP, fs->V, pv);                  // Pos+=-Pose*V*K
+    for (int i = 0; i < 3; i++) fs->Pos[i] = fs->Pos[i] + pv[i] * K;
+    rb_nav o;
+    o.t = t;
+    o.dt = dt_frame;
+    for (int i = 0; i < 9; i++) {
+        o.Rot[i] = fs->R[i];
+        o.Pose[i] = fs->Pose[i];
+    }
+    so3_ln_of_matrix(fs->R, o.RotLie);
+    so3_ln_of_matrix(fs->Pose, o.PoseLie);
+    for (int i = 0; i < 3; i++) {
+        o.Vel[i] = (-fs->V[i]) * K / dt_frame;
+        o.Pos[i] = fs->Pos[i];
+        o.V[i] = fs->V[i];
+        o.W[i] = fs->W[i];
+    }
+    o.K = K;
+    o.Kp = fs->Kp;
+    o.RKp = fs->P_Kp;
+    o.s_rho_p = ost->s_rho_q;
+    o.score = ts->lm.score;
+    o.kn = nst->kn;
+    o.matches = fs->klm_num;
+    o.fwd_matches = nst->fwd_match;
+    o.estimation_ok = fs->est_ok;
+    o.thresh = nst->thresh_used;
+    o.retuned_thresh = nst->retuned;
+    *nav = o;
+    for (int i = 0; i < 9; i++) fs->P_V[i] = fs->P_V[i] / (dt_frame * dt_frame);   // P_V/=dt_frame*dt_frame
+    fs->n_frame++;
+}
+
+// record for the very first frame (it only initialises the ring, :109-121)
+__global__ void k_frame_first(const FrameState *fs, const MapState *nst, rb_nav *nav, double t) {
+    rb_nav o;
+    memset(&o, 0, sizeof(o));
+    o.t = t;
+    for (int i = 0; i < 9; i++) {
+        o.Rot[i] = (i % 4 == 0) ? 1 : 0;
+        o.Pose[i] = fs->Pose[i];
+    }
+    o.K = fs->K;
+    o.Kp = fs->Kp;
+    o.RKp = fs->P_Kp;
+    o.kn = nst->kn;
+    o.estimation_ok = 0;
+    o.thresh = nst->thresh_used;
+    o.retuned_thresh = nst->retuned;
+    *nav = o;
+}
+
+static int pl_reset_state(rb_pipeline *pl) {
+    rb_ctx *c = pl->c;
+    FrameState h;
+    memset(&h, 0, sizeof(h));
+    set_eye(h.R, 1);
+    set_eye(h.Pose, 1);
+    set_eye(h.P_V, 1e50);
+    set_eye(h.P_W, 1e-10);
+    h.Kp = 1;
+    h.K = 1;
+    h.P_Kp = 5e-6;
+    RB_CUDA(cudaMemcpy(pl->fs, &h, sizeof(h), cudaMemcpyHostToDevice));
+    DetChain ch;
+    ch.tresh = pl->p.DetectorThresh;
+    ch.l_kl_num = 0;
+    ch.pad = 0;
+    RB_CUDA(cudaMemcpy(pl->chain, &ch, sizeof(ch), cudaMemcpyHostToDevice));
+    pl->n_pushed = 0;
+    pl->t_prev = 0;
+    return RB_OK;
+}
+
+extern "C" int rb_pipeline_create(rb_pipeline **out, int device, const rb_params *p, int max_batch) {
+    if (!out || !p || max_batch < 1) return RB_ERR_ARG;
+    *out = nullptr;
+    rb_ctx *c = nullptr;
+    int kcap = p->kl_capacity > 0 ? p->kl_capacity : 50000;
+    int r = rb_ctx_create(&c, device, &p->cam, p->Sigma0, p->KSigma, kcap);
+    if (r) {
+        if (c) rb_ctx_destroy(c);
+        return r;
+    }
+    rb_pipeline *pl = new (std::nothrow) rb_pipeline;
+    if (!pl) {
+        rb_ctx_destroy(c);
+        return RB_ERR_ARG;
+    }
+    memset(pl, 0, sizeof(*pl));
+    pl->c = c;
+    pl->p = *p;
+    pl->max_batch = max_batch;
+    *out = pl;
+    if ((r = rb_dogws_alloc(c, &pl->ws, max_batch))) return r;
+    for (int i = 0; i < 2; i++)
+        if ((r = rb_map_alloc(c, &pl->maps[i], false))) return r;
+    RB_CUDA(cudaMalloc(&pl->chain, sizeof(DetChain)));
+    RB_CUDA(cudaMalloc(&pl->fs, sizeof(FrameState)));
+    RB_CUDA(cudaMalloc(&pl->nav_dev, sizeof(rb_nav) * max_batch));
+    RB_CUDA(cudaMallocHost(&pl->nav_pin, sizeof(rb_nav) * max_batch));
+    for (int i = 0; i < 4; i++) RB_CUDA(cudaEventCreate(&pl->ev[i]));
+    if ((r = pl_reset_state(pl))) return r;
+    RB_CUDA(cudaStreamSynchronize(c->stream));
+    return RB_OK;
+}
+
+extern "C" void rb_pipeline_destroy(rb_pipeline *pl) {
+    if (!pl) return;
+    rb_ctx *c = pl->c;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 2; i++)
+        if (pl->maps[i]) rb_map_destroy(pl->maps[i]);
+    rb_dogws_free(&pl->ws);
+    cudaFree(pl->chain);
+    cudaFree(pl->fs);
+    cudaFree(pl->nav_dev);
+    if (pl->nav_pin) cudaFreeHost(pl->nav_pin);
+    for (int i = 0; i < 4; i++)
+        if (pl->ev[i]) cudaEventDestroy(pl->ev[i]);
+    rb_ctx_destroy(c);
+    delete pl;
+}
+
+extern "C" const char *rb_pipeline_last_error(const rb_pipeline *pl) { return pl ? pl->c->err : "null pipeline"; }
+extern "C" int64_t rb_pipeline_launch_count(const rb_pipeline *pl) { return pl->c->launches; }
+extern "C" void *rb_pipeline_stream(rb_pipeline *pl) { return (void *)pl->c->stream; }
+extern "C" rb_map *rb_pipeline_map(rb_pipeline *pl, int age) {
+    if (age < 0 || age > 1 || pl->n_pushed <= age) return nullptr;
+    return pl->maps[(pl->n_pushed - 1 - age) & 1];
+}
+extern "C" int rb_pipeline_stage_ms(const rb_pipeline *pl, float out[6]) {
+    memcpy(out, pl->stage_ms, sizeof(float) * 6);
+    return RB_OK;
+}
+
+extern "C" int rb_pipeline_reset(rb_pipeline *pl) {
+    rb_ctx *c = pl->c;
+    RB_CUDA(cudaStreamSynchronize(c->stream));
+    return pl_reset_state(pl);
+}
+
+// one frame of the tracker/mapper stage: new = maps[idx&1] (already detected), old = the other map
+static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, long long n, double t, double dt_frame,
+                       rb_nav *nav_slot) {
+    rb_ctx *c = pl->c;
+    const rb_params &p = pl->p;
+    int r;
+    k_frame_pre<<<1, 1, 0, c->stream>>>(pl->fs);
+    RB_LAUNCH_CHECK();
+    // :172  s_rho_q = old_buf.ef->EstimateQuantile(RHO_MIN,RHO_MAX,QCutOffQuantile,QCutOffNumBins)
+    if ((r = rb_quantile_enqueue(c, old, RB_RHO_MIN, RB_RHO_MAX, p.QCutOffQuantile, p.QCutOffNumBins))) return r;
+    // :177  new_buf.gt->build_field(*new_buf.ef,SearchRange,new_buf.ef->getThresh())
+    if ((r = rb_build_field_enqueue(c, neu, p.SearchRange, 0.f, true))) return r;
+    // :346  Minimizer_RV<double>(V,W,P_V,P_W,*old_buf.ef,...)
+    rb_minimizer_args a;
+    a.match_thresh = p.TrackerMatchThresh;
+    a.iter_max = p.TrackerIterNum;
+    a.init_type = p.TrackerInitType;
+    a.init_iter = p.TrackerInitIterNum;
+    a.reweight_distance = p.ReweigthDistance;
+    a.match_num_thresh = p.MatchNumThresh;
+    // FrameCount of the reference's ring slot serving frame n (8 slots, slot = (n+1)%8): (n-1)/8
+    const unsigned int frame_count = (unsigned int)((n - 1) / 8);
+    if ((r = rb_minimizer_enqueue(c, neu, old, pl->fs->VW, &a, 0.0, true, frame_count, false))) return r;
+    k_frame_post_min<<<1, 1, 0, c->stream>>>(pl->fs, neu->ts);
+    RB_LAUNCH_CHECK();
+    // :354  FordwardMatch ; :369 rotate_keylines(R0)
+    if ((r = rb_forward_match_enqueue(c, old, neu))) return r;
+    if ((r = rb_rotate_enqueue(c, old, pl->fs->R0))) return r;
+    // :410  directed_matching(V,P_V,R,old_buf.ef,...)
+    if ((r = rb_directed_matching_enqueue(c, neu, old, &pl->fs->dm, p.MatchThreshModule, p.MatchThreshAngle,
+                                          (double)p.SearchRange, p.LocationUncertaintyMatch, &pl->fs->do_match)))
+        return r;
+    k_frame_post_match<<<1, 1, 0, c->stream>>>(pl->fs, neu->st, p.MatchThreshold);
+    RB_LAUNCH_CHECK();
+    // :452-487  Regularize_1_iter, UpdateInverseDepthKalman, EstimateReScalingOpt
+    if ((r = rb_regularize_enqueue(c, neu, p.RegularizeThresh, &pl->fs->do_map))) return r;
+    if ((r = rb_ekf_enqueue(c, neu, pl->fs->V, p.ReshapeQAbsolute, p.LocationUncertainty, &pl->fs->do_map))) return r;
+    if ((r = rb_rescale_enqueue(c, neu, RB_RHO_MAX, 1, p.DoReScaling > 0 ? 1 : 0, &pl->fs->do_map))) return r;
+    k_frame_finish<<<1, 1, 0, c->stream>>>(pl->fs, neu->st, old->st, neu->ts, nav_slot, t, dt_frame);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+static int push_impl(rb_pipeline *pl, const uint8_t *rgb, bool on_device, const double *ts, int n, rb_nav *nav_out) {
+    rb_ctx *c = pl->c;
+    const rb_params &p = pl->p;
+    if (n < 1 || n > pl->max_batch || !rgb || !ts) return RB_ERR_ARG;
+    RB_CUDA(cudaSetDevice(c->device));
+    int r;
+    RB_CUDA(cudaEventRecord(pl->ev[0], c->stream));
+    RB_CUDA(cudaMemcpyAsync(pl->ws.rgb, rgb, (size_t)n * 3 * c->N,
+                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    if ((r = rb_dog_gray(c, &pl->ws, n))) return r;
+    RB_CUDA(cudaEventRecord(pl->ev[1], c->stream));
+    if ((r = rb_dog_build_batch(c, &pl->ws, n))) return r;
+    RB_CUDA(cudaEventRecord(pl->ev[2], c->stream));
+    for (int i = 0; i < n; i++) {
+        const long long fr = pl->n_pushed;
+        rb_map *neu = pl->maps[fr & 1], *old = pl->maps[(fr + 1) & 1];
+        const float *img0 = pl->ws.img0 + (size_t)i * c->N, *dog = pl->ws.dog + (size_t)i * c->N;
+        // FirstThr: detect + reEstimateThresh (rebvo_first_t.cpp:266-272)
+        if ((r = rb_detect_enqueue(c, neu, img0, dog, &p.det, pl->chain))) return r;
+        if ((r = rb_reestimate_enqueue(c, neu, p.TrackPoints, p.QCutOffNumBins))) return r;
+        if (fr == 0) {
+            k_frame_first<<<1, 1, 0, c->stream>>>(pl->fs, neu->st, pl->nav_dev + i, ts[i]);
+            RB_LAUNCH_CHECK();
+        } else {
+            double dt = ts[i] - pl->t_prev;                 // :146-149
+            if (dt < 0.001) dt = 1 / p.config_fps;
+            if ((r = track_frame(pl, neu, old, fr, ts[i], dt, pl->nav_dev + i))) return r;
+        }
+        pl->t_prev = ts[i];
+        pl->n_pushed++;
+    }
+    RB_CUDA(cudaMemcpyAsync(pl->nav_pin, pl->nav_dev, sizeof(rb_nav) * n, cudaMemcpyDeviceToHost, c->stream));
+    RB_CUDA(cudaEventRecord(pl->ev[3], c->stream));
+    RB_CUDA(cudaStreamSynchronize(c->stream));
+    if (nav_out) memcpy(nav_out, pl->nav_pin, sizeof(rb_nav) * n);
+    float ms;
+    cudaEventElapsedTime(&ms, pl->ev[0], pl->ev[1]);
+    pl->stage_ms[0] = ms;
+    cudaEventElapsedTime(&ms, pl->ev[1], pl->ev[2]);
+    pl->stage_ms[1] = ms;
+    cudaEventElapsedTime(&ms, pl->ev[2], pl->ev[3]);
+    pl->stage_ms[2] = ms;   // detect + tracker + mapper of all frames of the batch
+    pl->stage_ms[3] = pl->stage_ms[4] = 0;
+    cudaEventElapsedTime(&ms, pl->ev[0], pl->ev[3]);
+    pl->stage_ms[5] = ms;
+    return RB_OK;
+}
+
+extern "C" int rb_pipeline_push(rb_pipeline *pl, const uint8_t *rgb, const double *ts, int n, rb_nav *nav_out) {
+    return push_impl(pl, rgb, false, ts, n, nav_out);
+}
+extern "C" int rb_pipeline_push_dev(rb_pipeline *pl, const uint8_t *rgb_dev, const double *ts, int n,
+                                    rb_nav *nav_out) {
+    return push_impl(pl, rgb_dev, true, ts, n, nav_out);
+}

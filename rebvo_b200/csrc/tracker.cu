@@ -1,0 +1,1147 @@
+// tracker.cu -- edge-map tracker and mapper kernels:
+//   global_tracker::build_field / TryVelRot / Minimizer_RV   (src/mtracklib/global_tracker.cpp)
+//   edge_tracker::EstimateQuantile / FordwardMatch / rotate_keylines / directed_matching+search_match /
+//   Regularize_1_iter / UpdateInverseDepthKalman(ARLU) / EstimateReScalingOpt (src/mtracklib/edge_tracker.cpp)
+//
+// Per-keyline arithmetic follows the reference expression by expression in float64 (float32 where the
+// reference's operands are float) with contraction disabled (-fmad=false).  Sums over keylines (JtJ, JtF,
+// score, rescaling) use a fixed-order warp-shuffle / block / grid reduction: deterministic, but not the
+// reference's pairwise tree, so they agree to rounding (tests use rel 1e-11), not bitwise.
+#include "tracker.cuh"
+#include "lm.cuh"
+
+#define TVR_T 256
+#define RES_SENTINEL 0x7FF8DEADBEEF0001ull
+
+struct CamC {
+    double zfm, inv_zf;
+    float ppx, ppy;
+    int w, h;
+};
+
+static CamC make_cam(const rb_ctx *c) {
+    CamC k;
+    k.zfm = c->zfm;
+    k.inv_zf = 1 / c->zfm;
+    k.ppx = c->ppx;
+    k.ppy = c->ppy;
+    k.w = c->w;
+    k.h = c->h;
+    return k;
+}
+
+int rb_track_state_alloc(rb_ctx *c, rb_map *m) {
+    TrackState host;
+    memset(&host, 0, sizeof(host));
+    const int nblk = rb_div_up(c->kcap, TVR_T);
+    const size_t K = c->kcap + 32;
+    host.nblk = nblk;
+    RB_CUDA(cudaMalloc(&host.blk_first, sizeof(int) * nblk));
+    RB_CUDA(cudaMalloc(&host.blk_has, sizeof(int) * nblk));
+    RB_CUDA(cudaMalloc(&host.blk_last_fi, sizeof(double) * nblk));
+    RB_CUDA(cudaMalloc(&host.partials, sizeof(double) * 28 * nblk));
+    RB_CUDA(cudaMalloc(&host.fm_best, sizeof(unsigned long long) * K));
+    RB_CUDA(cudaMalloc(&host.fm_idx, sizeof(int) * K));
+    RB_CUDA(cudaMalloc(&host.reg_r, sizeof(double) * K));
+    RB_CUDA(cudaMalloc(&host.reg_s, sizeof(double) * K));
+    RB_CUDA(cudaMalloc(&host.reg_set, K));
+    RB_CUDA(cudaMalloc(&m->ts, sizeof(TrackState)));
+    RB_CUDA(cudaMemcpyAsync(m->ts, &host, sizeof(host), cudaMemcpyHostToDevice, c->stream));
+    RB_CUDA(cudaStreamSynchronize(c->stream));
+    m->ts_host = host;
+    return RB_OK;
+}
+
+void rb_track_state_free(rb_map *m) {
+    TrackState &h = m->ts_host;
+    cudaFree(h.blk_first);
+    cudaFree(h.blk_has);
+    cudaFree(h.blk_last_fi);
+    cudaFree(h.partials);
+    cudaFree(h.fm_best);
+    cudaFree(h.fm_idx);
+    cudaFree(h.reg_r);
+    cudaFree(h.reg_s);
+    cudaFree(h.reg_set);
+    cudaFree(m->ts);
+}
+
+// =====================================================================================================
+// EstimateQuantile (edge_tracker.cpp:1148-1186)
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_quantile(const double *__restrict__ s_rho, MapState *st,
+                                                  int *__restrict__ histo, unsigned int *ticket, double smin,
+                                                  double smax, double perc, int n) {
+    extern __shared__ int sh[];
+    const int kn = st->kn;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const double range = smax - smin;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kn; i += gridDim.x * blockDim.x) {
+        int b = (int)((double)n * (s_rho[i] - smin) / range);
+        b = b > n - 1 ? n - 1 : b;
+        b = b < 0 ? 0 : b;
+        atomicAdd(&sh[b], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (sh[i]) atomicAdd(&histo[i], sh[i]);
+    __threadfence();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        volatile int *vh = histo;
+        double q = 1e3;
+        for (int i = 0, a = 0; i < n; i++) {
+            if ((double)a > perc * (double)kn) {
+                q = (double)i * range / (double)n + smin;
+                break;
+            }
+            a += vh[i];
+        }
+        st->s_rho_q = q;
+        for (int i = 0; i < n; i++) histo[i] = 0;
+        *ticket = 0;
+    }
+}
+
+int rb_quantile_enqueue(rb_ctx *c, rb_map *m, double smin, double smax, double perc, int nbins) {
+    if (nbins < 1 || nbins > 4096) return RB_ERR_ARG;
+    int *histo = (int *)((char *)c->dev_small + RB_DS_QHISTO);  // zeroed at creation and by the kernel's tail
+    k_quantile<<<64, 256, sizeof(int) * nbins, c->stream>>>(m->kl.s_rho, m->st, histo, c->ticket + 2, smin, smax,
+                                                            perc, nbins);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+// =====================================================================================================
+// build_field (global_tracker.cpp:61-105): winner per pixel = smallest |t|, ties -> larger keyline id,
+// i.e. atomicMin of (|t| << 32 | ~ikl).  ~0 = no entry.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_build_field(unsigned long long *__restrict__ field, KLSoA kl,
+                                                     const MapState *__restrict__ st, int radius, float min_mod_v,
+                                                     int min_mod_from_state, int w, int h) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int span = 2 * radius;
+    const int ikl = (int)(gid / span);
+    if (ikl >= st->kn) return;
+    const int t = (int)(gid - (long long)ikl * span) - radius;   // t in [-radius, radius)
+    const float min_mod = min_mod_from_state ? st->retuned : min_mod_v;
+    if (min_mod > 0 && kl.n_m[ikl] < min_mod) return;
+    const float2 u = kl.u_m[ikl], cp = kl.c_p[ikl];
+    const float fx = u.x * (float)t + cp.x, fy = u.y * (float)t + cp.y;
+    const int xi = (int)roundf(fx), yi = (int)roundf(fy);       // Image::GetIndexRC (image.h:121-126)
+    if (xi >= w || yi >= h || xi < 0 || yi < 0) return;
+    const unsigned int at = (unsigned int)(t < 0 ? -t : t);
+    const unsigned long long key = ((unsigned long long)at << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)ikl);
+    atomicMin(&field[(size_t)yi * w + xi], key);
+}
+
+int rb_build_field_enqueue(rb_ctx *c, rb_map *m, int radius, float min_mod, bool from_state) {
+    if (radius < 1) return RB_ERR_ARG;
+    RB_CUDA(cudaMemsetAsync(m->field, 0xff, sizeof(unsigned long long) * (size_t)c->N, c->stream));
+    const long long threads = (long long)c->kcap * 2 * radius;
+    k_build_field<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(m->field, m->kl, m->st, radius, min_mod,
+                                                                          from_state ? 1 : 0, c->w, c->h);
+    RB_LAUNCH_CHECK();
+    m->field_radius = radius;
+    return RB_OK;
+}
+
+// =====================================================================================================
+// Minimizer_RV: LM driver executed by the last block of every evaluation kernel
+// =====================================================================================================
+__device__ __forceinline__ double max_element36(const double *M) {
+    double m = M[0];
+    for (int i = 1; i < 36; i++)
+        if (M[i] > m) m = M[i];
+    return m;
+}
+__device__ void lm_build_api(const LMState &s, double *A, double *rhs) {
+    for (int i = 0; i < 36; i++) A[i] = s.JtJ[i];
+    for (int i = 0; i < 6; i++) {
+        A[i * 6 + i] = s.JtJ[i * 6 + i] + s.u;  // ApI = JtJ + Identity*u
+        rhs[i] = -s.JtF[i];
+    }
+}
+__device__ void lm_solve(LMState &s, bool use_svd) {
+    double A[36], rhs[6];
+    lm_build_api(s, A, rhs);
+    if (use_svd) {
+        solve_sym6_like_svd(A, rhs, s.h);       // SVD<> svdApI(ApI); h = svdApI.backsub(-JtF)
+    } else {
+        Chol6 ch;                               // Cholesky<6> svdApI(ApI); h = svdApI.backsub(-JtF)
+        chol6_compute(A, &ch);
+        chol6_backsub(&ch, rhs, s.h);
+    }
+    for (int i = 0; i < 6; i++) s.Xnew[i] = s.X[i] + s.h[i];
+}
+__device__ void lm_request(LMState &s, const double *X, int res_in, int res_out) {
+    for (int i = 0; i < 6; i++) s.Xeval[i] = X[i];
+    s.res_in = res_in;
+    s.res_out = res_out;
+}
+__device__ void lm_take_first(LMState &s) {   // F = TryVelRot(JtJ, JtF, X ...); F0 = F; u = tau*max(JtJ)
+    s.F = s.last_score;
+    for (int i = 0; i < 36; i++) s.JtJ[i] = s.JtJn[i];
+    for (int i = 0; i < 6; i++) s.JtF[i] = s.JtFn[i];
+    s.F0 = s.F;
+    s.u = 1e-3 * max_element36(s.JtJ);
+}
+// returns true when the step was accepted
+__device__ bool lm_update(LMState &s, bool gain_with_den) {
+    s.Fnew = s.last_score;
+    if (gain_with_den) {
+        double den = 0;  // 0.5*h*(u*h-JtF): TooN dot of (0.5*h) and (u*h-JtF)
+        for (int i = 0; i < 6; i++) den += (0.5 * s.h[i]) * (s.u * s.h[i] - s.JtF[i]);
+        s.gain = (s.F - s.Fnew) / den;
+    } else {
+        s.gain = s.F - s.Fnew;
+    }
+    if (s.gain > 0) {
+        s.F = s.Fnew;
+        for (int i = 0; i < 6; i++) s.X[i] = s.Xnew[i];
+        for (int i = 0; i < 36; i++) s.JtJ[i] = s.JtJn[i];
+        for (int i = 0; i < 6; i++) s.JtF[i] = s.JtFn[i];
+        const double g = 2 * s.gain - 1;
+        const double f = 1 - (g * g * g);
+        s.u *= (0.33 > f ? 0.33 : f);  // std::max(0.33, ...)
+        s.v = 2;
+        s.eff_steps++;
+        return true;
+    }
+    s.u *= s.v;
+    s.v *= 2;
+    return false;
+}
+__device__ void lm_after_zero_pass(LMState &s) {   // global_tracker.cpp:686-700
+    for (int i = 0; i < 6; i++) s.Xt[i] = s.X[i];
+    s.Ft = s.F;
+    s.F0t = s.F0;
+    s.ut = s.u;
+    s.vt = s.v;
+    s.eff_steps_t = s.eff_steps;
+    s.eff_steps = 0;
+    for (int i = 0; i < 3; i++) {
+        s.X[i] = s.Vel_in[i];
+        s.X[3 + i] = s.W0_in[i];
+    }
+    lm_request(s, s.X, -1, s.iRN);
+}
+__device__ void lm_after_prior_pass(LMState &s) {  // :734-747
+    if (s.F > s.Ft) {
+        for (int i = 0; i < 6; i++) s.X[i] = s.Xt[i];
+        s.F = s.Ft;
+        s.F0 = s.F0t;
+        s.u = s.ut;
+        s.v = s.vt;
+        s.eff_steps = s.eff_steps_t;
+        s.iRN = s.iRt;
+    }
+    const int t = s.iRN;
+    s.iRN = s.iR;
+    s.iR = t;
+    lm_request(s, s.X, s.iR, s.iRN);
+}
+__device__ void lm_finalize(LMState &s, MapState *fst) {   // :793-816
+    Chol6 ch;
+    chol6_compute(s.JtJ, &ch);
+    double RRV[36];
+    chol6_inverse(&ch, RRV);
+    for (int i = 0; i < 3; i++) {
+        s.Vel[i] = s.X[i];
+        s.W0[i] = s.X[3 + i];
+        for (int j = 0; j < 3; j++) {
+            s.RVel[i * 3 + j] = RRV[i * 6 + j];
+            s.RW0[i * 3 + j] = RRV[(i + 3) * 6 + (j + 3)];
+        }
+    }
+    for (int i = 0; i < 36; i++) s.W_X[i] = s.JtJ[i];
+    if (s.eff_steps > 0) {
+        double nh = 0, nx = 0;
+        for (int i = 0; i < 6; i++) nh += s.h[i] * s.h[i];
+        for (int i = 0; i < 6; i++) nx += s.X[i] * s.X[i];
+        s.rel_error = sqrt(nh) / (sqrt(nx) + 1e-30);
+        s.rel_error_score = s.F / s.F0;
+    } else {
+        s.rel_error = 1e20;
+        s.rel_error_score = 1e20;
+    }
+    s.score = s.F;
+    fst->frame_count = fst->frame_count + 1;   // FrameCount++
+}
+
+__device__ void lm_step(LMState &s, int step, MapState *fst) {
+    switch (step) {
+        case STEP_INIT_FIRST_ZERO:
+            lm_take_first(s);   // v = 2 from the declaration (:620)
+            if (s.init_iter <= 0) {
+                lm_after_zero_pass(s);
+            } else {
+                lm_solve(s, true);
+                lm_request(s, s.Xnew, -1, s.iRt);
+            }
+            break;
+        case STEP_INIT_ITER_ZERO:
+            lm_update(s, true);
+            lm_solve(s, true);
+            lm_request(s, s.Xnew, -1, s.iRt);
+            break;
+        case STEP_INIT_LAST_ZERO:
+            lm_update(s, false);
+            lm_after_zero_pass(s);
+            break;
+        case STEP_INIT_FIRST_PRIOR:
+            lm_take_first(s);
+            s.v = 2;
+            if (s.init_iter <= 0) {
+                lm_after_prior_pass(s);
+            } else {
+                lm_solve(s, true);
+                lm_request(s, s.Xnew, -1, s.iRN);
+            }
+            break;
+        case STEP_INIT_ITER_PRIOR:
+            lm_update(s, true);
+            lm_solve(s, true);
+            lm_request(s, s.Xnew, -1, s.iRN);
+            break;
+        case STEP_INIT_LAST_PRIOR:
+            lm_update(s, false);
+            lm_after_prior_pass(s);
+            break;
+        case STEP_MAIN_FIRST:
+            lm_take_first(s);
+            s.v = 2;
+            if (s.iter_max <= 0) {
+                lm_finalize(s, fst);
+            } else {
+                lm_solve(s, false);
+                lm_request(s, s.Xnew, s.iR, s.iRN);
+            }
+            break;
+        case STEP_MAIN_ITER:
+        case STEP_MAIN_LAST:
+            if (lm_update(s, true)) {   // std::swap(ResidualNew,Residual)
+                const int t = s.iRN;
+                s.iRN = s.iR;
+                s.iR = t;
+            }
+            if (step == STEP_MAIN_LAST) {
+                lm_finalize(s, fst);
+            } else {
+                lm_solve(s, false);
+                lm_request(s, s.Xnew, s.iR, s.iRN);
+            }
+            break;
+        default:
+            break;
+    }
+}
+
+struct ResPtrs {
+    double *r[3];
+};
+
+__global__ void k_lm_begin(TrackState *ts, const MapState *old_st, const MapState *f_st, const double *VW,
+                           rb_minimizer_args a, double max_r, double max_s_rho, int s_rho_from_state,
+                           unsigned int frame_count, int fc_from_state) {
+    LMState &s = ts->lm;
+    s.max_r = max_r;
+    s.match_thresh = a.match_thresh;
+    s.k_huber = a.reweight_distance;
+    s.match_num_thresh = a.match_num_thresh;
+    s.iter_max = a.iter_max;
+    s.init_type = a.init_type;
+    s.init_iter = a.init_iter;
+    s.s_rho_min = s_rho_from_state ? old_st->s_rho_q : max_s_rho;
+    s.frame_count = fc_from_state ? f_st->frame_count : frame_count;
+    for (int i = 0; i < 3; i++) {
+        s.Vel_in[i] = VW[i];
+        s.W0_in[i] = VW[3 + i];
+    }
+    s.iR = 0;
+    s.iRN = 1;
+    s.iRt = 2;
+    s.v = 2;
+    s.u = 0;
+    s.eff_steps = 0;
+    s.n_eval = 0;
+    s.F = s.F0 = s.Fnew = 0;
+    for (int i = 0; i < 6; i++) s.h[i] = 0;
+    if (a.init_type == 1) {
+        for (int i = 0; i < 3; i++) {
+            s.X[i] = VW[i];
+            s.X[3 + i] = VW[3 + i];
+        }
+        lm_request(s, s.X, s.iR, s.iRN);
+    } else if (a.init_type == 0) {
+        for (int i = 0; i < 6; i++) s.X[i] = 0;
+        lm_request(s, s.X, s.iR, s.iRN);
+    } else {
+        for (int i = 0; i < 6; i++) s.X[i] = 0;
+        lm_request(s, s.X, -1, s.iRt);
+    }
+}
+
+// One TryVelRot evaluation (global_tracker.cpp:285-543) + the LM step that follows it.
+template <bool RW, bool PJ>
+__global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *__restrict__ old_st,
+                                                    const unsigned long long *__restrict__ field,
+                                                    const float4 *__restrict__ fpack, MapState *f_st,
+                                                    TrackState *ts, ResPtrs res, unsigned int *ticket, CamC cam,
+                                                    int step) {
+    __shared__ double sR[9], sV[3], sRM[4];
+    __shared__ double s_red[TVR_T / 32][28];
+    __shared__ int s_whas[TVR_T / 32], s_wfirst[TVR_T / 32];
+    __shared__ double s_wlast[TVR_T / 32];
+    __shared__ double s_tot[28];
+    __shared__ bool s_last;
+    LMState &lm = ts->lm;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        double X[6];
+        for (int i = 0; i < 6; i++) X[i] = lm.Xeval[i];
+        so3_exp(X + 3, sR);                        // SO3<> RotW0(VelRot.slice<3,3>())
+        double wz[3] = {0, 0, X[5]}, RMf[9];
+        so3_exp(wz, RMf);                          // SO3<> RotM(makeVector(0,0,VelRot[5]))
+        sRM[0] = RMf[0];
+        sRM[1] = RMf[1];
+        sRM[2] = RMf[3];
+        sRM[3] = RMf[4];
+        for (int i = 0; i < 3; i++) sV[i] = X[i];
+    }
+    __syncthreads();
+    const int res_in = lm.res_in, res_out = lm.res_out;
+    const double max_r = lm.max_r, match_thresh = lm.match_thresh, s_rho_min = lm.s_rho_min, k_huber = lm.k_huber;
+    const unsigned int mnt = lm.match_num_thresh < lm.frame_count ? lm.match_num_thresh : lm.frame_count;
+    const double *__restrict__ rin = (RW && res_in >= 0) ? res.r[res_in] : nullptr;
+    double *__restrict__ rout = res.r[res_out];
+
+    const int K0 = old_st->kn;
+    const int i = blockIdx.x * TVR_T + tid;
+    const bool active = i < K0;
+    double acc[28];
+#pragma unroll
+    for (int k = 0; k < 28; k++) acc[k] = 0;
+    bool matched = false, need = false;
+    double fi_own = 0;
+    if (active) {
+        const float2 pm = old.p_m[i];
+        const double rho = old.rho[i], s_rho = old.s_rho[i];
+        const int m_num = old.m_num[i];
+        // KltoI3PMatrix + ProyI3Pto3PMatrix (global_tracker.cpp:552-570, ne10wrapper.h:413-424)
+        const double z0 = 1 / rho;
+        const double pz_zf0 = cam.inv_zf * z0;
+        const double x0 = pz_zf0 * (double)pm.x, y0 = pz_zf0 * (double)pm.y;
+        // SE3on3PMatrix (ne10wrapper.h:375-405): MulC, MlAc, MlAc, then Vel + .
+        double px = sR[0] * x0;
+        px = px + sR[1] * y0;
+        px = px + sR[2] * z0;
+        px = sV[0] + px;
+        double py = sR[3] * x0;
+        py = py + sR[4] * y0;
+        py = py + sR[5] * z0;
+        py = sV[1] + py;
+        double pz = sR[6] * x0;
+        pz = pz + sR[7] * y0;
+        pz = pz + sR[8] * z0;
+        pz = sV[2] + pz;
+        // ProyP3toI3PMatrix (ne10wrapper.h:429-445)
+        const double rho_p = 1 / pz;
+        const double pz_zf = cam.zfm * rho_p;
+        const double qx = pz_zf * px, qy = pz_zf * py;
+        double f = 0, dfx = 0, dfy = 0;
+        int mid_f = -1;
+        const bool skip = (s_rho > s_rho_min) || ((unsigned int)m_num < mnt);   // :356
+        if (!skip) {
+            const double pix = qx + (double)cam.ppx, piy = qy + (double)cam.ppy;   // cam_mod.Hom2Img
+            const int x = (int)(pix + 0.5), y = (int)(piy + 0.5);                   // util::round2int_positive
+            double weight = 1;
+            if (RW && rin) {
+                const double r = fabs(rin[i]);
+                if (r > k_huber) weight = k_huber / r;                             // :370-372
+            }
+            if (x < 1 || y < 1 || x >= cam.w - 1 || y >= cam.h - 1) {               // :376
+                f = max_r;
+                if (RW) f *= weight;
+                rout[i] = max_r;
+            } else {
+                const float2 m = old.m_m[i];
+                const float mrx = (float)(sRM[0] * (double)m.x + sRM[1] * (double)m.y);   // :386-388
+                const float mry = (float)(sRM[2] * (double)m.x + sRM[3] * (double)m.y);
+                const unsigned long long key = field[(size_t)y * cam.w + x];
+                bool hit = false;
+                if (key != ~0ull) {
+                    const int ikl = (int)(0xFFFFFFFFu - (unsigned int)(key & 0xFFFFFFFFull));
+                    const float4 a = fpack[2 * ikl], b = fpack[2 * ikl + 1];
+                    const float n_m = old.n_m[i];
+                    const double p_n2 = (double)(n_m * n_m);                       // Test_f_k (global_tracker.h:89-104)
+                    const double p_esc = (double)(mrx * a.x + mry * a.y);
+                    if (!(fabs(p_esc - p_n2) > match_thresh * p_n2)) {
+                        const double dx = pix - (double)a.z, dy = piy - (double)a.w;   // Calc_f_J2 :254-262
+                        const double fi = dx * (double)b.x + dy * (double)b.y;
+                        dfx = (double)b.x;
+                        dfy = (double)b.y;
+                        f = fi;
+                        matched = true;
+                        fi_own = fi;
+                        mid_f = ikl;
+                        hit = true;
+                    }
+                }
+                if (!hit) {
+                    f = max_r;
+                    need = true;
+                }
+                if (RW) {
+                    f *= weight;
+                    dfx *= weight;
+                    dfy *= weight;
+                }
+            }
+        }
+        old.m_id_f[i] = mid_f;
+        // Jacobians (:419-449) and the 1/q_rho scaling (:452-463)
+        const double qvel = (cam.zfm * dfx * sV[0] + cam.zfm * dfy * sV[1]) + (qx * dfx + qy * dfy) * sV[2];
+        double q_rho = sqrt(s_rho * qvel * s_rho * qvel + 1);
+        if (!RW) q_rho = s_rho;
+        if (PJ) {
+            double t0 = cam.zfm * rho_p;
+            double J0 = t0 * dfx, J1 = t0 * dfy;
+            t0 = rho_p * qx;
+            double J2 = t0 * dfx;
+            t0 = rho_p * qy;
+            J2 = J2 + t0 * dfy;
+            double J3 = J1 * pz;
+            J3 = J3 + J2 * py;
+            double J4 = J0 * pz;
+            J4 = J4 + J2 * px;
+            t0 = J0 * py;
+            double J5 = -1.0 * t0;
+            J5 = J5 + J1 * px;
+            double J[6] = {J0 / q_rho, J1 / q_rho, J2 / q_rho, J3 / q_rho, J4 / q_rho, J5 / q_rho};
+            f = f / q_rho;
+            int k = 0;
+#pragma unroll
+            for (int a = 0; a < 6; a++)
+#pragma unroll
+                for (int b = a; b < 6; b++) acc[k++] = J[a] * J[b];
+#pragma unroll
+            for (int a = 0; a < 6; a++) acc[21 + a] = J[a] * f;
+        } else {
+            f = f / q_rho;
+        }
+        acc[27] = f * f;
+    }
+    // ---- "DResidualNew[ikl]=fi" keeps the fi of the last matched keyline before ikl (fi is a function-level
+    // variable, :341,399-408): in-block scan, cross-block part resolved by the last block --------------
+    const unsigned int bal = __ballot_sync(0xffffffffu, matched);
+    const unsigned int lower = bal & ((1u << lane) - 1u);
+    const int src = lower ? 31 - __clz(lower) : 0;
+    const double prev_fi = __shfl_sync(0xffffffffu, fi_own, src);
+    if (lane == 0) {
+        s_whas[wid] = bal != 0;
+        s_wfirst[wid] = bal ? (wid * 32 + __ffs(bal) - 1) : TVR_T;
+    }
+    {
+        const int hi = bal ? 31 - __clz(bal) : 0;
+        const double wl = __shfl_sync(0xffffffffu, fi_own, hi);
+        if (lane == 0) s_wlast[wid] = wl;
+    }
+    // ---- reduction of the 28 sums: warp shuffle, then across warps in fixed order
+    const int nred = PJ ? 28 : 1;
+    if (PJ) {
+#pragma unroll
+        for (int k = 0; k < 28; k++) {
+            double v = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s_red[wid][k] = v;
+        }
+    } else {
+        double v = acc[27];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_red[wid][27] = v;
+    }
+    __syncthreads();
+    if (active) {
+        if (matched) {
+            rout[i] = fi_own;
+        } else if (need) {
+            double v;
+            bool found = lower != 0;
+            v = prev_fi;
+            if (!found) {
+                for (int ww = wid - 1; ww >= 0; ww--)
+                    if (s_whas[ww]) {
+                        v = s_wlast[ww];
+                        found = true;
+                        break;
+                    }
+            }
+            if (found) rout[i] = v;
+            else reinterpret_cast<unsigned long long *>(rout)[i] = RES_SENTINEL;
+        }
+    }
+    if (tid < 28 && (PJ || tid == 27)) {
+        double v = 0;
+#pragma unroll
+        for (int ww = 0; ww < TVR_T / 32; ww++) v += s_red[ww][tid];
+        ts->partials[(size_t)blockIdx.x * 28 + tid] = v;
+    }
+    if (tid == 0) {
+        int first = TVR_T, has = 0;
+        double lastv = 0;
+        for (int ww = 0; ww < TVR_T / 32; ww++) {
+            if (s_whas[ww]) {
+                if (!has) first = s_wfirst[ww];
+                has = 1;
+                lastv = s_wlast[ww];
+            }
+        }
+        ts->blk_first[blockIdx.x] = first;
+        ts->blk_has[blockIdx.x] = has;
+        ts->blk_last_fi[blockIdx.x] = lastv;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    // ================= last block: grid reduction, stale-fi carries, LM step ==========================
+    __threadfence();
+    const int nb = gridDim.x;
+    if (tid < 28 && (PJ || tid == 27)) {
+        const volatile double *part = ts->partials;
+        double v = 0;
+        for (int b = 0; b < nb; b++) v += part[(size_t)b * 28 + tid];
+        s_tot[tid] = v;
+    }
+    // carries: block b inherits the last matched fi of the nearest earlier block that has one (0 at start)
+    __shared__ double s_carry[256];
+    if (tid == 0) {
+        const volatile int *bh = ts->blk_has;
+        const volatile double *bl = ts->blk_last_fi;
+        double carry = 0;
+        for (int b = 0; b < nb && b < 256; b++) {
+            s_carry[b] = carry;
+            if (bh[b]) carry = bl[b];
+        }
+    }
+    __syncthreads();
+    {
+        const volatile int *bf = ts->blk_first;
+        unsigned long long *rbits = reinterpret_cast<unsigned long long *>(rout);
+        for (int b = 0; b < nb && b < 256; b++) {
+            const int lim = bf[b];
+            if (tid < lim) {
+                const int idx = b * TVR_T + tid;
+                if (idx < K0 && __ldcg(&rbits[idx]) == RES_SENTINEL) rout[idx] = s_carry[b];
+            }
+        }
+    }
+    if (tid == 0) {
+        if (PJ) {
+            int k = 0;
+            for (int a = 0; a < 6; a++)
+                for (int b = a; b < 6; b++) lm.JtJn[a * 6 + b] = s_tot[k++];
+            for (int a = 0; a < 6; a++) lm.JtFn[a] = s_tot[21 + a];
+            for (int a = 0; a < 2; a++) {              // sign fix-ups (:484-490)
+                lm.JtFn[a + 2] = -lm.JtFn[a + 2];
+                for (int b = 0; b < 2; b++) {
+                    lm.JtJn[(a + 0) * 6 + (b + 2)] = -lm.JtJn[(a + 0) * 6 + (b + 2)];
+                    lm.JtJn[(a + 2) * 6 + (b + 4)] = -lm.JtJn[(a + 2) * 6 + (b + 4)];
+                }
+            }
+            for (int a = 0; a < 6; a++)
+                for (int b = a + 1; b < 6; b++) lm.JtJn[b * 6 + a] = lm.JtJn[a * 6 + b];
+        }
+        lm.last_score = s_tot[27];
+        lm.n_eval++;
+        lm_step(lm, step, f_st);
+        *ticket = 0;
+    }
+    (void)nred;
+}
+
+template <bool RW, bool PJ>
+static int launch_eval(rb_ctx *c, rb_map *fmap, rb_map *old, int step) {
+    ResPtrs rp;
+    for (int i = 0; i < 3; i++) rp.r[i] = fmap->res[i];
+    const int nblk = fmap->ts_host.nblk;
+    k_tvr_eval<RW, PJ><<<nblk, TVR_T, 0, c->stream>>>(old->kl, old->st, fmap->field, fmap->kl.pack, fmap->st,
+                                                     fmap->ts, rp, c->ticket + 1, make_cam(c), step);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+int rb_minimizer_enqueue(rb_ctx *c, rb_map *fmap, rb_map *old, const double *VW_dev, const rb_minimizer_args *a,
+                         double max_s_rho, bool s_rho_from_state, unsigned int frame_count, bool fc_from_state) {
+    if (fmap->field_radius <= 0) {
+        snprintf(c->err, sizeof(c->err), "Minimizer_RV before build_field");
+        return RB_ERR_STATE;
+    }
+    if (fmap->ts_host.nblk > 256) return RB_ERR_ARG;
+    int r;
+    RB_CUDA(cudaMemsetAsync(fmap->res[0], 0, sizeof(double) * (size_t)c->kcap, c->stream));   // Residual[i]=0 (:625)
+    k_lm_begin<<<1, 1, 0, c->stream>>>(fmap->ts, old->st, fmap->st, VW_dev, *a, (double)fmap->field_radius,
+                                       max_s_rho, s_rho_from_state ? 1 : 0, frame_count, fc_from_state ? 1 : 0);
+    RB_LAUNCH_CHECK();
+    const int n = a->init_iter, m = a->iter_max;
+    if (a->init_type != 0 && a->init_type != 1) {
+        if ((r = launch_eval<false, true>(c, fmap, old, STEP_INIT_FIRST_ZERO))) return r;
+        for (int i = 0; i < n; i++) {
+            if (i == n - 1) r = launch_eval<false, false>(c, fmap, old, STEP_INIT_LAST_ZERO);
+            else r = launch_eval<false, true>(c, fmap, old, STEP_INIT_ITER_ZERO);
+            if (r) return r;
+        }
+        if ((r = launch_eval<false, true>(c, fmap, old, STEP_INIT_FIRST_PRIOR))) return r;
+        for (int i = 0; i < n; i++) {
+            if (i == n - 1) r = launch_eval<false, false>(c, fmap, old, STEP_INIT_LAST_PRIOR);
+            else r = launch_eval<false, true>(c, fmap, old, STEP_INIT_ITER_PRIOR);
+            if (r) return r;
+        }
+    }
+    if ((r = launch_eval<true, true>(c, fmap, old, STEP_MAIN_FIRST))) return r;
+    for (int j = 0; j < m; j++)
+        if ((r = launch_eval<true, true>(c, fmap, old, j == m - 1 ? STEP_MAIN_LAST : STEP_MAIN_ITER))) return r;
+    return RB_OK;
+}
+
+// single evaluation for the parity tests (rb_try_vel_rot)
+__global__ void k_lm_single(TrackState *ts, const double *X, int res_in, int res_out, double max_r, double mt,
+                            double s_rho_min, unsigned int mnt, unsigned int fc, double k_huber) {
+    LMState &s = ts->lm;
+    for (int i = 0; i < 6; i++) s.Xeval[i] = X[i];
+    s.res_in = res_in;
+    s.res_out = res_out;
+    s.max_r = max_r;
+    s.match_thresh = mt;
+    s.s_rho_min = s_rho_min;
+    s.match_num_thresh = mnt;
+    s.frame_count = fc;
+    s.k_huber = k_huber;
+}
+
+int rb_try_vel_rot_enqueue(rb_ctx *c, rb_map *fmap, rb_map *old, const double *X_dev, int reweight, int procjf,
+                           double match_thresh, double s_rho_min, unsigned int mnt, unsigned int fc,
+                           double k_huber) {
+    if (fmap->field_radius <= 0) return RB_ERR_STATE;
+    k_lm_single<<<1, 1, 0, c->stream>>>(fmap->ts, X_dev, 0, 1, (double)fmap->field_radius, match_thresh, s_rho_min,
+                                        mnt, fc, k_huber);
+    RB_LAUNCH_CHECK();
+    if (reweight && procjf) return launch_eval<true, true>(c, fmap, old, STEP_NONE);
+    if (reweight) return launch_eval<true, false>(c, fmap, old, STEP_NONE);
+    if (procjf) return launch_eval<false, true>(c, fmap, old, STEP_NONE);
+    return launch_eval<false, false>(c, fmap, old, STEP_NONE);
+}
+
+// =====================================================================================================
+// FordwardMatch (edge_tracker.cpp:380-436).  Sequential rule: a later old keyline replaces the holder of
+// its target unless the holder's rho is strictly larger => winner = arg max rho, ties -> largest index.
+// =====================================================================================================
+__device__ __forceinline__ unsigned long long dbl_key(double v) {   // monotonic map double -> uint64
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__global__ void __launch_bounds__(256) k_fm_init(unsigned long long *best, int *idx, const MapState *nst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nst->kn) return;
+    best[i] = 0ull;
+    idx[i] = -1;
+}
+__global__ void __launch_bounds__(256) k_fm_pass1(KLSoA old, const MapState *ost, const MapState *nst,
+                                                  unsigned long long *best) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ost->kn) return;
+    const int f = old.m_id_f[i];
+    if (f < 0 || f >= nst->kn) return;
+    atomicMax(&best[f], dbl_key(old.rho[i]));
+}
+__global__ void __launch_bounds__(256) k_fm_pass2(KLSoA old, const MapState *ost, const MapState *nst,
+                                                  const unsigned long long *best, int *idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ost->kn) return;
+    const int f = old.m_id_f[i];
+    if (f < 0 || f >= nst->kn) return;
+    if (dbl_key(old.rho[i]) == best[f]) atomicMax(&idx[f], i);
+}
+__global__ void __launch_bounds__(256) k_fm_apply(KLSoA old, KLSoA neu, MapState *nst, const int *idx) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = f < nst->kn;
+    int i = valid ? idx[f] : -1;
+    if (i >= 0) {
+        neu.rho[f] = old.rho[i];
+        neu.s_rho[f] = old.s_rho[i];
+        neu.m_num[f] = old.m_num[i] + 1;
+        neu.m_id[f] = i;
+        neu.p_m_0[f] = old.p_m[i];
+        neu.m_m0[f] = old.m_m[i];
+        neu.n_m0[f] = (double)old.n_m[i];
+    }
+    const unsigned int bal = __ballot_sync(0xffffffffu, i >= 0);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&nst->fwd_match, __popc(bal));
+}
+__global__ void k_set_int(int *p, int v) { *p = v; }
+
+int rb_forward_match_enqueue(rb_ctx *c, rb_map *old, rb_map *neu) {
+    const int nb = rb_div_up(c->kcap, 256);
+    TrackState &t = neu->ts_host;
+    k_set_int<<<1, 1, 0, c->stream>>>(&neu->st->fwd_match, 0);
+    RB_LAUNCH_CHECK();
+    k_fm_init<<<nb, 256, 0, c->stream>>>(t.fm_best, t.fm_idx, neu->st);
+    RB_LAUNCH_CHECK();
+    k_fm_pass1<<<nb, 256, 0, c->stream>>>(old->kl, old->st, neu->st, t.fm_best);
+    RB_LAUNCH_CHECK();
+    k_fm_pass2<<<nb, 256, 0, c->stream>>>(old->kl, old->st, neu->st, t.fm_best, t.fm_idx);
+    RB_LAUNCH_CHECK();
+    k_fm_apply<<<nb, 256, 0, c->stream>>>(old->kl, neu->kl, neu->st, t.fm_idx);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+// =====================================================================================================
+// rotate_keylines (edge_tracker.cpp:42-76)
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_rotate(KLSoA kl, const MapState *st, const double *__restrict__ Rp,
+                                                double zf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st->kn) return;
+    double R[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = Rp[k];
+    const float2 pm = kl.p_m[i];
+    const double v0 = (double)pm.x / zf, v1 = (double)pm.y / zf, v2 = 1;
+    double q0 = 0, q1 = 0, q2 = 0;   // TooN Matrix*Vector: dot accumulates from 0
+    q0 = q0 + R[0] * v0; q0 = q0 + R[1] * v1; q0 = q0 + R[2] * v2;
+    q1 = q1 + R[3] * v0; q1 = q1 + R[4] * v1; q1 = q1 + R[5] * v2;
+    q2 = q2 + R[6] * v0; q2 = q2 + R[7] * v1; q2 = q2 + R[8] * v2;
+    if (fabs(q2) > 0) {
+        kl.p_m[i] = make_float2((float)(q0 / q2 * zf), (float)(q1 / q2 * zf));
+        kl.rho[i] = kl.rho[i] / q2;
+        kl.s_rho[i] = kl.s_rho[i] / q2;
+    }
+    const float2 m = kl.m_m[i];
+    const double m0 = (double)m.x, m1 = (double)m.y;
+    double r0 = 0, r1 = 0;
+    r0 = r0 + R[0] * m0; r0 = r0 + R[1] * m1; r0 = r0 + R[2] * 0.0;
+    r1 = r1 + R[3] * m0; r1 = r1 + R[4] * m1; r1 = r1 + R[5] * 0.0;
+    const float2 mr = make_float2((float)r0, (float)r1);
+    kl.m_m[i] = mr;
+    float4 p = kl.pack[2 * i];
+    p.x = mr.x;
+    p.y = mr.y;
+    kl.pack[2 * i] = p;
+}
+
+int rb_rotate_enqueue(rb_ctx *c, rb_map *m, const double *R_dev) {
+    k_rotate<<<rb_div_up(c->kcap, 256), 256, 0, c->stream>>>(m->kl, m->st, R_dev, c->zfm);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+// =====================================================================================================
+// directed_matching + search_match (edge_tracker.cpp:158-374)
+// =====================================================================================================
+__global__ void __launch_bounds__(128) k_directed_match(KLSoA neu, MapState *nst, KLSoA old,
+                                                        const int *__restrict__ omask, const DMatchArgs *__restrict__ ap,
+                                                        CamC cam, double min_thr_mod, double cang_min_edge,
+                                                        double max_radius, double loc_unc, const int *enable) {
+    if (enable && !*enable) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool got = false;
+    if (i < nst->kn) {
+        const double zf = cam.zfm;
+        const double *BR = ap->BackRot, *Vel = ap->Vel, *RV = ap->RVel;
+        const float2 kpm = neu.p_m[i];
+        const double krho = neu.rho[i], ks_rho = neu.s_rho[i];
+        const float2 km = neu.m_m[i];
+        const float kn_m = neu.n_m[i];
+        // p_m3 = BackRot*(p_m.x, p_m.y, zfm)
+        const double a0 = (double)kpm.x, a1 = (double)kpm.y, a2 = zf;
+        double p30 = 0, p31 = 0, p32 = 0;
+        p30 = p30 + BR[0] * a0; p30 = p30 + BR[1] * a1; p30 = p30 + BR[2] * a2;
+        p31 = p31 + BR[3] * a0; p31 = p31 + BR[4] * a1; p31 = p31 + BR[5] * a2;
+        p32 = p32 + BR[6] * a0; p32 = p32 + BR[7] * a1; p32 = p32 + BR[8] * a2;
+        const float pmx = (float)(p30 * zf / p32), pmy = (float)(p31 * zf / p32);
+        const double k_rho = krho * zf / p32;
+        const float pi0x = pmx + cam.ppx, pi0y = pmy + cam.ppy;             // Hom2Img on Point2DF
+        double t_x = -(Vel[0] * zf - Vel[2] * (double)pmx);
+        double t_y = -(Vel[1] * zf - Vel[2] * (double)pmy);
+        double norm_t = sqrt(t_x * t_x + t_y * t_y);
+        const double D0 = zf, D1 = zf, D2 = (double)(-pmx - pmy);           // DrDv
+        double r0 = 0, r1 = 0, r2 = 0;                                      // DrDv.as_row()*RVel
+        r0 = r0 + D0 * RV[0]; r0 = r0 + D1 * RV[3]; r0 = r0 + D2 * RV[6];
+        r1 = r1 + D0 * RV[1]; r1 = r1 + D1 * RV[4]; r1 = r1 + D2 * RV[7];
+        r2 = r2 + D0 * RV[2]; r2 = r2 + D1 * RV[5]; r2 = r2 + D2 * RV[8];
+        double sigma2_t = 0;
+        sigma2_t = sigma2_t + r0 * D0; sigma2_t = sigma2_t + r1 * D1; sigma2_t = sigma2_t + r2 * D2;
+        double dq_min, dq_max, dq_rho;
+        int t_steps;
+        if (norm_t > 1e-6) {
+            t_x /= norm_t;
+            t_y /= norm_t;
+            dq_rho = norm_t * k_rho;
+            dq_min = fmax(0.0, norm_t * (k_rho - ks_rho)) - loc_unc;
+            dq_max = fmin(max_radius, norm_t * (k_rho + ks_rho)) + loc_unc;
+            if (dq_rho > dq_max) {
+                dq_rho = (dq_max + dq_min) / 2;
+                t_steps = (int)(dq_rho + 0.5);
+            } else {
+                t_steps = (int)(fmax(dq_max - dq_rho, dq_rho - dq_min) + 0.5);
+            }
+        } else {
+            t_x = (double)km.x;
+            t_y = (double)km.y;
+            norm_t = (double)kn_m;
+            t_x /= norm_t;
+            t_y /= norm_t;
+            norm_t = 1;
+            dq_min = -max_radius - loc_unc;
+            dq_max = max_radius + loc_unc;
+            dq_rho = 0;
+            t_steps = (int)dq_max;
+        }
+        const double norm_m = (double)kn_m;
+        double tn = dq_rho, tp = dq_rho + 1;
+        int jm = -1;
+        for (int t_i = 0; t_i < t_steps && jm < 0; t_i++, tp += 1, tn -= 1) {
+#pragma unroll
+            for (int dir = 0; dir < 2; dir++) {
+                double t;
+                if (dir) {
+                    t = tp;
+                    if (t > dq_max) continue;
+                } else {
+                    t = tn;
+                    if (t < dq_min) continue;
+                }
+                const float fx = (float)(t_x * t + (double)pi0x), fy = (float)(t_y * t + (double)pi0y);
+                const int xi = (int)roundf(fx), yi = (int)roundf(fy);       // GetIndexRC
+                if (xi >= cam.w || yi >= cam.h || xi < 0 || yi < 0) continue;
+                const int j = omask[(size_t)yi * cam.w + xi];
+                if (j < 0) continue;
+                const double norm_m0 = (double)old.n_m[j];
+                const float2 om = old.m_m[j];
+                const double cang = (double)(om.x * km.x + om.y * km.y) / (norm_m0 * norm_m);
+                if (cang < cang_min_edge || fabs(norm_m0 / norm_m - 1) > min_thr_mod) continue;
+                const double s_rho = old.s_rho[j], rho = old.rho[j];
+                const double v_rho_dr = (loc_unc * loc_unc + s_rho * s_rho * norm_t * norm_t + sigma2_t * rho * rho);
+                const double e = t - norm_t * rho;
+                if (e * e > v_rho_dr) continue;
+                jm = j;
+                break;
+            }
+        }
+        if (jm >= 0) {                                                     // :343-366
+            neu.rho[i] = old.rho[jm];
+            neu.s_rho[i] = old.s_rho[jm];
+            neu.m_id[i] = jm;
+            neu.m_num[i] = old.m_num[jm] + 1;
+            neu.p_m_0[i] = old.p_m[jm];
+            neu.m_m0[i] = old.m_m[jm];
+            neu.n_m0[i] = (double)old.n_m[jm];
+            got = true;
+        }
+    }
+    const unsigned int bal = __ballot_sync(0xffffffffu, got);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&nst->nmatch, __popc(bal));
+}
+
+int rb_directed_matching_enqueue(rb_ctx *c, rb_map *neu, rb_map *old, const DMatchArgs *args_dev, double min_thr_mod,
+                                 double min_thr_ang, double max_radius, double loc_uncertainty, const int *enable_dev) {
+    const double cang_min_edge = cos(min_thr_ang * M_PI / 180.0);
+    k_set_int<<<1, 1, 0, c->stream>>>(&neu->st->nmatch, 0);
+    RB_LAUNCH_CHECK();
+    k_directed_match<<<rb_div_up(c->kcap, 128), 128, 0, c->stream>>>(neu->kl, neu->st, old->kl, old->mask, args_dev,
+                                                                    make_cam(c), min_thr_mod, cang_min_edge,
+                                                                    max_radius, loc_uncertainty, enable_dev);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+// =====================================================================================================
+// Regularize_1_iter (edge_tracker.cpp:87-148), double buffered like the reference
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_regularize_a(KLSoA kl, MapState *st, double *__restrict__ r,
+                                                      double *__restrict__ s, unsigned char *__restrict__ set,
+                                                      double thresh, const int *enable) {
+    if (enable && !*enable) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool did = false;
+    if (i < st->kn) {
+        unsigned char sv = 0;
+        const int ni = kl.n_id[i], pi = kl.p_id[i];
+        if (ni >= 0 && pi >= 0) {
+            const double krho = kl.rho[i], ks = kl.s_rho[i];
+            const double nrho = kl.rho[ni], ns = kl.s_rho[ni];
+            const double prho = kl.rho[pi], ps = kl.s_rho[pi];
+            const double d = nrho - prho;
+            if (!(d * d > ns * ns + ps * ps)) {
+                const float2 nm = kl.m_m[ni], pmv = kl.m_m[pi];
+                const float nnm = kl.n_m[ni], pnm = kl.n_m[pi];
+                // floats: (kn.m_m.x*kp.m_m.x+kn.m_m.y*kp.m_m.y)/(kn.n_m*kp.n_m) evaluates in float
+                double alpha = (double)((nm.x * pmv.x + nm.y * pmv.y) / (nnm * pnm));
+                if (!(alpha - thresh < 0)) {
+                    alpha = (alpha - thresh) / (1 - thresh);
+                    alpha /= fabs(nrho - prho) / (ns + ps) + 1;
+                    const double wr = 1 / (ks * ks);
+                    const double wrn = alpha / (ns * ns);
+                    const double wrp = alpha / (ps * ps);
+                    r[i] = (krho * wr + nrho * wrn + prho * wrp) / (wr + wrn + wrp);
+                    s[i] = (ks * wr + ns * wrn + ps * wrp) / (wr + wrn + wrp);
+                    sv = 1;
+                    did = true;
+                }
+            }
+        }
+        set[i] = sv;
+    }
+    const unsigned int bal = __ballot_sync(0xffffffffu, did);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&st->reg_num, __popc(bal));
+}
+__global__ void __launch_bounds__(256) k_regularize_b(KLSoA kl, const MapState *st, const double *__restrict__ r,
+                                                      const double *__restrict__ s,
+                                                      const unsigned char *__restrict__ set, const int *enable) {
+    if (enable && !*enable) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st->kn || !set[i]) return;
+    kl.rho[i] = r[i];
+    kl.s_rho[i] = s[i];
+}
+
+int rb_regularize_enqueue(rb_ctx *c, rb_map *m, double thresh, const int *enable_dev) {
+    TrackState &t = m->ts_host;
+    const int nb = rb_div_up(c->kcap, 256);
+    k_set_int<<<1, 1, 0, c->stream>>>(&m->st->reg_num, 0);
+    RB_LAUNCH_CHECK();
+    k_regularize_a<<<nb, 256, 0, c->stream>>>(m->kl, m->st, t.reg_r, t.reg_s, t.reg_set, thresh, enable_dev);
+    RB_LAUNCH_CHECK();
+    k_regularize_b<<<nb, 256, 0, c->stream>>>(m->kl, m->st, t.reg_r, t.reg_s, t.reg_set, enable_dev);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+// =====================================================================================================
+// UpdateInverseDepthKalman -> UpdateInverseDepthKalmanARLU (edge_tracker.cpp:695-724, 954-1055)
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_ekf(KLSoA kl, const MapState *st, const double *__restrict__ velp, double zf,
+                                             double q_abs, double loc_unc, const int *enable) {
+    if (enable && !*enable) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st->kn) return;
+    if (kl.m_id[i] < 0) return;
+    const double vel0 = velp[0], vel1 = velp[1], vel2 = velp[2];
+    double rho = kl.rho[i], s_rho = kl.s_rho[i];
+    kl.s_rho0[i] = s_rho;
+    const float2 pm = kl.p_m[i], pm0 = kl.p_m_0[i], mm0 = kl.m_m0[i];
+    const double n_m0 = kl.n_m0[i];
+    const double qx = (double)pm.x, qy = (double)pm.y, q0x = (double)pm0.x, q0y = (double)pm0.y;
+    double v_rho = s_rho * s_rho;
+    const double u_x = (double)mm0.x / n_m0, u_y = (double)mm0.y / n_m0;
+    const double Y = u_x * (qx - q0x) + u_y * (qy - q0y);
+    const double H = u_x * (vel0 * zf - vel2 * q0x) + u_y * (vel1 * zf - vel2 * q0y);
+    const double rho_p = 1 / (1.0 / rho + vel2);
+    kl.rho0[i] = rho_p;
+    double F = 1 / (1 + rho * vel2);
+    F = F * F;
+    const double p_p = F * v_rho * F + q_abs * q_abs;
+    const double e = Y - H * rho_p;
+    const double S = H * p_p * H + loc_unc * loc_unc;
+    const double K = p_p * H * (1 / S);
+    rho = rho_p + (K * e);
+    v_rho = (1 - K * H) * p_p;
+    s_rho = sqrt(v_rho);
+    if (rho < RB_RHO_MIN) {
+        s_rho += RB_RHO_MIN - rho;
+        rho = RB_RHO_MIN;
+    } else if (rho > RB_RHO_MAX) {
+        rho = RB_RHO_MAX;
+    } else if (isnan(rho) || isnan(s_rho) || isinf(rho) || isinf(s_rho)) {
+        rho = RB_RHO_INIT;
+        s_rho = RB_RHO_MAX;
+    } else if (s_rho < 0) {
+        rho = RB_RHO_INIT;
+        s_rho = RB_RHO_MAX;
+    }
+    kl.rho[i] = rho;
+    kl.s_rho[i] = s_rho;
+}
+
+int rb_ekf_enqueue(rb_ctx *c, rb_map *m, const double *vel_dev, double q_abs, double loc_unc, const int *enable_dev) {
+    k_ekf<<<rb_div_up(c->kcap, 256), 256, 0, c->stream>>>(m->kl, m->st, vel_dev, c->zfm, q_abs, loc_unc, enable_dev);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+// =====================================================================================================
+// EstimateReScalingOpt (edge_tracker.cpp:1104-1140): 5 fixed-point iterations, one block
+// =====================================================================================================
+__global__ void __launch_bounds__(1024) k_rescale(KLSoA kl, MapState *st, double s_rho_min, unsigned int mnm,
+                                                  int re_escale, const int *enable) {
+    if (enable && !*enable) return;
+    __shared__ double sa[32], sb[32];
+    __shared__ double sKp, sRKp;
+    const int kn = st->kn;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (kn <= 0) {
+        if (tid == 0) st->Kp = 1;
+        return;
+    }
+    if (tid == 0) sKp = 1;
+    __syncthreads();
+    for (int iter = 0; iter < 5; iter++) {
+        const double Kp = sKp;
+        double a = 0, b = 0;
+        for (int i = tid; i < kn; i += 1024) {
+            const double s0 = kl.s_rho0[i], s = kl.s_rho[i];
+            if ((unsigned int)kl.m_num[i] < mnm || s0 <= 0 || s > s_rho_min) continue;
+            const double r = kl.rho[i], r0 = kl.rho0[i];
+            const double den = s * s + Kp * Kp * s0 * s0;
+            a += r * r / den;
+            b += r0 * r0 / den;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (lane == 0) {
+            sa[wid] = a;
+            sb[wid] = b;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double rTr = 0, rTr0 = 0;
+            for (int k = 0; k < 32; k++) {
+                rTr += sa[k];
+                rTr0 += sb[k];
+            }
+            sKp = rTr0 > 0 ? sqrt(rTr / rTr0) : 1;
+            sRKp = 1 / rTr0;
+        }
+        __syncthreads();
+    }
+    const double Kp = sKp;
+    if (re_escale) {
+        for (int i = tid; i < kn; i += 1024) {
+            kl.rho[i] = kl.rho[i] / Kp;
+            kl.s_rho[i] = kl.s_rho[i] / Kp;
+        }
+    }
+    if (tid == 0) {
+        st->Kp = Kp;
+        st->RKp = sRKp;
+    }
+}
+
+int rb_rescale_enqueue(rb_ctx *c, rb_map *m, double s_rho_min, unsigned int match_num_min, int re_escale,
+                       const int *enable_dev) {
+    k_rescale<<<1, 1024, 0, c->stream>>>(m->kl, m->st, s_rho_min, match_num_min, re_escale, enable_dev);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}

@@ -1,0 +1,50 @@
+// tracker.cuh -- device-resident state of global_tracker::Minimizer_RV and entry points of tracker.cu
+#pragma once
+#include "common.cuh"
+
+enum LMStep {
+    STEP_NONE = 0,
+    STEP_INIT_FIRST_ZERO,   // first evaluation of the zero-initialised try   (global_tracker.cpp:651-653)
+    STEP_INIT_ITER_ZERO,    // an init iteration that still needs Jacobians  (:657-683)
+    STEP_INIT_LAST_ZERO,    // last init iteration, score only; then set up the prior-initialised try (:686-700)
+    STEP_INIT_FIRST_PRIOR,  // (:700-704)
+    STEP_INIT_ITER_PRIOR,   // (:706-732)
+    STEP_INIT_LAST_PRIOR,   // + pick the better start and swap the residual buffers (:734-747)
+    STEP_MAIN_FIRST,        // first re-weighted evaluation (:755-757)
+    STEP_MAIN_ITER,         // LM iteration with Cholesky solve (:760-791)
+    STEP_MAIN_LAST          // last iteration + uncertainties / outputs (:793-816)
+};
+
+int rb_track_state_alloc(rb_ctx *c, rb_map *m);
+void rb_track_state_free(rb_map *m);
+
+struct rb_minimizer_args {
+    double match_thresh;
+    int iter_max, init_type, init_iter;
+    double reweight_distance;
+    unsigned int match_num_thresh;
+};
+
+// Enqueue the whole Minimizer_RV on c->stream.  Vel/W0 priors are read from dev pointers VW_dev[6]
+// (V then W); max_s_rho is read from old->st->s_rho_q when s_rho_from_state, else from the argument.
+int rb_minimizer_enqueue(rb_ctx *c, rb_map *fmap, rb_map *old, const double *VW_dev,
+                         const rb_minimizer_args *a, double max_s_rho, bool s_rho_from_state,
+                         unsigned int frame_count, bool frame_count_from_state);
+int rb_quantile_enqueue(rb_ctx *c, rb_map *m, double smin, double smax, double perc, int nbins);
+int rb_build_field_enqueue(rb_ctx *c, rb_map *m, int radius, float min_mod, bool min_mod_from_state);
+int rb_forward_match_enqueue(rb_ctx *c, rb_map *old, rb_map *neu);
+int rb_rotate_enqueue(rb_ctx *c, rb_map *m, const double *R_dev);
+struct DMatchArgs {       // device-resident arguments of directed_matching (after the back-rotation)
+    double Vel[3];        // BackRot*Vel
+    double RVel[9];       // BackRot*RVel*BackRot^T
+    double BackRot[9];
+};
+int rb_directed_matching_enqueue(rb_ctx *c, rb_map *neu, rb_map *old, const DMatchArgs *args_dev,
+                                 double min_thr_mod, double min_thr_ang, double max_radius,
+                                 double loc_uncertainty, const int *enable_dev);
+int rb_regularize_enqueue(rb_ctx *c, rb_map *m, double thresh, const int *enable_dev);
+int rb_ekf_enqueue(rb_ctx *c, rb_map *m, const double *vel_dev, double q_abs, double loc_unc,
+                   const int *enable_dev);
+int rb_rescale_enqueue(rb_ctx *c, rb_map *m, double s_rho_min, unsigned int match_num_min, int re_escale,
+                       const int *enable_dev);
+int rb_read_map_state(rb_map *m, MapState *host);
