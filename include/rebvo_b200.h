@@ -200,6 +200,16 @@ int64_t rb_pipeline_launch_count(const rb_pipeline *pl);
 int rb_pipeline_stage_ms(const rb_pipeline *pl, float out[6]);
 /* opaque stream handle (cudaStream_t) the pipeline launches on, for CUDA-event timing by the caller */
 void *rb_pipeline_stream(rb_pipeline *pl);
+/* CUDA-event stopwatch on the pipeline's own stream (bench.py): record slot 0..7, elapsed(a,b) in ms
+ * (synchronises on event b) */
+int rb_pipeline_event_record(rb_pipeline *pl, int slot);
+int rb_pipeline_event_elapsed(rb_pipeline *pl, int a, int b, float *ms);
+/* Measurement hook: re-run ONE scale-space pass over the pipeline's batched workspace `iters` times and
+ * return the mean CUDA-event duration per launch.  pass_id: 0 row pass (plain), 1 row pass with box
+ * average (2*nimg images), 2 column pass (2*nimg images), 3 last box + DoG, 4 rgb->gray.
+ * bytes_per_launch receives the algorithmic bytes of one launch. */
+int rb_pipeline_bench_pass(rb_pipeline *pl, int pass_id, int nimg, int iters, float *ms_per_launch,
+                           double *bytes_per_launch);
 
 #ifdef __cplusplus
 }

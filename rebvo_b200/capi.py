@@ -64,7 +64,8 @@ SYMBOLS = ["rb_ctx_create", "rb_ctx_destroy", "rb_last_error", "rb_ctx_sync", "r
            "rb_map_rotate_keylines", "rb_directed_matching", "rb_map_regularize", "rb_map_ekf_update",
            "rb_map_rescale_opt", "rb_map_set_frame_count", "rb_pipeline_create", "rb_pipeline_destroy",
            "rb_pipeline_last_error", "rb_pipeline_push", "rb_pipeline_push_dev", "rb_pipeline_reset",
-           "rb_pipeline_map", "rb_pipeline_launch_count", "rb_pipeline_stage_ms", "rb_pipeline_stream"]
+           "rb_pipeline_map", "rb_pipeline_launch_count", "rb_pipeline_stage_ms", "rb_pipeline_stream",
+           "rb_pipeline_event_record", "rb_pipeline_event_elapsed", "rb_pipeline_bench_pass"]
 
 _lib = None
 
@@ -349,6 +350,19 @@ class Pipeline:
 
     def stream(self):
         return self.L.rb_pipeline_stream(self.h_)
+
+    def event_record(self, slot):
+        self.check(self.L.rb_pipeline_event_record(self.h_, slot))
+
+    def event_elapsed(self, a, b):
+        ms = C.c_float(0)
+        self.check(self.L.rb_pipeline_event_elapsed(self.h_, a, b, C.byref(ms)))
+        return ms.value
+
+    def bench_pass(self, pass_id, nimg, iters):
+        ms, by = C.c_float(0), C.c_double(0)
+        self.check(self.L.rb_pipeline_bench_pass(self.h_, pass_id, nimg, iters, C.byref(ms), C.byref(by)))
+        return ms.value, by.value
 
     def map(self, age=0):
         """Edge map of the ring: age 0 = newest.  Returns a Map view bound to a throw-away context facade."""

@@ -280,3 +280,33 @@ int rb_dog_aux_planes(rb_ctx *c, DogWS *ws, int img) {
     RB_LAUNCH_CHECK();
     return RB_OK;
 }
+
+// measurement hook used by rb_pipeline_bench_pass
+int rb_dog_single_pass(rb_ctx *c, DogWS *ws, int pass_id, int nimg, double *bytes) {
+    const BoxPlan &p = c->plan;
+    const double N = (double)c->N;
+    switch (pass_id) {
+        case 0:
+            *bytes = 8.0 * N * nimg;   // read gray 4N, write S 4N
+            return rowscan(c, false, ws->gray, ws->S, nimg, nimg, nimg, 1, 1);
+        case 1:
+            *bytes = 8.0 * N * 2 * nimg;   // read I 4N (each tap row is re-used from L1/L2), write S 4N
+            return rowscan(c, true, ws->I, ws->S, 2 * nimg, 2 * nimg, nimg, p.d[0][1], p.d[1][1]);
+        case 2:
+            *bytes = 8.0 * N * 2 * nimg;   // read S 4N, write I 4N
+            return colscan(c, ws->S, ws->I, 2 * nimg);
+        case 3: {
+            *bytes = 16.0 * N * nimg;      // read I of both filters 8N, write img0 + dog 8N
+            dim3 grid(rb_div_up(c->w, 256), c->h, nimg);
+            k_blur_dog<<<grid, 256, 0, c->stream>>>(ws->I, ws->img0, ws->dog, nullptr, c->w, c->h, nimg, p.d[0][2],
+                                                    p.d[1][2]);
+            RB_LAUNCH_CHECK();
+            return RB_OK;
+        }
+        case 4:
+            *bytes = 7.0 * N * nimg;       // read RGB 3N, write gray 4N
+            return rb_dog_gray(c, ws, nimg);
+        default:
+            return RB_ERR_ARG;
+    }
+}

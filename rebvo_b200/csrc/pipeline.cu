@@ -42,8 +42,11 @@ struct rb_pipeline {
     long long n_pushed;   // frames pushed so far
     double t_prev;
     cudaEvent_t ev[4];
+    cudaEvent_t user_ev[8];
     float stage_ms[6];
 };
+
+int rb_dog_single_pass(rb_ctx *c, DogWS *ws, int pass_id, int nimg, double *bytes);
 
 static void set_eye(double *M, double v) {
     for (int i = 0; i < 9; i++) M[i] = 0;
@@ -242,6 +245,7 @@ extern "C" int rb_pipeline_create(rb_pipeline **out, int device, const rb_params
     RB_CUDA(cudaMalloc(&pl->nav_dev, sizeof(rb_nav) * max_batch));
     RB_CUDA(cudaMallocHost(&pl->nav_pin, sizeof(rb_nav) * max_batch));
     for (int i = 0; i < 4; i++) RB_CUDA(cudaEventCreate(&pl->ev[i]));
+    for (int i = 0; i < 8; i++) RB_CUDA(cudaEventCreate(&pl->user_ev[i]));
     if ((r = pl_reset_state(pl))) return r;
     RB_CUDA(cudaStreamSynchronize(c->stream));
     return RB_OK;
@@ -261,6 +265,8 @@ extern "C" void rb_pipeline_destroy(rb_pipeline *pl) {
     if (pl->nav_pin) cudaFreeHost(pl->nav_pin);
     for (int i = 0; i < 4; i++)
         if (pl->ev[i]) cudaEventDestroy(pl->ev[i]);
+    for (int i = 0; i < 8; i++)
+        if (pl->user_ev[i]) cudaEventDestroy(pl->user_ev[i]);
     rb_ctx_destroy(c);
     delete pl;
 }
@@ -380,4 +386,37 @@ extern "C" int rb_pipeline_push(rb_pipeline *pl, const uint8_t *rgb, const doubl
 extern "C" int rb_pipeline_push_dev(rb_pipeline *pl, const uint8_t *rgb_dev, const double *ts, int n,
                                     rb_nav *nav_out) {
     return push_impl(pl, rgb_dev, true, ts, n, nav_out);
+}
+
+extern "C" int rb_pipeline_event_record(rb_pipeline *pl, int slot) {
+    rb_ctx *c = pl->c;
+    if (slot < 0 || slot > 7) return RB_ERR_ARG;
+    RB_CUDA(cudaEventRecord(pl->user_ev[slot], c->stream));
+    return RB_OK;
+}
+extern "C" int rb_pipeline_event_elapsed(rb_pipeline *pl, int a, int b, float *ms) {
+    rb_ctx *c = pl->c;
+    if (a < 0 || a > 7 || b < 0 || b > 7) return RB_ERR_ARG;
+    RB_CUDA(cudaEventSynchronize(pl->user_ev[b]));
+    RB_CUDA(cudaEventElapsedTime(ms, pl->user_ev[a], pl->user_ev[b]));
+    return RB_OK;
+}
+extern "C" int rb_pipeline_bench_pass(rb_pipeline *pl, int pass_id, int nimg, int iters, float *ms_per_launch,
+                                      double *bytes_per_launch) {
+    rb_ctx *c = pl->c;
+    if (nimg < 1 || nimg > pl->max_batch || iters < 1) return RB_ERR_ARG;
+    int r;
+    double bytes = 0;
+    for (int i = 0; i < 3; i++)
+        if ((r = rb_dog_single_pass(c, &pl->ws, pass_id, nimg, &bytes))) return r;
+    RB_CUDA(cudaEventRecord(pl->user_ev[6], c->stream));
+    for (int i = 0; i < iters; i++)
+        if ((r = rb_dog_single_pass(c, &pl->ws, pass_id, nimg, &bytes))) return r;
+    RB_CUDA(cudaEventRecord(pl->user_ev[7], c->stream));
+    RB_CUDA(cudaEventSynchronize(pl->user_ev[7]));
+    float ms = 0;
+    RB_CUDA(cudaEventElapsedTime(&ms, pl->user_ev[6], pl->user_ev[7]));
+    *ms_per_launch = ms / iters;
+    *bytes_per_launch = bytes;
+    return RB_OK;
 }

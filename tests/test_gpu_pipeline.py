@@ -1,0 +1,104 @@
+"""Whole-pipeline parity: rb_pipeline_push (device-resident REBVO flow) against the reference's own 3-thread
+REBVO class (oracle/_ref/ref_rebvo, built from the unmodified sources) on the same synthetic 752x480 stream.
+
+Bars (north_star): identical keyline counts per frame (integer work is bit-exact), directed-matching counts equal,
+pose ATE <= 1e-3 m (here the streams are deterministic, so the observed ATE is ~1e-9); batch size must not
+change the result (frames are processed in order)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+NF = 60
+
+
+@pytest.fixture(scope="module")
+def stream():
+    from rebvo_b200 import synth
+    cam = synth.EUROC
+    seq = synth.Sequence(w=cam["w"], h=cam["h"], seed=7, zf=cam["zfx"])
+    return seq.frames(NF)
+
+
+@pytest.fixture(scope="module")
+def ref_run(stream, tmp_path_factory):
+    from oracle import refapi
+    from rebvo_b200 import synth
+    if not os.path.exists(refapi.EXE):
+        pytest.skip("oracle/_ref/ref_rebvo not built")
+    d = tmp_path_factory.mktemp("ref")
+    ts, fr = stream
+    path = str(d / "frames.bin")
+    synth.write_frames_file(path, ts, fr)
+    info, rec = refapi.run_full_rebvo(path, str(d / "out.bin"))
+    os.remove(path)
+    return info, rec
+
+
+def _gpu_run(stream, batch):
+    from rebvo_b200 import capi, synth
+    ts, fr = stream
+    pl = capi.Pipeline(capi.default_params(synth.EUROC), max_batch=batch)
+    navs = []
+    for s in range(0, NF, batch):
+        navs.append(pl.push(fr[s:s + batch], ts[s:s + batch]))
+    launches = pl.launches()
+    pl.close()
+    return np.concatenate(navs), launches
+
+
+def test_trajectory_vs_reference(built, stream, ref_run):
+    info, rec = ref_run
+    nav, launches = _gpu_run(stream, 20)
+    n = min(len(rec), NF - 1)
+    assert n >= NF - 2
+    print("ref fps %.1f, launches/frame %.1f" % (info["fps"], launches / NF))
+    kn_ref, kn_gpu = rec["kn"][:n], nav["kn"][:n]
+    assert np.array_equal(kn_ref, kn_gpu), "keyline counts differ at frames %s" % np.nonzero(kn_ref != kn_gpu)[0][:10]
+    m_ref, m_gpu = rec["matches"][1:n], nav["matches"][1:n]
+    assert np.array_equal(m_ref, m_gpu), "match counts differ: %s vs %s" % (m_ref[:10], m_gpu[:10])
+    d = rec["Pos"][:n] - nav["Pos"][:n]
+    ate = float(np.sqrt((d ** 2).sum(1).mean()))
+    mx = float(np.sqrt((d ** 2).sum(1)).max())
+    path_len = float(np.linalg.norm(np.diff(rec["Pos"][:n], axis=0), axis=1).sum())
+    print("ATE rmse %.3e m, max %.3e m over %d frames (path length %.3f)" % (ate, mx, n, path_len))
+    assert path_len > 1e-3, "degenerate trajectory"
+    assert ate <= 1e-3
+    assert ate <= 1e-7, "expected near bit-level agreement on a deterministic stream"
+    dl = np.abs(rec["PoseLie"][:n] - nav["PoseLie"][:n]).max()
+    print("max |PoseLie diff| %.3e rad" % dl)
+    assert dl <= 1e-7
+    assert np.allclose(rec["Kp"][1:n], nav["Kp"][1:n], rtol=1e-9, atol=0)
+    assert np.array_equal(rec["est_ok"][1:n] != 0, nav["estimation_ok"][1:n] != 0)
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        np.savez("gpurun_out/trajectory_parity.npz", ref_pos=rec["Pos"][:n], gpu_pos=nav["Pos"][:n], ate=ate)
+    except OSError:
+        pass
+
+
+def test_batch_size_invariance(built, stream):
+    a, _ = _gpu_run(stream, 20)
+    b, _ = _gpu_run(stream, 7)
+    c, _ = _gpu_run(stream, 1)
+    for f in ("Pos", "Pose", "kn", "matches", "Kp"):
+        assert np.array_equal(a[f], b[f]) and np.array_equal(a[f], c[f]), f
+
+
+def test_keyline_mirror_matches_reference_layout(built, stream):
+    """The 168-byte AoS mirror handed to host consumers (callback / net packer) is populated and consistent."""
+    from rebvo_b200 import capi, synth
+    ts, fr = stream
+    pl = capi.Pipeline(capi.default_params(synth.EUROC), max_batch=4)
+    nav = pl.push(fr[:4], ts[:4])
+    m = pl.map(0)
+    kl = m.keylines()
+    assert len(kl) == nav["kn"][3] and capi.KEYLINE.itemsize == 168
+    mask = m.mask()
+    assert (mask >= 0).sum() == len(kl)
+    assert np.array_equal(mask.ravel()[kl["p_inx"]], np.arange(len(kl)))
+    assert (kl["m_id"] >= 0).sum() == nav["matches"][3] or (kl["m_id"] >= 0).sum() >= nav["matches"][3]
+    assert np.all(kl["rho"] > 0) and np.all(kl["s_rho"] > 0)
+    pl.close()
