@@ -158,19 +158,18 @@ def bench_reference(args):
 
 def bench_ours(args):
     import torch
-    rank, local_rank, world = rank_info()
+    from rebvo_b200 import multi
+    rank, local_rank, world = multi.rank_info()
     dist = None
     if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = multi.init("nccl", device=torch.device("cuda", local_rank))
     dev = local_rank if world > 1 else 0
     torch.cuda.set_device(dev)
     from rebvo_b200 import capi, synth
     B, K, W = args.batch, args.steps, args.warmup
     total = B * (K + W)
-    ts, base, idx = make_stream(7 + rank, total)
+    ts, base, idx = make_stream(multi.stream_seed(rank), total)
     cam = synth.EUROC
     h, w = cam["h"], cam["w"]
     fbytes = h * w * 3
@@ -229,18 +228,13 @@ def bench_ours(args):
     clocks = sampler.summary(c0, c1)
     same = bool(np.array_equal(nav_dev["Pos"], nav_e2e["Pos"]))
 
-    t_max, t_e2e_max = t_dev_ms, t_e2e_ms
-    if dist is not None:
-        t = torch.tensor([t_dev_ms, t_e2e_ms], device="cuda:%d" % dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_max, t_e2e_max = float(t[0]), float(t[1])
+    t_max, t_e2e_max = multi.max_over_ranks(dist, [t_dev_ms, t_e2e_ms], device="cuda:%d" % dev)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-    frames = K * B * world
-    value = frames / (t_max * 1e-3)
-    e2e = frames / (t_e2e_max * 1e-3)
+    value = multi.aggregate_fps(K * B, world, t_max)
+    e2e = multi.aggregate_fps(K * B, world, t_e2e_max)
     peak, peak_src = peaks()
     dom = "k_rowscan<avg>"
     roof = {"bound": "hbm", "kernel": dom, "achieved": passes[dom]["gbs"], "peak": peak, "unit": "GB/s",

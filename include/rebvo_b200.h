@@ -132,6 +132,9 @@ int rb_map_get_plane(rb_map *m, int which, float *out);
 /* edge_finder::detect (edge_finder.cpp:342-365): UpdateThresh + build_mask + join_edges.
  * tresh / l_kl_num are the caller-held feedback state of FirstThr (rebvo_first_t.cpp:92-94). */
 int rb_map_detect(rb_map *m, const rb_detect_params *p, double *tresh, int *l_kl_num, int *kn_out);
+/* same, reading the scale space of another ring object (the reference passes `sspace *ss` to detect()) */
+int rb_map_detect_ss(rb_map *m, rb_map *ss, const rb_detect_params *p, double *tresh, int *l_kl_num,
+                     int *kn_out);
 /* edge_finder::reEstimateThresh (edge_finder.cpp:373-405) */
 int rb_map_reestimate_thresh(rb_map *m, int knum, int nbins, float *out_thresh);
 int rb_map_knum(rb_map *m, int *kn);

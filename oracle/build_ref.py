@@ -153,6 +153,25 @@ def build(level_b=True, force=False):
     return True
 
 
+def build_shim_driver(force=False):
+    """tests/shim_driver.cpp: the reference's call sequence compiled against include/rebvo_b200_shim.hpp with
+    the reference's own non-hot-path headers (Image<>, cam_model, TooN).  Output: oracle/_ref/shim_driver."""
+    if not os.path.isdir(REF):
+        return False
+    repo = os.path.dirname(HERE)
+    src = os.path.join(repo, "tests", "shim_driver.cpp")
+    exe = os.path.join(OUT, "shim_driver")
+    lib = os.path.join(repo, "rebvo_b200", "librebvo_b200.so")
+    deps = [src, os.path.join(repo, "include", "rebvo_b200_shim.hpp"), os.path.join(repo, "include", "rebvo_b200.h"), lib]
+    if not force and os.path.exists(exe) and all(os.path.getmtime(exe) > os.path.getmtime(d) for d in deps):
+        return True
+    toon = os.path.join(OUT, "toon")
+    run(["g++", "-std=c++11", "-O2", "-w", "-include", os.path.join(OUT, "shim", "fix_gcc13.h"),
+         "-I" + os.path.join(OUT, "shim"), "-I" + os.path.join(repo, "include"), "-I" + os.path.join(REF, "include"),
+         "-I" + toon, src, "-o", exe, lib, "-Wl,-rpath,$ORIGIN/../../rebvo_b200"])
+    return True
+
+
 if __name__ == "__main__":
     ok = build(level_b="--no-level-b" not in sys.argv, force="--force" in sys.argv)
     print("reference oracle built" if ok else "reference sources not present; using prebuilt oracle/_ref if any")

@@ -193,6 +193,7 @@ extern "C" int rb_ctx_create(rb_ctx **out, int device, const rb_camera *cam, dou
     CK(cudaMalloc(&c->dev_small, 1 << 16));
     CK(cudaMemset(c->dev_small, 0, 1 << 16));
     if ((r = rb_detect_upload_pinv(c))) return fail(r);
+    if ((r = rb_dog_make_tables(c))) return fail(r);
 #undef CK
     *out = c;
     return RB_OK;
@@ -210,6 +211,7 @@ extern "C" void rb_ctx_destroy(rb_ctx *c) {
     cudaFree(c->red_part);
     cudaFree(c->ticket);
     cudaFree(c->dev_small);
+    cudaFree(c->boxtab);
     if (c->pinned) cudaFreeHost(c->pinned);
     delete c;
 }
@@ -353,16 +355,23 @@ static int read_state(rb_map *m, MapState *host) {
     return RB_OK;
 }
 
+extern "C" int rb_map_detect_ss(rb_map *m, rb_map *ss, const rb_detect_params *p, double *tresh, int *l_kl_num,
+                                int *kn_out);
 extern "C" int rb_map_detect(rb_map *m, const rb_detect_params *p, double *tresh, int *l_kl_num, int *kn_out) {
+    return rb_map_detect_ss(m, m, p, tresh, l_kl_num, kn_out);
+}
+extern "C" int rb_map_detect_ss(rb_map *m, rb_map *ss, const rb_detect_params *p, double *tresh, int *l_kl_num,
+                                int *kn_out) {
+    if (!m || !ss) return RB_ERR_ARG;
     rb_ctx *c = m->c;
-    if (!m->img0 || !p || !tresh || !l_kl_num) return RB_ERR_ARG;
+    if (!ss->img0 || ss->c != c || !p || !tresh || !l_kl_num) return RB_ERR_ARG;
     DetChain *ch_dev = (DetChain *)((char *)c->dev_small + RB_DS_CHAIN);
     DetChain *ch_host = (DetChain *)((char *)c->pinned + RB_DS_CHAIN);
     ch_host->tresh = *tresh;
     ch_host->l_kl_num = *l_kl_num;
     ch_host->pad = 0;
     RB_CUDA(cudaMemcpyAsync(ch_dev, ch_host, sizeof(DetChain), cudaMemcpyHostToDevice, c->stream));
-    int r = rb_detect_enqueue(c, m, m->img0, m->dog, p, ch_dev);
+    int r = rb_detect_enqueue(c, m, ss->img0, ss->dog, p, ch_dev);
     if (r) return r;
     RB_CUDA(cudaMemcpyAsync(ch_host, ch_dev, sizeof(DetChain), cudaMemcpyDeviceToHost, c->stream));
     RB_CUDA(cudaStreamSynchronize(c->stream));

@@ -88,6 +88,7 @@ struct rb_ctx {
     unsigned int *ticket;  // last-block-done counters
     void *pinned;        // small pinned host buffer for scalar read-back
     void *dev_small;     // small device buffer for scalar parameters / results (64 KiB, zero-initialised)
+    float *boxtab;       // 6 x 64 reciprocal clipped-area tables (iimage::build_average), see dog.cu
 };
 // layout of rb_ctx::dev_small / pinned (byte offsets)
 #define RB_DS_REEST 0        // int[2 + nbins + 1]  reEstimateThresh min/max bits + histogram
@@ -181,6 +182,7 @@ void rb_dogws_free(DogWS *ws);
 int rb_dog_gray(rb_ctx *c, DogWS *ws, int nimg);                 // rgb -> gray
 int rb_dog_build_batch(rb_ctx *c, DogWS *ws, int nimg);          // gray -> img0, dog
 int rb_dog_aux_planes(rb_ctx *c, DogWS *ws, int img);            // Img(1), dx, dy into ws->aux
+int rb_dog_make_tables(rb_ctx *c);
 // detect.cu
 int rb_detect_enqueue(rb_ctx *c, rb_map *m, const float *img0, const float *dog,
                       const rb_detect_params *p, DetChain *chain_dev);

@@ -278,17 +278,19 @@ __global__ void __launch_bounds__(256) k_nm_histo(const float *__restrict__ n_m,
     __shared__ bool last;
     if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (last && threadIdx.x == 0) {
-        __threadfence();
+    if (!last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sh[i] = __ldcg(&histo[i]);   // whole histogram in one go
+    __syncthreads();
+    if (threadIdx.x == 0) {
         float ret = 0.f;
         if (kn > 0) {
             int i = 0;
-            volatile int *vh = histo;
             // for(int a=0;i<n && a<knum;i++,a+=histo[i]);  -- skips bin 0, may index histo[n] (ignored: the
             // loop ends on i<n regardless)
             for (int a = 0; i < n && a < knum;) {
                 i++;
-                a += (i < n) ? vh[i] : 0;
+                a += (i < n) ? sh[i] : 0;
             }
             ret = max_dog - (float)i * range / (float)n;   // :403
         }

@@ -21,35 +21,31 @@
 // yt=y-d2-1; a tap whose xl / yt is negative is absent; the subtraction order is A-B-C+D except in the
 // bottom band (y >= h-d2) where the reference writes A-C-B+D; the factor is a=1.0/(d*d) in the centre
 // region and the per-pixel reciprocal box area of iimage::build_average (iimage.cpp:134-179) elsewhere.
+//
+// The code is branch-free on purpose: the four loads are unconditional (an absent tap reads a clamped address and
+// is dropped by a select) and the factor comes from a (d2+1)x(d2+1) table of the reciprocal clipped areas
+// tab[(cy-d2-1)*8 + (cx-d2-1)] = (float)(1.0/(double)(float)(cx*cy)) (host-computed, staged in shared memory; its
+// centre entry cx=cy=d equals a).  With branches around each pixel the compiler cannot hoist the loads of the
+// next pixels, and a 32x32 tile degenerates into 32 dependent L2 round trips.
+#define BOX_TAB_W 8
+#define BOX_TAB_N (BOX_TAB_W * BOX_TAB_W)
 __device__ __forceinline__ float box_avg(const float *__restrict__ I, int x, int y, int w, int h, int d,
-                                         int d2, float a) {
+                                         int d2, const float *__restrict__ tab) {
     const bool left = x < d2 + 1, right = x >= w - d2;
     const bool top = y < d2 + 1, bottom = y >= h - d2;
     const int xr = right ? w - 1 : x + d2;
     const int yb = bottom ? h - 1 : y + d2;
-    const int xl = x - d2 - 1, yt = y - d2 - 1;
-    float r = I[yb * w + xr];
-    if (!(left | right | top | bottom)) {
-        r = r - I[yb * w + xl];
-        r = r - I[yt * w + xr];
-        r = r + I[yt * w + xl];
-        return r * a;
-    }
-    if (bottom) {
-        if (!top) r = r - I[yt * w + xr];           // A - C
-        if (!left) r = r - I[yb * w + xl];          //   - B
-        if (!top && !left) r = r + I[yt * w + xl];  //   + D
-    } else {
-        if (!left) r = r - I[yb * w + xl];          // A - B
-        if (!top) r = r - I[yt * w + xr];           //   - C
-        if (!top && !left) r = r + I[yt * w + xl];  //   + D
-    }
-    // build_average: div = (float)(1.0 / (double)(float)(cx*cy)), cx/cy = clipped box extents
-    const int cx = left ? x + d2 + 1 : (right ? w - x + d2 : d);
+    const int xl = left ? 0 : x - d2 - 1, yt = top ? 0 : y - d2 - 1;
+    const float A = I[yb * w + xr], B = I[yb * w + xl], C = I[yt * w + xr], D = I[yt * w + xl];
+    const float t1 = bottom ? C : B, t2 = bottom ? B : C;   // bottom band: A-C-B+D, elsewhere A-B-C+D
+    const bool h1 = bottom ? !top : !left, h2 = bottom ? !left : !top;
+    float r = A;
+    r = h1 ? r - t1 : r;
+    r = h2 ? r - t2 : r;
+    r = (!top && !left) ? r + D : r;
+    const int cx = left ? x + d2 + 1 : (right ? w - x + d2 : d);   // clipped box extents (build_average)
     const int cy = top ? y + d2 + 1 : (bottom ? h - y + d2 : d);
-    const float area = (float)(cx * cy);
-    const float div = (float)(1.0 / (double)area);
-    return r * div;
+    return r * tab[(cy - d2 - 1) * BOX_TAB_W + (cx - d2 - 1)];
 }
 
 // Image<float>::ConvertRGB2BW (image.h:197-203): b+g+r as float, 4 pixels per thread
@@ -73,8 +69,10 @@ __global__ void __launch_bounds__(256) k_rgb2gray(const uint32_t *__restrict__ r
 template <bool AVG>
 __global__ void __launch_bounds__(128) k_rowscan(const float *__restrict__ in, float *__restrict__ out,
                                                  int w, int h, int nimg, int in_mod, int nper, int d_f0,
-                                                 int d_f1) {
+                                                 int d_f1, const float *__restrict__ tab_f0,
+                                                 const float *__restrict__ tab_f1) {
     __shared__ float tile[4][32][33];
+    __shared__ float stab[4][BOX_TAB_N];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gw = blockIdx.x * 4 + warp;
     const int bands = (h + 31) >> 5;
@@ -83,21 +81,30 @@ __global__ void __launch_bounds__(128) k_rowscan(const float *__restrict__ in, f
     const size_t N = (size_t)w * h;
     const float *__restrict__ I = in + (size_t)(img % in_mod) * N;
     float *__restrict__ O = out + (size_t)img * N;
-    const int d = (img / nper) ? d_f1 : d_f0;
+    const bool f1 = (img / nper) != 0;
+    const int d = f1 ? d_f1 : d_f0;
     const int d2 = d / 2;
-    const float a = (float)(1.0 / (double)(d * d));
+    if (AVG) {
+        const float *__restrict__ tg = f1 ? tab_f1 : tab_f0;
+        stab[warp][lane] = tg[lane];
+        stab[warp][lane + 32] = tg[lane + 32];
+        __syncwarp();
+    }
+    const float *tab = stab[warp];
     const int y0 = band * 32;
     float v[32];
     float carry = 0.f;
 
+    // branch-free tile production: clamped coordinates + select, so that all loads of a tile are in flight at once
 #define LOAD_TILE(X0)                                                           \
     {                                                                           \
         const int x = (X0) + lane;                                              \
+        const int xc = x < w ? x : w - 1;                                       \
         _Pragma("unroll") for (int r = 0; r < 32; r++) {                        \
             const int y = y0 + r;                                               \
-            float t = 0.f;                                                      \
-            if (y < h && x < w) t = AVG ? box_avg(I, x, y, w, h, d, d2, a) : I[(size_t)y * w + x]; \
-            v[r] = t;                                                           \
+            const int yc = y < h ? y : h - 1;                                   \
+            const float t = AVG ? box_avg(I, xc, yc, w, h, d, d2, tab) : I[(size_t)yc * w + xc]; \
+            v[r] = (y < h && x < w) ? t : 0.f;                                  \
         }                                                                       \
     }
     LOAD_TILE(0);
@@ -156,15 +163,19 @@ __global__ void __launch_bounds__(64) k_colscan(const float4 *__restrict__ in, f
 // Last box of both filters + sspace::build_dog (sspace.cpp:63-70): img0, dog = img1 - img0
 __global__ void __launch_bounds__(256) k_blur_dog(const float *__restrict__ I, float *__restrict__ img0,
                                                   float *__restrict__ dog, float *__restrict__ img1_opt,
-                                                  int w, int h, int B, int d0, int d1) {
+                                                  int w, int h, int B, int d0, int d1,
+                                                  const float *__restrict__ tab0, const float *__restrict__ tab1) {
+    __shared__ float st0[BOX_TAB_N], st1[BOX_TAB_N];
+    if (threadIdx.x < BOX_TAB_N) st0[threadIdx.x] = tab0[threadIdx.x];
+    else if (threadIdx.x < 2 * BOX_TAB_N) st1[threadIdx.x - BOX_TAB_N] = tab1[threadIdx.x - BOX_TAB_N];
+    __syncthreads();
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     const int b = blockIdx.z;
     if (x >= w) return;
     const size_t N = (size_t)w * h;
-    const float a0 = (float)(1.0 / (double)(d0 * d0)), a1 = (float)(1.0 / (double)(d1 * d1));
-    const float v0 = box_avg(I + (size_t)b * N, x, y, w, h, d0, d0 / 2, a0);
-    const float v1 = box_avg(I + (size_t)(B + b) * N, x, y, w, h, d1, d1 / 2, a1);
+    const float v0 = box_avg(I + (size_t)b * N, x, y, w, h, d0, d0 / 2, st0);
+    const float v1 = box_avg(I + (size_t)(B + b) * N, x, y, w, h, d1, d1 / 2, st1);
     const size_t o = (size_t)b * N + (size_t)y * w + x;
     img0[o] = v0;
     dog[o] = v1 - v0;
@@ -222,16 +233,50 @@ int rb_dog_gray(rb_ctx *c, DogWS *ws, int nimg) {
     return RB_OK;
 }
 
-static int rowscan(rb_ctx *c, bool avg, const float *in, float *out, int nimg, int in_mod, int nper,
-                   int d0, int d1) {
+// stage < 0: plain row scan of the input; stage 0..1: row scan of box `stage` of both filters
+static int rowscan(rb_ctx *c, int stage, const float *in, float *out, int nimg, int in_mod, int nper) {
     const int bands = (c->h + 31) / 32;
     const int warps = nimg * bands;
     const int blocks = rb_div_up(warps, 4);
-    if (avg)
-        k_rowscan<true><<<blocks, 128, 0, c->stream>>>(in, out, c->w, c->h, nimg, in_mod, nper, d0, d1);
+    if (stage >= 0)
+        k_rowscan<true><<<blocks, 128, 0, c->stream>>>(in, out, c->w, c->h, nimg, in_mod, nper, c->plan.d[0][stage],
+                                                       c->plan.d[1][stage], c->boxtab + (0 * 3 + stage) * BOX_TAB_N,
+                                                       c->boxtab + (1 * 3 + stage) * BOX_TAB_N);
     else
-        k_rowscan<false><<<blocks, 128, 0, c->stream>>>(in, out, c->w, c->h, nimg, in_mod, nper, d0, d1);
+        k_rowscan<false><<<blocks, 128, 0, c->stream>>>(in, out, c->w, c->h, nimg, in_mod, nper, 1, 1, nullptr, nullptr);
     RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+static int blur_dog(rb_ctx *c, DogWS *ws, int nimg, float *img1_opt) {
+    dim3 grid(rb_div_up(c->w, 256), c->h, nimg);
+    k_blur_dog<<<grid, 256, 0, c->stream>>>(ws->I, ws->img0, ws->dog, img1_opt, c->w, c->h, nimg, c->plan.d[0][2],
+                                            c->plan.d[1][2], c->boxtab + (0 * 3 + 2) * BOX_TAB_N,
+                                            c->boxtab + (1 * 3 + 2) * BOX_TAB_N);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+// reciprocal clipped-area tables of iimage::build_average for the six boxes of the plan (see box_avg)
+int rb_dog_make_tables(rb_ctx *c) {
+    float host[6 * BOX_TAB_N];
+    for (int f = 0; f < 2; f++)
+        for (int i = 0; i < 3; i++) {
+            const int d = c->plan.d[f][i], d2 = d / 2;
+            if (d2 + 1 > BOX_TAB_W) {
+                snprintf(c->err, sizeof(c->err), "box width %d too large for this build", d);
+                return RB_ERR_ARG;
+            }
+            float *t = host + (f * 3 + i) * BOX_TAB_N;
+            for (int k = 0; k < BOX_TAB_N; k++) t[k] = 0.f;
+            for (int cy = d2 + 1; cy <= d; cy++)
+                for (int cx = d2 + 1; cx <= d; cx++) {
+                    const float area = (float)(cx * cy);   // div(x,y)=cx*cy stored in a float image, then 1.0/div
+                    t[(cy - d2 - 1) * BOX_TAB_W + (cx - d2 - 1)] = (float)(1.0 / (double)area);
+                }
+        }
+    RB_CUDA(cudaMalloc(&c->boxtab, sizeof(host)));
+    RB_CUDA(cudaMemcpy(c->boxtab, host, sizeof(host), cudaMemcpyHostToDevice));
     return RB_OK;
 }
 
@@ -247,34 +292,27 @@ static int colscan(rb_ctx *c, const float *in, float *out, int nimg) {
 // sspace::build for nimg images of the workspace (gray already present)
 int rb_dog_build_batch(rb_ctx *c, DogWS *ws, int nimg) {
     if (nimg < 1 || nimg > ws->B) return RB_ERR_ARG;
-    const BoxPlan &p = c->plan;
     int r;
     // iimage::load(in): identical for both filters -> computed once
-    if ((r = rowscan(c, false, ws->gray, ws->S, nimg, nimg, nimg, 1, 1))) return r;
+    if ((r = rowscan(c, -1, ws->gray, ws->S, nimg, nimg, nimg))) return r;
     if ((r = colscan(c, ws->S, ws->I0, nimg))) return r;
     // box 0 of both filters reads the shared integral; image index = filter * nimg + b
-    if ((r = rowscan(c, true, ws->I0, ws->S, 2 * nimg, nimg, nimg, p.d[0][0], p.d[1][0]))) return r;
+    if ((r = rowscan(c, 0, ws->I0, ws->S, 2 * nimg, nimg, nimg))) return r;
     if ((r = colscan(c, ws->S, ws->I, 2 * nimg))) return r;
     // box 1
-    if ((r = rowscan(c, true, ws->I, ws->S, 2 * nimg, 2 * nimg, nimg, p.d[0][1], p.d[1][1]))) return r;
+    if ((r = rowscan(c, 1, ws->I, ws->S, 2 * nimg, 2 * nimg, nimg))) return r;
     if ((r = colscan(c, ws->S, ws->I, 2 * nimg))) return r;
     // box 2 + DoG.  Filter f of image b lives at I[(f*nimg + b)*N]
-    dim3 grid(rb_div_up(c->w, 256), c->h, nimg);
-    k_blur_dog<<<grid, 256, 0, c->stream>>>(ws->I, ws->img0, ws->dog, nullptr, c->w, c->h, nimg,
-                                            p.d[0][2], p.d[1][2]);
-    RB_LAUNCH_CHECK();
-    return RB_OK;
+    return blur_dog(c, ws, nimg, nullptr);
 }
 
 // Img(1), dx, dy of image `img` into ws->aux (debug accessor; needs ws->I from the last build with
 // the same nimg = ws_last_nimg, passed through B of the call: only valid for nimg == 1 workspaces)
 int rb_dog_aux_planes(rb_ctx *c, DogWS *ws, int img) {
     if (ws->B != 1 || img != 0) return RB_ERR_ARG;
-    const BoxPlan &p = c->plan;
+    int r = blur_dog(c, ws, 1, ws->aux);
+    if (r) return r;
     dim3 grid(rb_div_up(c->w, 256), c->h, 1);
-    k_blur_dog<<<grid, 256, 0, c->stream>>>(ws->I, ws->img0, ws->dog, ws->aux, c->w, c->h, 1, p.d[0][2],
-                                            p.d[1][2]);
-    RB_LAUNCH_CHECK();
     k_gradient<<<grid, 256, 0, c->stream>>>(ws->img0, ws->aux + c->N, ws->aux + 2 * (size_t)c->N, c->w,
                                             c->h);
     RB_LAUNCH_CHECK();
@@ -283,26 +321,20 @@ int rb_dog_aux_planes(rb_ctx *c, DogWS *ws, int img) {
 
 // measurement hook used by rb_pipeline_bench_pass
 int rb_dog_single_pass(rb_ctx *c, DogWS *ws, int pass_id, int nimg, double *bytes) {
-    const BoxPlan &p = c->plan;
     const double N = (double)c->N;
     switch (pass_id) {
         case 0:
             *bytes = 8.0 * N * nimg;   // read gray 4N, write S 4N
-            return rowscan(c, false, ws->gray, ws->S, nimg, nimg, nimg, 1, 1);
+            return rowscan(c, -1, ws->gray, ws->S, nimg, nimg, nimg);
         case 1:
             *bytes = 8.0 * N * 2 * nimg;   // read I 4N (each tap row is re-used from L1/L2), write S 4N
-            return rowscan(c, true, ws->I, ws->S, 2 * nimg, 2 * nimg, nimg, p.d[0][1], p.d[1][1]);
+            return rowscan(c, 1, ws->I, ws->S, 2 * nimg, 2 * nimg, nimg);
         case 2:
             *bytes = 8.0 * N * 2 * nimg;   // read S 4N, write I 4N
             return colscan(c, ws->S, ws->I, 2 * nimg);
-        case 3: {
+        case 3:
             *bytes = 16.0 * N * nimg;      // read I of both filters 8N, write img0 + dog 8N
-            dim3 grid(rb_div_up(c->w, 256), c->h, nimg);
-            k_blur_dog<<<grid, 256, 0, c->stream>>>(ws->I, ws->img0, ws->dog, nullptr, c->w, c->h, nimg, p.d[0][2],
-                                                    p.d[1][2]);
-            RB_LAUNCH_CHECK();
-            return RB_OK;
-        }
+            return blur_dog(c, ws, nimg, nullptr);
         case 4:
             *bytes = 7.0 * N * nimg;       // read RGB 3N, write gray 4N
             return rb_dog_gray(c, ws, nimg);

@@ -157,10 +157,13 @@ RB_HD void chol6_compute(const double *M, Chol6 *ch) {
     for (int i = 0; i < 36; i++) ch->c[i] = M[i];
     double *a = ch->c;
     const int n = 6;
+#pragma unroll
     for (int col = 0; col < n; col++) {
         double inv_diag = 1;
+#pragma unroll
         for (int row = col; row < n; row++) {
             double val = a[row * 6 + col];
+#pragma unroll
             for (int col2 = 0; col2 < col; col2++) val -= a[col2 * 6 + col] * a[row * 6 + col2];
             if (row == col) {
                 a[row * 6 + col] = val;
@@ -180,14 +183,19 @@ RB_HD void chol6_compute(const double *M, Chol6 *ch) {
 RB_HD void chol6_backsub(const Chol6 *ch, const double *v, double *x) {
     const double *a = ch->c;
     double y[6];
+#pragma unroll
     for (int i = 0; i < 6; i++) {
         double val = v[i];
+#pragma unroll
         for (int j = 0; j < i; j++) val -= a[i * 6 + j] * y[j];
         y[i] = val;
     }
+#pragma unroll
     for (int i = 0; i < 6; i++) y[i] /= a[i * 6 + i];
+#pragma unroll
     for (int i = 5; i >= 0; i--) {
         double val = y[i];
+#pragma unroll
         for (int j = i + 1; j < 6; j++) val -= a[j * 6 + i] * x[j];
         x[i] = val;
     }

@@ -5,6 +5,7 @@
 // integration and the NavData record are all computed by 1-thread kernels from device state, so a batch of
 // frames costs one H2D copy, one stream of launches and one D2H copy of the nav records.
 #include <math.h>
+#include <stdlib.h>
 #include <new>
 
 #include "common.cuh"
@@ -44,6 +45,12 @@ struct rb_pipeline {
     cudaEvent_t ev[4];
     cudaEvent_t user_ev[8];
     float stage_ms[6];
+    struct FrameArgs *fa_dev, *fa_pin;
+    // one instantiated CUDA graph per (batch size, parity of the first frame): the kernel sequence of a batch is
+    // static once the per-frame scalars live in fa_dev
+    cudaGraphExec_t *gexec;       // [2 * (max_batch + 1)]
+    int *glaunches;               // kernel launches inside each graph
+    bool use_graph;
 };
 
 int rb_dog_single_pass(rb_ctx *c, DogWS *ws, int pass_id, int nimg, double *bytes);
@@ -58,8 +65,17 @@ __device__ void d_eye(double *M, double v) {
     M[0] = M[4] = M[8] = v;
 }
 
+// per-frame scalars that change from push to push; kept in device memory so that the kernel arguments of a batch
+// are constant and the whole batch can be replayed as one CUDA graph
+struct FrameArgs {
+    double t, dt;
+    unsigned int frame_count;   // global_tracker::FrameCount of the reference ring slot serving this frame
+    int pad;
+};
+
 // start of the SecondThread loop body (:167-169) + minimiser priors
-__global__ void k_frame_pre(FrameState *fs) {
+__global__ void k_frame_pre(FrameState *fs, const FrameArgs *fa, MapState *nst) {
+    nst->frame_count = fa->frame_count;
     d_eye(fs->P_V, 1e50);
     d_eye(fs->P_W, 1e50);
     d_eye(fs->R, 1);
@@ -132,7 +148,8 @@ __global__ void k_frame_post_match(FrameState *fs, const MapState *nst, int matc
 
 // pose integration + NavData (:545-585)
 __global__ void k_frame_finish(FrameState *fs, const MapState *nst, const MapState *ost, const TrackState *ts,
-                               rb_nav *nav, double t, double dt_frame) {
+                               rb_nav *nav, const FrameArgs *fa) {
+    const double t = fa->t, dt_frame = fa->dt;
     if (fs->do_map) {
         fs->Kp = nst->Kp;      // Kp=EstimateReScalingOpt(P_Kp,...)
         fs->P_Kp = nst->RKp;
@@ -177,10 +194,10 @@ __global__ void k_frame_finish(FrameState *fs, const MapState *nst, const MapSta
 }
 
 // record for the very first frame (it only initialises the ring, :109-121)
-__global__ void k_frame_first(const FrameState *fs, const MapState *nst, rb_nav *nav, double t) {
+__global__ void k_frame_first(const FrameState *fs, const MapState *nst, rb_nav *nav, const FrameArgs *fa) {
     rb_nav o;
     memset(&o, 0, sizeof(o));
-    o.t = t;
+    o.t = fa->t;
     for (int i = 0; i < 9; i++) {
         o.Rot[i] = (i % 4 == 0) ? 1 : 0;
         o.Pose[i] = fs->Pose[i];
@@ -244,6 +261,17 @@ extern "C" int rb_pipeline_create(rb_pipeline **out, int device, const rb_params
     RB_CUDA(cudaMalloc(&pl->fs, sizeof(FrameState)));
     RB_CUDA(cudaMalloc(&pl->nav_dev, sizeof(rb_nav) * max_batch));
     RB_CUDA(cudaMallocHost(&pl->nav_pin, sizeof(rb_nav) * max_batch));
+    RB_CUDA(cudaMalloc(&pl->fa_dev, sizeof(FrameArgs) * max_batch));
+    RB_CUDA(cudaMallocHost(&pl->fa_pin, sizeof(FrameArgs) * max_batch));
+    pl->gexec = new (std::nothrow) cudaGraphExec_t[2 * (max_batch + 1)];
+    pl->glaunches = new (std::nothrow) int[2 * (max_batch + 1)];
+    if (!pl->gexec || !pl->glaunches) return RB_ERR_ARG;
+    for (int i = 0; i < 2 * (max_batch + 1); i++) {
+        pl->gexec[i] = nullptr;
+        pl->glaunches[i] = 0;
+    }
+    const char *ng = getenv("REBVO_B200_NO_GRAPH");
+    pl->use_graph = !(ng && ng[0] == '1');
     for (int i = 0; i < 4; i++) RB_CUDA(cudaEventCreate(&pl->ev[i]));
     for (int i = 0; i < 8; i++) RB_CUDA(cudaEventCreate(&pl->user_ev[i]));
     if ((r = pl_reset_state(pl))) return r;
@@ -263,6 +291,14 @@ extern "C" void rb_pipeline_destroy(rb_pipeline *pl) {
     cudaFree(pl->fs);
     cudaFree(pl->nav_dev);
     if (pl->nav_pin) cudaFreeHost(pl->nav_pin);
+    cudaFree(pl->fa_dev);
+    if (pl->fa_pin) cudaFreeHost(pl->fa_pin);
+    if (pl->gexec) {
+        for (int i = 0; i < 2 * (pl->max_batch + 1); i++)
+            if (pl->gexec[i]) cudaGraphExecDestroy(pl->gexec[i]);
+        delete[] pl->gexec;
+    }
+    delete[] pl->glaunches;
     for (int i = 0; i < 4; i++)
         if (pl->ev[i]) cudaEventDestroy(pl->ev[i]);
     for (int i = 0; i < 8; i++)
@@ -290,12 +326,11 @@ extern "C" int rb_pipeline_reset(rb_pipeline *pl) {
 }
 
 // one frame of the tracker/mapper stage: new = maps[idx&1] (already detected), old = the other map
-static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, long long n, double t, double dt_frame,
-                       rb_nav *nav_slot) {
+static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, const FrameArgs *fa, rb_nav *nav_slot) {
     rb_ctx *c = pl->c;
     const rb_params &p = pl->p;
     int r;
-    k_frame_pre<<<1, 1, 0, c->stream>>>(pl->fs);
+    k_frame_pre<<<1, 1, 0, c->stream>>>(pl->fs, fa, neu->st);
     RB_LAUNCH_CHECK();
     // :172  s_rho_q = old_buf.ef->EstimateQuantile(RHO_MIN,RHO_MAX,QCutOffQuantile,QCutOffNumBins)
     if ((r = rb_quantile_enqueue(c, old, RB_RHO_MIN, RB_RHO_MAX, p.QCutOffQuantile, p.QCutOffNumBins))) return r;
@@ -309,9 +344,8 @@ static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, long long n, d
     a.init_iter = p.TrackerInitIterNum;
     a.reweight_distance = p.ReweigthDistance;
     a.match_num_thresh = p.MatchNumThresh;
-    // FrameCount of the reference's ring slot serving frame n (8 slots, slot = (n+1)%8): (n-1)/8
-    const unsigned int frame_count = (unsigned int)((n - 1) / 8);
-    if ((r = rb_minimizer_enqueue(c, neu, old, pl->fs->VW, &a, 0.0, true, frame_count, false))) return r;
+    // FrameCount comes from fa (written into neu->st by k_frame_pre)
+    if ((r = rb_minimizer_enqueue(c, neu, old, pl->fs->VW, &a, 0.0, true, 0, true))) return r;
     k_frame_post_min<<<1, 1, 0, c->stream>>>(pl->fs, neu->ts);
     RB_LAUNCH_CHECK();
     // :354  FordwardMatch ; :369 rotate_keylines(R0)
@@ -327,8 +361,34 @@ static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, long long n, d
     if ((r = rb_regularize_enqueue(c, neu, p.RegularizeThresh, &pl->fs->do_map))) return r;
     if ((r = rb_ekf_enqueue(c, neu, pl->fs->V, p.ReshapeQAbsolute, p.LocationUncertainty, &pl->fs->do_map))) return r;
     if ((r = rb_rescale_enqueue(c, neu, RB_RHO_MAX, 1, p.DoReScaling > 0 ? 1 : 0, &pl->fs->do_map))) return r;
-    k_frame_finish<<<1, 1, 0, c->stream>>>(pl->fs, neu->st, old->st, neu->ts, nav_slot, t, dt_frame);
+    k_frame_finish<<<1, 1, 0, c->stream>>>(pl->fs, neu->st, old->st, neu->ts, nav_slot, fa);
     RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+// everything of a batch after the H2D copy: gray, batched scale space, then per frame detect + track + map
+static int enqueue_batch(rb_pipeline *pl, int n, long long first_frame, bool with_events) {
+    rb_ctx *c = pl->c;
+    const rb_params &p = pl->p;
+    int r;
+    if ((r = rb_dog_gray(c, &pl->ws, n))) return r;
+    if (with_events) RB_CUDA(cudaEventRecord(pl->ev[1], c->stream));
+    if ((r = rb_dog_build_batch(c, &pl->ws, n))) return r;
+    if (with_events) RB_CUDA(cudaEventRecord(pl->ev[2], c->stream));
+    for (int i = 0; i < n; i++) {
+        const long long fr = first_frame + i;
+        rb_map *neu = pl->maps[fr & 1], *old = pl->maps[(fr + 1) & 1];
+        const float *img0 = pl->ws.img0 + (size_t)i * c->N, *dog = pl->ws.dog + (size_t)i * c->N;
+        // FirstThr: detect + reEstimateThresh (rebvo_first_t.cpp:266-272)
+        if ((r = rb_detect_enqueue(c, neu, img0, dog, &p.det, pl->chain))) return r;
+        if ((r = rb_reestimate_enqueue(c, neu, p.TrackPoints, p.QCutOffNumBins))) return r;
+        if (fr == 0) {
+            k_frame_first<<<1, 1, 0, c->stream>>>(pl->fs, neu->st, pl->nav_dev + i, pl->fa_dev + i);
+            RB_LAUNCH_CHECK();
+        } else {
+            if ((r = track_frame(pl, neu, old, pl->fa_dev + i, pl->nav_dev + i))) return r;
+        }
+    }
     return RB_OK;
 }
 
@@ -338,42 +398,70 @@ static int push_impl(rb_pipeline *pl, const uint8_t *rgb, bool on_device, const 
     if (n < 1 || n > pl->max_batch || !rgb || !ts) return RB_ERR_ARG;
     RB_CUDA(cudaSetDevice(c->device));
     int r;
+    const long long first = pl->n_pushed;
+    // per-frame scalars -> device (SecondThread :146-149 for dt; FrameCount of the reference's 8-slot ring:
+    // frame fr is served by slot (fr+1)%8, whose global_tracker has run (fr-1)/8 minimisations before)
+    for (int i = 0; i < n; i++) {
+        const long long fr = first + i;
+        double dt = ts[i] - (i == 0 ? pl->t_prev : ts[i - 1]);
+        if (dt < 0.001) dt = 1 / p.config_fps;
+        pl->fa_pin[i].t = ts[i];
+        pl->fa_pin[i].dt = dt;
+        pl->fa_pin[i].frame_count = fr > 0 ? (unsigned int)((fr - 1) / 8) : 0;
+        pl->fa_pin[i].pad = 0;
+    }
     RB_CUDA(cudaEventRecord(pl->ev[0], c->stream));
+    RB_CUDA(cudaMemcpyAsync(pl->fa_dev, pl->fa_pin, sizeof(FrameArgs) * n, cudaMemcpyHostToDevice, c->stream));
     RB_CUDA(cudaMemcpyAsync(pl->ws.rgb, rgb, (size_t)n * 3 * c->N,
                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
-    if ((r = rb_dog_gray(c, &pl->ws, n))) return r;
-    RB_CUDA(cudaEventRecord(pl->ev[1], c->stream));
-    if ((r = rb_dog_build_batch(c, &pl->ws, n))) return r;
-    RB_CUDA(cudaEventRecord(pl->ev[2], c->stream));
-    for (int i = 0; i < n; i++) {
-        const long long fr = pl->n_pushed;
-        rb_map *neu = pl->maps[fr & 1], *old = pl->maps[(fr + 1) & 1];
-        const float *img0 = pl->ws.img0 + (size_t)i * c->N, *dog = pl->ws.dog + (size_t)i * c->N;
-        // FirstThr: detect + reEstimateThresh (rebvo_first_t.cpp:266-272)
-        if ((r = rb_detect_enqueue(c, neu, img0, dog, &p.det, pl->chain))) return r;
-        if ((r = rb_reestimate_enqueue(c, neu, p.TrackPoints, p.QCutOffNumBins))) return r;
-        if (fr == 0) {
-            k_frame_first<<<1, 1, 0, c->stream>>>(pl->fs, neu->st, pl->nav_dev + i, ts[i]);
-            RB_LAUNCH_CHECK();
-        } else {
-            double dt = ts[i] - pl->t_prev;                 // :146-149
-            if (dt < 0.001) dt = 1 / p.config_fps;
-            if ((r = track_frame(pl, neu, old, fr, ts[i], dt, pl->nav_dev + i))) return r;
+    const bool graph_ok = pl->use_graph && first > 0;
+    if (!graph_ok) {
+        if ((r = enqueue_batch(pl, n, first, true))) return r;
+    } else {
+        const int key = (int)(first & 1) * (pl->max_batch + 1) + n;
+        if (!pl->gexec[key]) {
+            // capture the batch once; replays only differ through fa_dev / ws.rgb contents
+            cudaGraph_t g = nullptr;
+            const int64_t l0 = c->launches;
+            RB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            r = enqueue_batch(pl, n, first, false);
+            cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+            if (r) {
+                if (g) cudaGraphDestroy(g);
+                return r;
+            }
+            if (e != cudaSuccess) {
+                snprintf(c->err, sizeof(c->err), "graph capture: %s", cudaGetErrorString(e));
+                return RB_ERR_CUDA;
+            }
+            pl->glaunches[key] = (int)(c->launches - l0);
+            c->launches = l0;
+            e = cudaGraphInstantiate(&pl->gexec[key], g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) {
+                pl->gexec[key] = nullptr;
+                snprintf(c->err, sizeof(c->err), "graph instantiate: %s", cudaGetErrorString(e));
+                return RB_ERR_CUDA;
+            }
         }
-        pl->t_prev = ts[i];
-        pl->n_pushed++;
+        RB_CUDA(cudaEventRecord(pl->ev[1], c->stream));
+        RB_CUDA(cudaGraphLaunch(pl->gexec[key], c->stream));
+        RB_CUDA(cudaEventRecord(pl->ev[2], c->stream));
+        c->launches += pl->glaunches[key];
     }
+    pl->t_prev = ts[n - 1];
+    pl->n_pushed += n;
     RB_CUDA(cudaMemcpyAsync(pl->nav_pin, pl->nav_dev, sizeof(rb_nav) * n, cudaMemcpyDeviceToHost, c->stream));
     RB_CUDA(cudaEventRecord(pl->ev[3], c->stream));
     RB_CUDA(cudaStreamSynchronize(c->stream));
     if (nav_out) memcpy(nav_out, pl->nav_pin, sizeof(rb_nav) * n);
     float ms;
     cudaEventElapsedTime(&ms, pl->ev[0], pl->ev[1]);
-    pl->stage_ms[0] = ms;
+    pl->stage_ms[0] = ms;   // copies (+ gray when not replayed as a graph)
     cudaEventElapsedTime(&ms, pl->ev[1], pl->ev[2]);
-    pl->stage_ms[1] = ms;
+    pl->stage_ms[1] = ms;   // scale space (eager) or the whole batch graph
     cudaEventElapsedTime(&ms, pl->ev[2], pl->ev[3]);
-    pl->stage_ms[2] = ms;   // detect + tracker + mapper of all frames of the batch
+    pl->stage_ms[2] = ms;   // detect + tracker + mapper of all frames (eager) / nav copy (graph)
     pl->stage_ms[3] = pl->stage_ms[4] = 0;
     cudaEventElapsedTime(&ms, pl->ev[0], pl->ev[3]);
     pl->stage_ms[5] = ms;

@@ -90,19 +90,23 @@ __global__ void __launch_bounds__(256) k_quantile(const double *__restrict__ s_r
     __shared__ bool last;
     if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (last && threadIdx.x == 0) {
-        __threadfence();
-        volatile int *vh = histo;
+    if (!last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        sh[i] = __ldcg(&histo[i]);
+        histo[i] = 0;   // leave the scratch histogram zeroed for the next call
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
         double q = 1e3;
         for (int i = 0, a = 0; i < n; i++) {
             if ((double)a > perc * (double)kn) {
                 q = (double)i * range / (double)n + smin;
                 break;
             }
-            a += vh[i];
+            a += sh[i];
         }
         st->s_rho_q = q;
-        for (int i = 0; i < n; i++) histo[i] = 0;
         *ticket = 0;
     }
 }
@@ -273,7 +277,7 @@ __device__ void lm_finalize(LMState &s, MapState *fst) {   // :793-816
     fst->frame_count = fst->frame_count + 1;   // FrameCount++
 }
 
-__device__ void lm_step(LMState &s, int step, MapState *fst) {
+__device__ __noinline__ void lm_step(LMState &s, int step, MapState *fst) {
     switch (step) {
         case STEP_INIT_FIRST_ZERO:
             lm_take_first(s);   // v = 2 from the declaration (:620)
@@ -432,6 +436,9 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
         const float2 pm = old.p_m[i];
         const double rho = old.rho[i], s_rho = old.s_rho[i];
         const int m_num = old.m_num[i];
+        const float2 m = old.m_m[i];          // all streamed operands are requested up front
+        const float n_m = old.n_m[i];
+        const double r_prev = (RW && rin) ? rin[i] : 0.0;
         // KltoI3PMatrix + ProyI3Pto3PMatrix (global_tracker.cpp:552-570, ne10wrapper.h:413-424)
         const double z0 = 1 / rho;
         const double pz_zf0 = cam.inv_zf * z0;
@@ -461,7 +468,7 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
             const int x = (int)(pix + 0.5), y = (int)(piy + 0.5);                   // util::round2int_positive
             double weight = 1;
             if (RW && rin) {
-                const double r = fabs(rin[i]);
+                const double r = fabs(r_prev);
                 if (r > k_huber) weight = k_huber / r;                             // :370-372
             }
             if (x < 1 || y < 1 || x >= cam.w - 1 || y >= cam.h - 1) {               // :376
@@ -469,7 +476,6 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
                 if (RW) f *= weight;
                 rout[i] = max_r;
             } else {
-                const float2 m = old.m_m[i];
                 const float mrx = (float)(sRM[0] * (double)m.x + sRM[1] * (double)m.y);   // :386-388
                 const float mry = (float)(sRM[2] * (double)m.x + sRM[3] * (double)m.y);
                 const unsigned long long key = field[(size_t)y * cam.w + x];
@@ -477,7 +483,6 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
                 if (key != ~0ull) {
                     const int ikl = (int)(0xFFFFFFFFu - (unsigned int)(key & 0xFFFFFFFFull));
                     const float4 a = fpack[2 * ikl], b = fpack[2 * ikl + 1];
-                    const float n_m = old.n_m[i];
                     const double p_n2 = (double)(n_m * n_m);                       // Test_f_k (global_tracker.h:89-104)
                     const double p_esc = (double)(mrx * a.x + mry * a.y);
                     if (!(fabs(p_esc - p_n2) > match_thresh * p_n2)) {
@@ -568,6 +573,7 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
         if (lane == 0) s_red[wid][27] = v;
     }
     __syncthreads();
+    int wrote_sentinel = 0;
     if (active) {
         if (matched) {
             rout[i] = fi_own;
@@ -584,9 +590,13 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
                     }
             }
             if (found) rout[i] = v;
-            else reinterpret_cast<unsigned long long *>(rout)[i] = RES_SENTINEL;
+            else {
+                reinterpret_cast<unsigned long long *>(rout)[i] = RES_SENTINEL;
+                wrote_sentinel = 1;
+            }
         }
     }
+    const int any_sentinel = __syncthreads_or(wrote_sentinel);
     if (tid < 28 && (PJ || tid == 27)) {
         double v = 0;
 #pragma unroll
@@ -603,7 +613,7 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
                 lastv = s_wlast[ww];
             }
         }
-        ts->blk_first[blockIdx.x] = first;
+        ts->blk_first[blockIdx.x] = any_sentinel ? first : 0;   // how many leading entries the last block must patch
         ts->blk_has[blockIdx.x] = has;
         ts->blk_last_fi[blockIdx.x] = lastv;
     }
@@ -614,56 +624,108 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
     if (!s_last) return;
     // ================= last block: grid reduction, stale-fi carries, LM step ==========================
     __threadfence();
-    const int nb = gridDim.x;
-    if (tid < 28 && (PJ || tid == 27)) {
-        const volatile double *part = ts->partials;
-        double v = 0;
-        for (int b = 0; b < nb; b++) v += part[(size_t)b * 28 + tid];
-        s_tot[tid] = v;
-    }
-    // carries: block b inherits the last matched fi of the nearest earlier block that has one (0 at start)
-    __shared__ double s_carry[256];
-    if (tid == 0) {
-        const volatile int *bh = ts->blk_has;
-        const volatile double *bl = ts->blk_last_fi;
-        double carry = 0;
-        for (int b = 0; b < nb && b < 256; b++) {
-            s_carry[b] = carry;
-            if (bh[b]) carry = bl[b];
-        }
-    }
-    __syncthreads();
+    const int nb = gridDim.x;   // <= TVR_T (checked by the host)
+    // grid reduction in a fixed order: thread b owns block b's partials (independent L2 loads, all in flight at
+    // once), then the same warp-shuffle / cross-warp tree as inside a block
     {
-        const volatile int *bf = ts->blk_first;
-        unsigned long long *rbits = reinterpret_cast<unsigned long long *>(rout);
-        for (int b = 0; b < nb && b < 256; b++) {
-            const int lim = bf[b];
-            if (tid < lim) {
-                const int idx = b * TVR_T + tid;
-                if (idx < K0 && __ldcg(&rbits[idx]) == RES_SENTINEL) rout[idx] = s_carry[b];
+        double pv[28];
+#pragma unroll
+        for (int k = 0; k < 28; k++) pv[k] = 0;
+        if (tid < nb) {
+            const double *part = ts->partials + (size_t)tid * 28;
+            if (PJ) {
+#pragma unroll
+                for (int k = 0; k < 28; k++) pv[k] = __ldcg(part + k);
+            } else {
+                pv[27] = __ldcg(part + 27);
             }
         }
+        __syncthreads();   // s_red is reused
+        if (PJ) {
+#pragma unroll
+            for (int k = 0; k < 28; k++) {
+                double v = pv[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) s_red[wid][k] = v;
+            }
+        } else {
+            double v = pv[27];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s_red[wid][27] = v;
+        }
     }
+    // carries: block b inherits the last matched fi of the nearest earlier block that has one (0 at start)
+    __shared__ double s_carry[TVR_T], s_blast[TVR_T];
+    __shared__ int s_bhas[TVR_T], s_bfirst[TVR_T];
+    if (tid < nb) {
+        s_bhas[tid] = __ldcg(ts->blk_has + tid);
+        s_blast[tid] = __ldcg(ts->blk_last_fi + tid);
+        s_bfirst[tid] = __ldcg(ts->blk_first + tid);
+    }
+    __syncthreads();
+    if (tid < 28 && (PJ || tid == 27)) {
+        double v = 0;
+#pragma unroll
+        for (int ww = 0; ww < TVR_T / 32; ww++) v += s_red[ww][tid];
+        s_tot[tid] = v;
+    }
+    if (tid < nb) {   // nearest earlier block with a match (almost always the previous one)
+        double carry = 0;
+        for (int b = tid - 1; b >= 0; b--)
+            if (s_bhas[b]) {
+                carry = s_blast[b];
+                break;
+            }
+        s_carry[tid] = carry;
+    }
+    __syncthreads();
+    if (tid < nb) {   // thread b patches block b's leading misses (those before its first match)
+        unsigned long long *rbits = reinterpret_cast<unsigned long long *>(rout);
+        const int lim = s_bfirst[tid];
+        const double cv = s_carry[tid];
+        for (int j = 0; j < lim; j++) {
+            const int idx = tid * TVR_T + j;
+            if (idx >= K0) break;
+            if (__ldcg(&rbits[idx]) == RES_SENTINEL) rout[idx] = cv;
+        }
+    }
+    // the serial LM step works on a shared-memory copy of the state (global round trips would dominate it)
+    __shared__ LMState s_lm;
+    {
+        const double *src = reinterpret_cast<const double *>(&lm);
+        double *dst = reinterpret_cast<double *>(&s_lm);
+        for (int k = tid; k < (int)(sizeof(LMState) / sizeof(double)); k += TVR_T) dst[k] = __ldcg(src + k);
+    }
+    __syncthreads();
     if (tid == 0) {
+        LMState &L = s_lm;
         if (PJ) {
             int k = 0;
             for (int a = 0; a < 6; a++)
-                for (int b = a; b < 6; b++) lm.JtJn[a * 6 + b] = s_tot[k++];
-            for (int a = 0; a < 6; a++) lm.JtFn[a] = s_tot[21 + a];
+                for (int b = a; b < 6; b++) L.JtJn[a * 6 + b] = s_tot[k++];
+            for (int a = 0; a < 6; a++) L.JtFn[a] = s_tot[21 + a];
             for (int a = 0; a < 2; a++) {              // sign fix-ups (:484-490)
-                lm.JtFn[a + 2] = -lm.JtFn[a + 2];
+                L.JtFn[a + 2] = -L.JtFn[a + 2];
                 for (int b = 0; b < 2; b++) {
-                    lm.JtJn[(a + 0) * 6 + (b + 2)] = -lm.JtJn[(a + 0) * 6 + (b + 2)];
-                    lm.JtJn[(a + 2) * 6 + (b + 4)] = -lm.JtJn[(a + 2) * 6 + (b + 4)];
+                    L.JtJn[(a + 0) * 6 + (b + 2)] = -L.JtJn[(a + 0) * 6 + (b + 2)];
+                    L.JtJn[(a + 2) * 6 + (b + 4)] = -L.JtJn[(a + 2) * 6 + (b + 4)];
                 }
             }
             for (int a = 0; a < 6; a++)
-                for (int b = a + 1; b < 6; b++) lm.JtJn[b * 6 + a] = lm.JtJn[a * 6 + b];
+                for (int b = a + 1; b < 6; b++) L.JtJn[b * 6 + a] = L.JtJn[a * 6 + b];
         }
-        lm.last_score = s_tot[27];
-        lm.n_eval++;
-        lm_step(lm, step, f_st);
+        L.last_score = s_tot[27];
+        L.n_eval++;
+        lm_step(L, step, f_st);
         *ticket = 0;
+    }
+    __syncthreads();
+    {
+        const double *src = reinterpret_cast<const double *>(&s_lm);
+        double *dst = reinterpret_cast<double *>(&lm);
+        for (int k = tid; k < (int)(sizeof(LMState) / sizeof(double)); k += TVR_T) dst[k] = src[k];
     }
     (void)nred;
 }
@@ -1081,67 +1143,92 @@ int rb_ekf_enqueue(rb_ctx *c, rb_map *m, const double *vel_dev, double q_abs, do
 // =====================================================================================================
 // EstimateReScalingOpt (edge_tracker.cpp:1104-1140): 5 fixed-point iterations, one block
 // =====================================================================================================
-__global__ void __launch_bounds__(1024) k_rescale(KLSoA kl, MapState *st, double s_rho_min, unsigned int mnm,
-                                                  int re_escale, const int *enable) {
+// one fixed-point iteration over the whole grid; the last block to finish folds the per-block partials in a fixed
+// order and publishes Kp / RKp for the next launch (iter 0 starts from Kp = 1)
+__global__ void __launch_bounds__(256) k_rescale_iter(KLSoA kl, MapState *st, double *__restrict__ part,
+                                                      unsigned int *ticket, double s_rho_min, unsigned int mnm,
+                                                      int iter, const int *enable) {
     if (enable && !*enable) return;
-    __shared__ double sa[32], sb[32];
-    __shared__ double sKp, sRKp;
+    __shared__ double sa[8], sb[8];
+    __shared__ double pa[256], pb[256];
+    __shared__ bool last;
     const int kn = st->kn;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (kn <= 0) {
-        if (tid == 0) st->Kp = 1;
-        return;
-    }
-    if (tid == 0) sKp = 1;
-    __syncthreads();
-    for (int iter = 0; iter < 5; iter++) {
-        const double Kp = sKp;
-        double a = 0, b = 0;
-        for (int i = tid; i < kn; i += 1024) {
-            const double s0 = kl.s_rho0[i], s = kl.s_rho[i];
-            if ((unsigned int)kl.m_num[i] < mnm || s0 <= 0 || s > s_rho_min) continue;
+    const double Kp = iter == 0 ? 1.0 : st->Kp;
+    const int i = blockIdx.x * 256 + tid;
+    double a = 0, b = 0;
+    if (i < kn) {
+        const double s0 = kl.s_rho0[i], s = kl.s_rho[i];
+        if (!((unsigned int)kl.m_num[i] < mnm || s0 <= 0 || s > s_rho_min)) {
             const double r = kl.rho[i], r0 = kl.rho0[i];
             const double den = s * s + Kp * Kp * s0 * s0;
-            a += r * r / den;
-            b += r0 * r0 / den;
+            a = r * r / den;
+            b = r0 * r0 / den;
         }
+    }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, o);
-            b += __shfl_xor_sync(0xffffffffu, b, o);
-        }
-        if (lane == 0) {
-            sa[wid] = a;
-            sb[wid] = b;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            double rTr = 0, rTr0 = 0;
-            for (int k = 0; k < 32; k++) {
-                rTr += sa[k];
-                rTr0 += sb[k];
-            }
-            sKp = rTr0 > 0 ? sqrt(rTr / rTr0) : 1;
-            sRKp = 1 / rTr0;
-        }
-        __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
     }
-    const double Kp = sKp;
-    if (re_escale) {
-        for (int i = tid; i < kn; i += 1024) {
-            kl.rho[i] = kl.rho[i] / Kp;
-            kl.s_rho[i] = kl.s_rho[i] / Kp;
-        }
+    if (lane == 0) {
+        sa[wid] = a;
+        sb[wid] = b;
     }
+    __syncthreads();
     if (tid == 0) {
-        st->Kp = Kp;
-        st->RKp = sRKp;
+        double x = 0, y = 0;
+        for (int k = 0; k < 8; k++) {
+            x += sa[k];
+            y += sb[k];
+        }
+        part[2 * blockIdx.x] = x;
+        part[2 * blockIdx.x + 1] = y;
+        __threadfence();
+        last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const int nb = gridDim.x;   // <= 256
+    pa[tid] = tid < nb ? __ldcg(part + 2 * tid) : 0.0;
+    pb[tid] = tid < nb ? __ldcg(part + 2 * tid + 1) : 0.0;
+    __syncthreads();
+    if (tid == 0) {
+        double rTr = 0, rTr0 = 0;
+        for (int k = 0; k < nb; k++) {
+            rTr += pa[k];
+            rTr0 += pb[k];
+        }
+        if (kn <= 0) {
+            st->Kp = 1;   // "if(kn<=0) return 1;"
+        } else {
+            st->Kp = rTr0 > 0 ? sqrt(rTr / rTr0) : 1;
+            st->RKp = 1 / rTr0;
+        }
+        *ticket = 0;
+    }
+}
+__global__ void __launch_bounds__(256) k_rescale_apply(KLSoA kl, const MapState *st, const int *enable) {
+    if (enable && !*enable) return;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= st->kn) return;
+    const double Kp = st->Kp;
+    kl.rho[i] = kl.rho[i] / Kp;
+    kl.s_rho[i] = kl.s_rho[i] / Kp;
 }
 
 int rb_rescale_enqueue(rb_ctx *c, rb_map *m, double s_rho_min, unsigned int match_num_min, int re_escale,
                        const int *enable_dev) {
-    k_rescale<<<1, 1024, 0, c->stream>>>(m->kl, m->st, s_rho_min, match_num_min, re_escale, enable_dev);
-    RB_LAUNCH_CHECK();
+    const int nb = m->ts_host.nblk;
+    for (int iter = 0; iter < 5; iter++) {
+        k_rescale_iter<<<nb, 256, 0, c->stream>>>(m->kl, m->st, m->ts_host.partials, c->ticket + 3, s_rho_min,
+                                                  match_num_min, iter, enable_dev);
+        RB_LAUNCH_CHECK();
+    }
+    if (re_escale) {
+        k_rescale_apply<<<nb, 256, 0, c->stream>>>(m->kl, m->st, enable_dev);
+        RB_LAUNCH_CHECK();
+    }
     return RB_OK;
 }

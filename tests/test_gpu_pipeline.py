@@ -87,6 +87,16 @@ def test_batch_size_invariance(built, stream):
         assert np.array_equal(a[f], b[f]) and np.array_equal(a[f], c[f]), f
 
 
+def test_graph_replay_equals_eager_launches(built, stream, monkeypatch):
+    """Batches after the first are replayed as a CUDA graph; the eager path must give the same bits."""
+    a, la = _gpu_run(stream, 10)
+    monkeypatch.setenv("REBVO_B200_NO_GRAPH", "1")
+    b, lb = _gpu_run(stream, 10)
+    assert la == lb, "launch accounting differs between graph replay and eager launches"
+    for f in ("Pos", "Pose", "kn", "matches", "Kp", "score"):
+        assert np.array_equal(a[f], b[f]), f
+
+
 def test_keyline_mirror_matches_reference_layout(built, stream):
     """The 168-byte AoS mirror handed to host consumers (callback / net packer) is populated and consistent."""
     from rebvo_b200 import capi, synth
