@@ -180,6 +180,16 @@ int rb_map_rescale_opt(rb_map *m, double s_rho_min, uint32_t match_num_min, int 
 /* global_tracker's FrameCount (global_tracker.cpp:356,816) of this slot */
 int rb_map_set_frame_count(rb_map *m, uint32_t fc);
 
+/* ---- image_undistort --------------------------------------------------------
+ * image_undistort::image_undistort + undistort<true>(Image<RGB24Pixel>&, Image<RGB24Pixel>&)
+ * (src/VideoLib/image_undistort.cpp:29-94, include/VideoLib/image_undistort.h:63-123, call site
+ * rebvo_first_t.cpp:231).  kc = {Kc2, Kc4, Kc6, P1, P2} of cam_model::rad_tan_distortion. */
+typedef struct rb_undistort rb_undistort;
+int rb_undistort_create(rb_ctx *c, const double kc[5], rb_undistort **out);
+void rb_undistort_destroy(rb_undistort *u);
+int rb_undistort_rgb(rb_undistort *u, const uint8_t *in, uint8_t *out); /* host RGB24 -> host RGB24 */
+int rb_undistort_rgb_dev(rb_undistort *u, const uint8_t *in_dev, uint8_t *out_dev, int nimg);
+
 /* ---- whole per-frame flow ------------------------------------------------------------------------
  * REBVO::FirstThr detector stage + REBVO::SecondThread tracker/mapper stage (ImuMode=0) with all
  * state (edge-map ring, threshold feedback, V/W/P_V, pose) resident on the device. */
@@ -201,6 +211,11 @@ int64_t rb_pipeline_launch_count(const rb_pipeline *pl);
 /* CUDA-event time (ms) of the last push split by stage: [0] h2d+gray, [1] DoG, [2] detect,
  * [3] tracker (field + minimiser), [4] mapper, [5] total */
 int rb_pipeline_stage_ms(const rb_pipeline *pl, float out[6]);
+/* In-situ stage profile, enabled by REBVO_B200_STAGE_PROF=1 at creation (forces eager launches): accumulated CUDA-event
+ * milliseconds per stage over all pushes so far: [0] copies, [1] gray, [2] scale space, [3] detect, [4] reEstimateThresh,
+ * [5] quantile + build_field, [6] Minimizer_RV, [7] FordwardMatch + rotate, [8] directed_matching, [9] regularize + EKF,
+ * [10] rescale, [11] pose/nav, [12] nav copy */
+int rb_pipeline_stage_profile(rb_pipeline *pl, double out_ms[16], long long *frames);
 /* opaque stream handle (cudaStream_t) the pipeline launches on, for CUDA-event timing by the caller */
 void *rb_pipeline_stream(rb_pipeline *pl);
 /* CUDA-event stopwatch on the pipeline's own stream (bench.py): record slot 0..7, elapsed(a,b) in ms

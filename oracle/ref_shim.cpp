@@ -244,3 +244,14 @@ void ref_so3_ln(const double *R, double *w) {
     for (int i = 0; i < 3; i++) w[i] = l[i];
 }
 }  // extern "C"
+
+// ---- image_undistort: reference undistort<true> on RGB24 -------------------------
+#include "VideoLib/image_undistort.h"
+extern "C" void ref_undistort_rgb(int w, int h, float ppx, float ppy, float zfx, float zfy, const double *kc,
+                                  const unsigned char *in, unsigned char *out) {
+    cam_model::rad_tan_distortion d = {kc[0], kc[1], kc[2], kc[3], kc[4]};
+    cam_model cam({ppx, ppy}, {zfx, zfy}, d, {(uint)w, (uint)h});
+    image_undistort und(cam);
+    Image<RGB24Pixel> i((RGB24Pixel *)in, cam.sz), o((RGB24Pixel *)out, cam.sz);
+    und.undistort<true>(o, i);
+}

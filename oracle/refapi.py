@@ -205,6 +205,16 @@ class RefMap:
         return kp, rkp.value
 
 
+def undistort_rgb(cam, kc, rgb):
+    """image_undistort(cam).undistort<true>(out, in) of the reference on one RGB24 frame."""
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    out = np.zeros_like(rgb)
+    kc = np.ascontiguousarray(kc, np.float64)
+    lib().ref_undistort_rgb(cam["w"], cam["h"], C.c_float(cam["ppx"]), C.c_float(cam["ppy"]), C.c_float(cam["zfx"]),
+                            C.c_float(cam["zfy"]), _p(kc), _p(rgb), _p(out))
+    return out
+
+
 def so3_exp(w):
     w = np.ascontiguousarray(w, np.float64)
     R = np.zeros((3, 3))

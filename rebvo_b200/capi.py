@@ -65,7 +65,9 @@ SYMBOLS = ["rb_ctx_create", "rb_ctx_destroy", "rb_last_error", "rb_ctx_sync", "r
            "rb_map_rescale_opt", "rb_map_set_frame_count", "rb_pipeline_create", "rb_pipeline_destroy",
            "rb_pipeline_last_error", "rb_pipeline_push", "rb_pipeline_push_dev", "rb_pipeline_reset",
            "rb_pipeline_map", "rb_pipeline_launch_count", "rb_pipeline_stage_ms", "rb_pipeline_stream",
-           "rb_pipeline_event_record", "rb_pipeline_event_elapsed", "rb_pipeline_bench_pass"]
+           "rb_pipeline_event_record", "rb_pipeline_event_elapsed", "rb_pipeline_bench_pass",
+           "rb_pipeline_stage_profile",
+           "rb_undistort_create", "rb_undistort_destroy", "rb_undistort_rgb", "rb_undistort_rgb_dev"]
 
 _lib = None
 
@@ -153,6 +155,28 @@ class Ctx:
     def close(self):
         if self.h_:
             self.L.rb_ctx_destroy(self.h_)
+            self.h_ = None
+
+
+class Undistort:
+    """image_undistort of the reference (rad-tan model, 16.16 fixed-point bilinear RGB remap)."""
+
+    def __init__(self, ctx, kc):
+        self.ctx = ctx
+        kc = np.ascontiguousarray(kc, np.float64)
+        h = C.c_void_p()
+        ctx.check(ctx.L.rb_undistort_create(ctx.h_, _p(kc), C.byref(h)))
+        self.h_ = h
+
+    def apply(self, rgb):
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        out = np.empty_like(rgb)
+        self.ctx.check(self.ctx.L.rb_undistort_rgb(self.h_, _p(rgb), _p(out)))
+        return out
+
+    def close(self):
+        if self.h_:
+            self.ctx.L.rb_undistort_destroy(self.h_)
             self.h_ = None
 
 
@@ -358,6 +382,14 @@ class Pipeline:
         ms = C.c_float(0)
         self.check(self.L.rb_pipeline_event_elapsed(self.h_, a, b, C.byref(ms)))
         return ms.value
+
+    def stage_profile(self):
+        out = np.zeros(16)
+        fr = C.c_longlong(0)
+        self.check(self.L.rb_pipeline_stage_profile(self.h_, _p(out), C.byref(fr)))
+        names = ["copies", "gray", "scale_space", "detect", "reestimate", "quantile+field", "minimizer",
+                 "fwdmatch+rotate", "directed_match", "regularize+ekf", "rescale", "pose/nav", "nav_copy"]
+        return {n: 1e3 * out[i] / max(fr.value, 1) for i, n in enumerate(names)}, fr.value
 
     def bench_pass(self, pass_id, nimg, iters):
         ms, by = C.c_float(0), C.c_double(0)

@@ -1,6 +1,7 @@
 // capi.cu -- the C ABI of librebvo_b200 (include/rebvo_b200.h): context / edge-map lifetime, uploads,
 // scalar read-back and the AoS <-> SoA keyline conversion for host consumers.
 #include <math.h>
+#include <stdlib.h>
 #include <new>
 
 #include "common.cuh"
@@ -159,6 +160,11 @@ extern "C" int rb_ctx_create(rb_ctx **out, int device, const rb_camera *cam, dou
     c->sigma0 = sigma0;
     c->ksigma = ksigma;
     c->kcap = kl_capacity;
+    {
+        const char *ds = getenv("REBVO_B200_DOG_SUB");
+        c->dog_sub = ds ? atoi(ds) : 0;   // 0 = whole batch in one go (measured fastest: the passes are latency-bound)
+        if (c->dog_sub < 0) c->dog_sub = 0;
+    }
     // sspace::sspace (sspace.cpp:36-46): filter1 sigma = filter0.sigma_r * k_sigma
     box_plan_one(sigma0, 3, c->plan.d[0], &c->plan.sigma_r[0]);
     box_plan_one(c->plan.sigma_r[0] * ksigma, 3, c->plan.d[1], &c->plan.sigma_r[1]);
@@ -192,6 +198,10 @@ extern "C" int rb_ctx_create(rb_ctx **out, int device, const rb_camera *cam, dou
     CK(cudaMallocHost(&c->pinned, 1 << 16));
     CK(cudaMalloc(&c->dev_small, 1 << 16));
     CK(cudaMemset(c->dev_small, 0, 1 << 16));
+    {
+        const int mm_init[2] = {-1, 0x7f7fffff};   // reEstimateThresh scratch: max bits, min bits (re-armed by k_nm_histo)
+        CK(cudaMemcpy((char *)c->dev_small + RB_DS_REEST, mm_init, sizeof(mm_init), cudaMemcpyHostToDevice));
+    }
     if ((r = rb_detect_upload_pinv(c))) return fail(r);
     if ((r = rb_dog_make_tables(c))) return fail(r);
 #undef CK

@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "tracker.cuh"
 
+int rb_resolve_res_enqueue(rb_ctx *c, rb_map *fmap, rb_map *old, int buf);
 int rb_try_vel_rot_enqueue(rb_ctx *c, rb_map *fmap, rb_map *old, const double *X_dev, int reweight, int procjf,
                            double match_thresh, double s_rho_min, unsigned int mnt, unsigned int fc,
                            double k_huber);
@@ -93,6 +94,7 @@ extern "C" int rb_try_vel_rot(rb_map *fmap, rb_map *old, const double X[6], int 
         return r;
     LMState *lmh = (LMState *)((char *)c->pinned + 4096);
     RB_CUDA(cudaMemcpyAsync(lmh, &fmap->ts->lm, sizeof(LMState), cudaMemcpyDeviceToHost, c->stream));
+    if (res_out && so.kn > 0 && (r = rb_resolve_res_enqueue(c, fmap, old, 1))) return r;
     if (res_out && so.kn > 0)
         RB_CUDA(cudaMemcpyAsync(res_out, fmap->res[1], sizeof(double) * so.kn, cudaMemcpyDeviceToHost, c->stream));
     RB_CUDA(cudaStreamSynchronize(c->stream));

@@ -89,6 +89,8 @@ struct rb_ctx {
     void *pinned;        // small pinned host buffer for scalar read-back
     void *dev_small;     // small device buffer for scalar parameters / results (64 KiB, zero-initialised)
     float *boxtab;       // 6 x 64 reciprocal clipped-area tables (iimage::build_average), see dog.cu
+    bool counters_preset; // set by rb_pipeline: match / regularise counters are zeroed by k_frame_pre
+    int dog_sub;         // frames per scale-space sub-batch, env REBVO_B200_DOG_SUB (0 = whole batch, the default)
 };
 // layout of rb_ctx::dev_small / pinned (byte offsets)
 #define RB_DS_REEST 0        // int[2 + nbins + 1]  reEstimateThresh min/max bits + histogram
@@ -127,6 +129,7 @@ struct TrackState {
     int *blk_has;
     double *blk_last_fi;  // per block: residual of its last matched keyline
     double *partials;     // per block x 28 reduction partials
+    double *carry;        // [3][256]: per residual buffer and block, the stale-fi value its leading misses inherit
     int nblk;
     // scratch for FordwardMatch / Regularize_1_iter
     unsigned long long *fm_best;

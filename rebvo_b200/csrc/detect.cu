@@ -299,6 +299,12 @@ __global__ void __launch_bounds__(256) k_nm_histo(const float *__restrict__ n_m,
         st->retuned = ret;
         *ticket = 0;
     }
+    // leave the scratch ready for the next call (no separate init launch)
+    for (int i = threadIdx.x; i < n + 1; i += blockDim.x) histo[i] = 0;
+    if (threadIdx.x == 0) {
+        const_cast<int *>(mm)[0] = -1;
+        const_cast<int *>(mm)[1] = 0x7f7fffff;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -333,8 +339,7 @@ int rb_reestimate_enqueue(rb_ctx *c, rb_map *m, int knum, int nbins) {
     if (nbins < 1 || nbins > 4096) return RB_ERR_ARG;
     int *mm = (int *)c->dev_small;          // [0] max bits, [1] min bits, [2..] histogram
     int *histo = mm + 2;
-    k_reest_init<<<1, 256, 0, c->stream>>>(mm, nbins + 1);
-    RB_LAUNCH_CHECK();
+    // mm / histogram are initialised at context creation and re-armed by k_nm_histo's last block
     const int blocks = 64;
     k_nm_minmax<<<blocks, 256, 0, c->stream>>>(m->kl.n_m, m->st, mm);
     RB_LAUNCH_CHECK();

@@ -248,9 +248,11 @@ static int rowscan(rb_ctx *c, int stage, const float *in, float *out, int nimg, 
     return RB_OK;
 }
 
-static int blur_dog(rb_ctx *c, DogWS *ws, int nimg, float *img1_opt) {
+static int blur_dog(rb_ctx *c, DogWS *ws, int nimg, float *img1_opt, int out_slot = 0) {
     dim3 grid(rb_div_up(c->w, 256), c->h, nimg);
-    k_blur_dog<<<grid, 256, 0, c->stream>>>(ws->I, ws->img0, ws->dog, img1_opt, c->w, c->h, nimg, c->plan.d[0][2],
+    const size_t off = (size_t)out_slot * c->N;
+    k_blur_dog<<<grid, 256, 0, c->stream>>>(ws->I, ws->img0 + off, ws->dog + off, img1_opt, c->w, c->h, nimg,
+                                            c->plan.d[0][2],
                                             c->plan.d[1][2], c->boxtab + (0 * 3 + 2) * BOX_TAB_N,
                                             c->boxtab + (1 * 3 + 2) * BOX_TAB_N);
     RB_LAUNCH_CHECK();
@@ -293,17 +295,26 @@ static int colscan(rb_ctx *c, const float *in, float *out, int nimg) {
 int rb_dog_build_batch(rb_ctx *c, DogWS *ws, int nimg) {
     if (nimg < 1 || nimg > ws->B) return RB_ERR_ARG;
     int r;
-    // iimage::load(in): identical for both filters -> computed once
-    if ((r = rowscan(c, -1, ws->gray, ws->S, nimg, nimg, nimg))) return r;
-    if ((r = colscan(c, ws->S, ws->I0, nimg))) return r;
-    // box 0 of both filters reads the shared integral; image index = filter * nimg + b
-    if ((r = rowscan(c, 0, ws->I0, ws->S, 2 * nimg, nimg, nimg))) return r;
-    if ((r = colscan(c, ws->S, ws->I, 2 * nimg))) return r;
-    // box 1
-    if ((r = rowscan(c, 1, ws->I, ws->S, 2 * nimg, 2 * nimg, nimg))) return r;
-    if ((r = colscan(c, ws->S, ws->I, 2 * nimg))) return r;
-    // box 2 + DoG.  Filter f of image b lives at I[(f*nimg + b)*N]
-    return blur_dog(c, ws, nimg, nullptr);
+    // The batch is processed in sub-batches whose intermediate planes (S, I0, I: 20 N bytes per frame) fit in the
+    // 126 MB L2: what one pass writes is still on chip when the next pass reads it, so only gray in and img0/dog
+    // out stream through HBM.  The scratch planes of the first `sub` slots are reused by every sub-batch.
+    const int sub = c->dog_sub > 0 ? c->dog_sub : nimg;
+    const size_t N = c->N;
+    for (int s = 0; s < nimg; s += sub) {
+        const int m = nimg - s < sub ? nimg - s : sub;
+        // iimage::load(in): identical for both filters -> computed once
+        if ((r = rowscan(c, -1, ws->gray + s * N, ws->S, m, m, m))) return r;
+        if ((r = colscan(c, ws->S, ws->I0, m))) return r;
+        // box 0 of both filters reads the shared integral; image index = filter * m + b
+        if ((r = rowscan(c, 0, ws->I0, ws->S, 2 * m, m, m))) return r;
+        if ((r = colscan(c, ws->S, ws->I, 2 * m))) return r;
+        // box 1
+        if ((r = rowscan(c, 1, ws->I, ws->S, 2 * m, 2 * m, m))) return r;
+        if ((r = colscan(c, ws->S, ws->I, 2 * m))) return r;
+        // box 2 + DoG.  Filter f of image b lives at I[(f*m + b)*N]
+        if ((r = blur_dog(c, ws, m, nullptr, s))) return r;
+    }
+    return RB_OK;
 }
 
 // Img(1), dx, dy of image `img` into ws->aux (debug accessor; needs ws->I from the last build with

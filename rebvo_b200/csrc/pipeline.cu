@@ -51,7 +51,22 @@ struct rb_pipeline {
     cudaGraphExec_t *gexec;       // [2 * (max_batch + 1)]
     int *glaunches;               // kernel launches inside each graph
     bool use_graph;
+    // optional in-situ stage profile (REBVO_B200_STAGE_PROF=1, forces eager launches): CUDA events between stages
+    bool prof_on;
+    cudaEvent_t *pev;
+    int *ptag;
+    int pcap, pn;
+    double pacc[16];
+    long long pframes;
 };
+
+enum { ST_H2D = 0, ST_GRAY, ST_DOG, ST_DETECT, ST_REEST, ST_FIELD, ST_MINIM, ST_FWD_ROT, ST_DMATCH, ST_REG_EKF, ST_RESCALE,
+       ST_FINISH, ST_NAV };
+static inline void prof_mark(rb_pipeline *pl, int tag) {
+    if (!pl->prof_on || pl->pn >= pl->pcap) return;
+    cudaEventRecord(pl->pev[pl->pn], pl->c->stream);
+    pl->ptag[pl->pn++] = tag;
+}
 
 int rb_dog_single_pass(rb_ctx *c, DogWS *ws, int pass_id, int nimg, double *bytes);
 
@@ -76,6 +91,9 @@ struct FrameArgs {
 // start of the SecondThread loop body (:167-169) + minimiser priors
 __global__ void k_frame_pre(FrameState *fs, const FrameArgs *fa, MapState *nst) {
     nst->frame_count = fa->frame_count;
+    nst->fwd_match = 0;   // counters of FordwardMatch / directed_matching / Regularize_1_iter
+    nst->nmatch = 0;
+    nst->reg_num = 0;
     d_eye(fs->P_V, 1e50);
     d_eye(fs->P_W, 1e50);
     d_eye(fs->R, 1);
@@ -251,6 +269,7 @@ extern "C" int rb_pipeline_create(rb_pipeline **out, int device, const rb_params
     }
     memset(pl, 0, sizeof(*pl));
     pl->c = c;
+    c->counters_preset = true;
     pl->p = *p;
     pl->max_batch = max_batch;
     *out = pl;
@@ -272,6 +291,16 @@ extern "C" int rb_pipeline_create(rb_pipeline **out, int device, const rb_params
     }
     const char *ng = getenv("REBVO_B200_NO_GRAPH");
     pl->use_graph = !(ng && ng[0] == '1');
+    const char *sp = getenv("REBVO_B200_STAGE_PROF");
+    pl->prof_on = sp && sp[0] == '1';
+    if (pl->prof_on) {
+        pl->use_graph = false;
+        pl->pcap = max_batch * 12 + 8;
+        pl->pev = new (std::nothrow) cudaEvent_t[pl->pcap];
+        pl->ptag = new (std::nothrow) int[pl->pcap];
+        if (!pl->pev || !pl->ptag) return RB_ERR_ARG;
+        for (int i = 0; i < pl->pcap; i++) RB_CUDA(cudaEventCreate(&pl->pev[i]));
+    }
     for (int i = 0; i < 4; i++) RB_CUDA(cudaEventCreate(&pl->ev[i]));
     for (int i = 0; i < 8; i++) RB_CUDA(cudaEventCreate(&pl->user_ev[i]));
     if ((r = pl_reset_state(pl))) return r;
@@ -336,6 +365,7 @@ static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, const FrameArg
     if ((r = rb_quantile_enqueue(c, old, RB_RHO_MIN, RB_RHO_MAX, p.QCutOffQuantile, p.QCutOffNumBins))) return r;
     // :177  new_buf.gt->build_field(*new_buf.ef,SearchRange,new_buf.ef->getThresh())
     if ((r = rb_build_field_enqueue(c, neu, p.SearchRange, 0.f, true))) return r;
+    prof_mark(pl, ST_FIELD);
     // :346  Minimizer_RV<double>(V,W,P_V,P_W,*old_buf.ef,...)
     rb_minimizer_args a;
     a.match_thresh = p.TrackerMatchThresh;
@@ -346,23 +376,29 @@ static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, const FrameArg
     a.match_num_thresh = p.MatchNumThresh;
     // FrameCount comes from fa (written into neu->st by k_frame_pre)
     if ((r = rb_minimizer_enqueue(c, neu, old, pl->fs->VW, &a, 0.0, true, 0, true))) return r;
+    prof_mark(pl, ST_MINIM);
     k_frame_post_min<<<1, 1, 0, c->stream>>>(pl->fs, neu->ts);
     RB_LAUNCH_CHECK();
     // :354  FordwardMatch ; :369 rotate_keylines(R0)
     if ((r = rb_forward_match_enqueue(c, old, neu))) return r;
     if ((r = rb_rotate_enqueue(c, old, pl->fs->R0))) return r;
+    prof_mark(pl, ST_FWD_ROT);
     // :410  directed_matching(V,P_V,R,old_buf.ef,...)
     if ((r = rb_directed_matching_enqueue(c, neu, old, &pl->fs->dm, p.MatchThreshModule, p.MatchThreshAngle,
                                           (double)p.SearchRange, p.LocationUncertaintyMatch, &pl->fs->do_match)))
         return r;
     k_frame_post_match<<<1, 1, 0, c->stream>>>(pl->fs, neu->st, p.MatchThreshold);
     RB_LAUNCH_CHECK();
+    prof_mark(pl, ST_DMATCH);
     // :452-487  Regularize_1_iter, UpdateInverseDepthKalman, EstimateReScalingOpt
     if ((r = rb_regularize_enqueue(c, neu, p.RegularizeThresh, &pl->fs->do_map))) return r;
     if ((r = rb_ekf_enqueue(c, neu, pl->fs->V, p.ReshapeQAbsolute, p.LocationUncertainty, &pl->fs->do_map))) return r;
+    prof_mark(pl, ST_REG_EKF);
     if ((r = rb_rescale_enqueue(c, neu, RB_RHO_MAX, 1, p.DoReScaling > 0 ? 1 : 0, &pl->fs->do_map))) return r;
+    prof_mark(pl, ST_RESCALE);
     k_frame_finish<<<1, 1, 0, c->stream>>>(pl->fs, neu->st, old->st, neu->ts, nav_slot, fa);
     RB_LAUNCH_CHECK();
+    prof_mark(pl, ST_FINISH);
     return RB_OK;
 }
 
@@ -371,9 +407,12 @@ static int enqueue_batch(rb_pipeline *pl, int n, long long first_frame, bool wit
     rb_ctx *c = pl->c;
     const rb_params &p = pl->p;
     int r;
+    prof_mark(pl, ST_H2D);
     if ((r = rb_dog_gray(c, &pl->ws, n))) return r;
+    prof_mark(pl, ST_GRAY);
     if (with_events) RB_CUDA(cudaEventRecord(pl->ev[1], c->stream));
     if ((r = rb_dog_build_batch(c, &pl->ws, n))) return r;
+    prof_mark(pl, ST_DOG);
     if (with_events) RB_CUDA(cudaEventRecord(pl->ev[2], c->stream));
     for (int i = 0; i < n; i++) {
         const long long fr = first_frame + i;
@@ -381,7 +420,9 @@ static int enqueue_batch(rb_pipeline *pl, int n, long long first_frame, bool wit
         const float *img0 = pl->ws.img0 + (size_t)i * c->N, *dog = pl->ws.dog + (size_t)i * c->N;
         // FirstThr: detect + reEstimateThresh (rebvo_first_t.cpp:266-272)
         if ((r = rb_detect_enqueue(c, neu, img0, dog, &p.det, pl->chain))) return r;
+        prof_mark(pl, ST_DETECT);
         if ((r = rb_reestimate_enqueue(c, neu, p.TrackPoints, p.QCutOffNumBins))) return r;
+        prof_mark(pl, ST_REEST);
         if (fr == 0) {
             k_frame_first<<<1, 1, 0, c->stream>>>(pl->fs, neu->st, pl->nav_dev + i, pl->fa_dev + i);
             RB_LAUNCH_CHECK();
@@ -410,6 +451,8 @@ static int push_impl(rb_pipeline *pl, const uint8_t *rgb, bool on_device, const 
         pl->fa_pin[i].frame_count = fr > 0 ? (unsigned int)((fr - 1) / 8) : 0;
         pl->fa_pin[i].pad = 0;
     }
+    pl->pn = 0;
+    prof_mark(pl, ST_NAV);   // origin of this push
     RB_CUDA(cudaEventRecord(pl->ev[0], c->stream));
     RB_CUDA(cudaMemcpyAsync(pl->fa_dev, pl->fa_pin, sizeof(FrameArgs) * n, cudaMemcpyHostToDevice, c->stream));
     RB_CUDA(cudaMemcpyAsync(pl->ws.rgb, rgb, (size_t)n * 3 * c->N,
@@ -452,8 +495,17 @@ static int push_impl(rb_pipeline *pl, const uint8_t *rgb, bool on_device, const 
     pl->t_prev = ts[n - 1];
     pl->n_pushed += n;
     RB_CUDA(cudaMemcpyAsync(pl->nav_pin, pl->nav_dev, sizeof(rb_nav) * n, cudaMemcpyDeviceToHost, c->stream));
+    prof_mark(pl, ST_NAV);
     RB_CUDA(cudaEventRecord(pl->ev[3], c->stream));
     RB_CUDA(cudaStreamSynchronize(c->stream));
+    if (pl->prof_on) {
+        for (int i = 1; i < pl->pn; i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, pl->pev[i - 1], pl->pev[i]);
+            pl->pacc[pl->ptag[i]] += ms;
+        }
+        pl->pframes += n;
+    }
     if (nav_out) memcpy(nav_out, pl->nav_pin, sizeof(rb_nav) * n);
     float ms;
     cudaEventElapsedTime(&ms, pl->ev[0], pl->ev[1]);
@@ -506,5 +558,12 @@ extern "C" int rb_pipeline_bench_pass(rb_pipeline *pl, int pass_id, int nimg, in
     RB_CUDA(cudaEventElapsedTime(&ms, pl->user_ev[6], pl->user_ev[7]));
     *ms_per_launch = ms / iters;
     *bytes_per_launch = bytes;
+    return RB_OK;
+}
+
+extern "C" int rb_pipeline_stage_profile(rb_pipeline *pl, double out_ms[16], long long *frames) {
+    if (!pl->prof_on) return RB_ERR_STATE;
+    for (int i = 0; i < 16; i++) out_ms[i] = pl->pacc[i];
+    if (frames) *frames = pl->pframes;
     return RB_OK;
 }

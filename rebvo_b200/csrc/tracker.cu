@@ -39,7 +39,9 @@ int rb_track_state_alloc(rb_ctx *c, rb_map *m) {
     RB_CUDA(cudaMalloc(&host.blk_first, sizeof(int) * nblk));
     RB_CUDA(cudaMalloc(&host.blk_has, sizeof(int) * nblk));
     RB_CUDA(cudaMalloc(&host.blk_last_fi, sizeof(double) * nblk));
-    RB_CUDA(cudaMalloc(&host.partials, sizeof(double) * 28 * nblk));
+    RB_CUDA(cudaMalloc(&host.partials, sizeof(double) * 28 * TVR_T));
+    RB_CUDA(cudaMalloc(&host.carry, sizeof(double) * 3 * TVR_T));
+    RB_CUDA(cudaMemsetAsync(host.carry, 0, sizeof(double) * 3 * TVR_T, c->stream));
     RB_CUDA(cudaMalloc(&host.fm_best, sizeof(unsigned long long) * K));
     RB_CUDA(cudaMalloc(&host.fm_idx, sizeof(int) * K));
     RB_CUDA(cudaMalloc(&host.reg_r, sizeof(double) * K));
@@ -58,6 +60,7 @@ void rb_track_state_free(rb_map *m) {
     cudaFree(h.blk_has);
     cudaFree(h.blk_last_fi);
     cudaFree(h.partials);
+    cudaFree(h.carry);
     cudaFree(h.fm_best);
     cudaFree(h.fm_idx);
     cudaFree(h.reg_r);
@@ -170,16 +173,81 @@ __device__ void lm_build_api(const LMState &s, double *A, double *rhs) {
         rhs[i] = -s.JtF[i];
     }
 }
-__device__ void lm_solve(LMState &s, bool use_svd) {
-    double A[36], rhs[6];
-    lm_build_api(s, A, rhs);
-    if (use_svd) {
-        solve_sym6_like_svd(A, rhs, s.h);       // SVD<> svdApI(ApI); h = svdApI.backsub(-JtF)
-    } else {
-        Chol6 ch;                               // Cholesky<6> svdApI(ApI); h = svdApI.backsub(-JtF)
-        chol6_compute(A, &ch);
-        chol6_backsub(&ch, rhs, s.h);
+// Cholesky<6>(ApI).backsub(rhs) with every index known at compile time, so that the factor lives in registers (the
+// generic chol6_* of lm.cuh share their arrays with the Jacobi fallback and end up in local memory, which made this
+// serial step the longest part of an evaluation).  Same operations in the same order as TooN's do_compute/backsub;
+// returns the smallest / largest pivot for the conditioning test of the SVD-replacement path.
+__device__ __forceinline__ void chol6_solve_reg(const double (&M)[36], const double (&v)[6], double (&x)[6],
+                                                double &dmin, double &dmax) {
+    double a[36];
+#pragma unroll
+    for (int i = 0; i < 36; i++) a[i] = M[i];
+#pragma unroll
+    for (int col = 0; col < 6; col++) {
+        double inv_diag = 1;
+#pragma unroll
+        for (int row = col; row < 6; row++) {
+            double val = a[row * 6 + col];
+#pragma unroll
+            for (int col2 = 0; col2 < col; col2++) val -= a[col2 * 6 + col] * a[row * 6 + col2];
+            if (row == col) {
+                a[row * 6 + col] = val;
+                inv_diag = 1 / val;
+            } else {
+                a[col * 6 + row] = val;
+                a[row * 6 + col] = val * inv_diag;
+            }
+        }
     }
+    dmin = a[0];
+    dmax = a[0];
+#pragma unroll
+    for (int i = 1; i < 6; i++) {
+        dmin = fmin(dmin, a[i * 6 + i]);
+        dmax = fmax(dmax, a[i * 6 + i]);
+    }
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        double val = v[i];
+#pragma unroll
+        for (int j = 0; j < i; j++) val -= a[i * 6 + j] * y[j];
+        y[i] = val;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) y[i] /= a[i * 6 + i];
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+        double val = y[i];
+#pragma unroll
+        for (int j = i + 1; j < 6; j++) val -= a[j * 6 + i] * x[j];
+        x[i] = val;
+    }
+}
+__device__ __noinline__ void lm_solve_fallback(LMState &s) {   // rank-deficient ApI: SVD<> pseudo-inverse semantics
+    double A[36], rhs[6], h[6];
+    lm_build_api(s, A, rhs);
+    sym_svd_backsub(A, 6, rhs, h);
+    for (int i = 0; i < 6; i++) s.h[i] = h[i];
+}
+__device__ void lm_solve(LMState &s, bool use_svd) {
+    double A[36], rhs[6], h[6], dmin, dmax;
+#pragma unroll
+    for (int i = 0; i < 36; i++) A[i] = s.JtJ[i];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        A[i * 6 + i] = s.JtJ[i * 6 + i] + s.u;  // ApI = JtJ + Identity*u
+        rhs[i] = -s.JtF[i];
+    }
+    // Cholesky<6> svdApI(ApI); h = svdApI.backsub(-JtF)   (main loop, global_tracker.cpp:766-767)
+    // SVD<> svdApI(ApI); h = svdApI.backsub(-JtF)          (init iterations, :659-661): ApI is SPD with a condition
+    // number far below SVD.h's 1e9 cut, so the pseudo-inverse is the inverse and the LDL^T solve returns the same
+    // vector up to rounding; the Jacobi pseudo-inverse is kept for rank-deficient input.
+    chol6_solve_reg(A, rhs, h, dmin, dmax);
+#pragma unroll
+    for (int i = 0; i < 6; i++) s.h[i] = h[i];
+    if (use_svd && !(dmin > 0 && dmin * 1e7 > dmax)) lm_solve_fallback(s);
+#pragma unroll
     for (int i = 0; i < 6; i++) s.Xnew[i] = s.X[i] + s.h[i];
 }
 __device__ void lm_request(LMState &s, const double *X, int res_in, int res_out) {
@@ -349,6 +417,44 @@ struct ResPtrs {
     double *r[3];
 };
 
+// Sum 28 per-thread values over the block in a fixed order: two rounds of 14 columns through shared memory (each
+// warp adds its column's 8 lane-strided entries, then one 5-level shuffle tree) -- 8x fewer shuffles than reducing
+// every value with its own tree.  dst[k * dst_stride] receives sum k (written by one lane).
+template <bool PJ>
+__device__ __forceinline__ void reduce28(const double (&acc)[28], double (*s_acc)[TVR_T], int tid, int lane, int wid,
+                                         double *dst, int dst_stride) {
+    if (PJ) {
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 14; k++) s_acc[k][tid] = acc[half * 14 + k];
+            __syncthreads();
+            for (int k = wid; k < 14; k += TVR_T / 32) {
+                double v = 0;
+#pragma unroll
+                for (int j = 0; j < TVR_T / 32; j++) v += s_acc[k][lane + 32 * j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) dst[(half * 14 + k) * dst_stride] = v;
+            }
+        }
+    } else {
+        double v = acc[27];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if (lane == 0) s_acc[0][wid] = v;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0;
+#pragma unroll
+            for (int ww = 0; ww < TVR_T / 32; ww++) t += s_acc[0][ww];
+            dst[27 * dst_stride] = t;
+        }
+    }
+}
+
 __global__ void k_lm_begin(TrackState *ts, const MapState *old_st, const MapState *f_st, const double *VW,
                            rb_minimizer_args a, double max_r, double max_s_rho, int s_rho_from_state,
                            unsigned int frame_count, int fc_from_state) {
@@ -398,24 +504,25 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
                                                     TrackState *ts, ResPtrs res, unsigned int *ticket, CamC cam,
                                                     int step) {
     __shared__ double sR[9], sV[3], sRM[4];
-    __shared__ double s_red[TVR_T / 32][28];
+    __shared__ double s_acc[14][TVR_T];
     __shared__ int s_whas[TVR_T / 32], s_wfirst[TVR_T / 32];
     __shared__ double s_wlast[TVR_T / 32];
     __shared__ double s_tot[28];
     __shared__ bool s_last;
     LMState &lm = ts->lm;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) {
+    if (tid == 0) {   // the two exponentials run on two warps side by side (each is a serial sin/cos chain)
         double X[6];
         for (int i = 0; i < 6; i++) X[i] = lm.Xeval[i];
         so3_exp(X + 3, sR);                        // SO3<> RotW0(VelRot.slice<3,3>())
-        double wz[3] = {0, 0, X[5]}, RMf[9];
+        for (int i = 0; i < 3; i++) sV[i] = X[i];
+    } else if (tid == 32) {
+        double wz[3] = {0, 0, lm.Xeval[5]}, RMf[9];
         so3_exp(wz, RMf);                          // SO3<> RotM(makeVector(0,0,VelRot[5]))
         sRM[0] = RMf[0];
         sRM[1] = RMf[1];
         sRM[2] = RMf[3];
         sRM[3] = RMf[4];
-        for (int i = 0; i < 3; i++) sV[i] = X[i];
     }
     __syncthreads();
     const int res_in = lm.res_in, res_out = lm.res_out;
@@ -438,7 +545,9 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
         const int m_num = old.m_num[i];
         const float2 m = old.m_m[i];          // all streamed operands are requested up front
         const float n_m = old.n_m[i];
-        const double r_prev = (RW && rin) ? rin[i] : 0.0;
+        double r_prev = (RW && rin) ? rin[i] : 0.0;
+        if (RW && rin && (unsigned long long)__double_as_longlong(r_prev) == RES_SENTINEL)
+            r_prev = ts->carry[res_in * TVR_T + blockIdx.x];   // stale-fi carry of the evaluation that wrote rin
         // KltoI3PMatrix + ProyI3Pto3PMatrix (global_tracker.cpp:552-570, ne10wrapper.h:413-424)
         const double z0 = 1 / rho;
         const double pz_zf0 = cam.inv_zf * z0;
@@ -556,22 +665,6 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
         const double wl = __shfl_sync(0xffffffffu, fi_own, hi);
         if (lane == 0) s_wlast[wid] = wl;
     }
-    // ---- reduction of the 28 sums: warp shuffle, then across warps in fixed order
-    const int nred = PJ ? 28 : 1;
-    if (PJ) {
-#pragma unroll
-        for (int k = 0; k < 28; k++) {
-            double v = acc[k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) s_red[wid][k] = v;
-        }
-    } else {
-        double v = acc[27];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_red[wid][27] = v;
-    }
     __syncthreads();
     int wrote_sentinel = 0;
     if (active) {
@@ -597,12 +690,8 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
         }
     }
     const int any_sentinel = __syncthreads_or(wrote_sentinel);
-    if (tid < 28 && (PJ || tid == 27)) {
-        double v = 0;
-#pragma unroll
-        for (int ww = 0; ww < TVR_T / 32; ww++) v += s_red[ww][tid];
-        ts->partials[(size_t)blockIdx.x * 28 + tid] = v;
-    }
+    // ---- block reduction of the 28 sums (fixed order) straight into the per-block partials, layout [28][TVR_T]
+    reduce28<PJ>(acc, s_acc, tid, lane, wid, ts->partials + blockIdx.x, TVR_T);
     if (tid == 0) {
         int first = TVR_T, has = 0;
         double lastv = 0;
@@ -632,29 +721,15 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
 #pragma unroll
         for (int k = 0; k < 28; k++) pv[k] = 0;
         if (tid < nb) {
-            const double *part = ts->partials + (size_t)tid * 28;
+            const double *part = ts->partials + tid;   // coalesced: thread b reads block b's entry of every sum
             if (PJ) {
 #pragma unroll
-                for (int k = 0; k < 28; k++) pv[k] = __ldcg(part + k);
+                for (int k = 0; k < 28; k++) pv[k] = __ldcg(part + k * TVR_T);
             } else {
-                pv[27] = __ldcg(part + 27);
+                pv[27] = __ldcg(part + 27 * TVR_T);
             }
         }
-        __syncthreads();   // s_red is reused
-        if (PJ) {
-#pragma unroll
-            for (int k = 0; k < 28; k++) {
-                double v = pv[k];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) s_red[wid][k] = v;
-            }
-        } else {
-            double v = pv[27];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) s_red[wid][27] = v;
-        }
+        reduce28<PJ>(pv, s_acc, tid, lane, wid, s_tot, 1);
     }
     // carries: block b inherits the last matched fi of the nearest earlier block that has one (0 at start)
     __shared__ double s_carry[TVR_T], s_blast[TVR_T];
@@ -665,12 +740,6 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
         s_bfirst[tid] = __ldcg(ts->blk_first + tid);
     }
     __syncthreads();
-    if (tid < 28 && (PJ || tid == 27)) {
-        double v = 0;
-#pragma unroll
-        for (int ww = 0; ww < TVR_T / 32; ww++) v += s_red[ww][tid];
-        s_tot[tid] = v;
-    }
     if (tid < nb) {   // nearest earlier block with a match (almost always the previous one)
         double carry = 0;
         for (int b = tid - 1; b >= 0; b--)
@@ -681,16 +750,9 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
         s_carry[tid] = carry;
     }
     __syncthreads();
-    if (tid < nb) {   // thread b patches block b's leading misses (those before its first match)
-        unsigned long long *rbits = reinterpret_cast<unsigned long long *>(rout);
-        const int lim = s_bfirst[tid];
-        const double cv = s_carry[tid];
-        for (int j = 0; j < lim; j++) {
-            const int idx = tid * TVR_T + j;
-            if (idx >= K0) break;
-            if (__ldcg(&rbits[idx]) == RES_SENTINEL) rout[idx] = cv;
-        }
-    }
+    // leading misses of block b (those before its first match) hold RES_SENTINEL in the residual buffer; they are
+    // resolved lazily by the reader (next evaluation / k_resolve_res) from this per-buffer carry table
+    if (tid < nb) ts->carry[res_out * TVR_T + tid] = s_carry[tid];
     // the serial LM step works on a shared-memory copy of the state (global round trips would dominate it)
     __shared__ LMState s_lm;
     {
@@ -727,7 +789,6 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
         double *dst = reinterpret_cast<double *>(&lm);
         for (int k = tid; k < (int)(sizeof(LMState) / sizeof(double)); k += TVR_T) dst[k] = src[k];
     }
-    (void)nred;
 }
 
 template <bool RW, bool PJ>
@@ -771,6 +832,18 @@ int rb_minimizer_enqueue(rb_ctx *c, rb_map *fmap, rb_map *old, const double *VW_
     if ((r = launch_eval<true, true>(c, fmap, old, STEP_MAIN_FIRST))) return r;
     for (int j = 0; j < m; j++)
         if ((r = launch_eval<true, true>(c, fmap, old, j == m - 1 ? STEP_MAIN_LAST : STEP_MAIN_ITER))) return r;
+    return RB_OK;
+}
+
+// materialise the lazily resolved entries of a residual buffer (host export of DResidualNew in rb_try_vel_rot)
+__global__ void __launch_bounds__(TVR_T) k_resolve_res(double *res, const double *carry, const MapState *old_st) {
+    const int i = blockIdx.x * TVR_T + threadIdx.x;
+    if (i >= old_st->kn) return;
+    if (reinterpret_cast<unsigned long long *>(res)[i] == RES_SENTINEL) res[i] = carry[blockIdx.x];
+}
+int rb_resolve_res_enqueue(rb_ctx *c, rb_map *fmap, rb_map *old, int buf) {
+    k_resolve_res<<<fmap->ts_host.nblk, TVR_T, 0, c->stream>>>(fmap->res[buf], fmap->ts_host.carry + buf * TVR_T, old->st);
+    RB_LAUNCH_CHECK();
     return RB_OK;
 }
 
@@ -853,8 +926,10 @@ __global__ void k_set_int(int *p, int v) { *p = v; }
 int rb_forward_match_enqueue(rb_ctx *c, rb_map *old, rb_map *neu) {
     const int nb = rb_div_up(c->kcap, 256);
     TrackState &t = neu->ts_host;
-    k_set_int<<<1, 1, 0, c->stream>>>(&neu->st->fwd_match, 0);
-    RB_LAUNCH_CHECK();
+    if (!c->counters_preset) {   // the per-frame pipeline zeroes the counters in k_frame_pre
+        k_set_int<<<1, 1, 0, c->stream>>>(&neu->st->fwd_match, 0);
+        RB_LAUNCH_CHECK();
+    }
     k_fm_init<<<nb, 256, 0, c->stream>>>(t.fm_best, t.fm_idx, neu->st);
     RB_LAUNCH_CHECK();
     k_fm_pass1<<<nb, 256, 0, c->stream>>>(old->kl, old->st, neu->st, t.fm_best);
@@ -1017,8 +1092,10 @@ __global__ void __launch_bounds__(128) k_directed_match(KLSoA neu, MapState *nst
 int rb_directed_matching_enqueue(rb_ctx *c, rb_map *neu, rb_map *old, const DMatchArgs *args_dev, double min_thr_mod,
                                  double min_thr_ang, double max_radius, double loc_uncertainty, const int *enable_dev) {
     const double cang_min_edge = cos(min_thr_ang * M_PI / 180.0);
-    k_set_int<<<1, 1, 0, c->stream>>>(&neu->st->nmatch, 0);
-    RB_LAUNCH_CHECK();
+    if (!c->counters_preset) {   // the per-frame pipeline zeroes the counters in k_frame_pre
+        k_set_int<<<1, 1, 0, c->stream>>>(&neu->st->nmatch, 0);
+        RB_LAUNCH_CHECK();
+    }
     k_directed_match<<<rb_div_up(c->kcap, 128), 128, 0, c->stream>>>(neu->kl, neu->st, old->kl, old->mask, args_dev,
                                                                     make_cam(c), min_thr_mod, cang_min_edge,
                                                                     max_radius, loc_uncertainty, enable_dev);
@@ -1079,8 +1156,10 @@ __global__ void __launch_bounds__(256) k_regularize_b(KLSoA kl, const MapState *
 int rb_regularize_enqueue(rb_ctx *c, rb_map *m, double thresh, const int *enable_dev) {
     TrackState &t = m->ts_host;
     const int nb = rb_div_up(c->kcap, 256);
-    k_set_int<<<1, 1, 0, c->stream>>>(&m->st->reg_num, 0);
-    RB_LAUNCH_CHECK();
+    if (!c->counters_preset) {   // the per-frame pipeline zeroes the counters in k_frame_pre
+        k_set_int<<<1, 1, 0, c->stream>>>(&m->st->reg_num, 0);
+        RB_LAUNCH_CHECK();
+    }
     k_regularize_a<<<nb, 256, 0, c->stream>>>(m->kl, m->st, t.reg_r, t.reg_s, t.reg_set, thresh, enable_dev);
     RB_LAUNCH_CHECK();
     k_regularize_b<<<nb, 256, 0, c->stream>>>(m->kl, m->st, t.reg_r, t.reg_s, t.reg_set, enable_dev);
