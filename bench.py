@@ -205,7 +205,8 @@ def bench_ours(args):
     nav_dev = np.concatenate(navs)
     # ---------------- roofline of the scale-space passes (same workspace, same batch) --------------------
     passes = {}
-    for pid, name in ((4, "k_rgb2gray"), (0, "k_rowscan<plain>"), (1, "k_rowscan<avg>"), (2, "k_colscan"),
+    rs = "k_rowscan_ring" if os.environ.get("REBVO_B200_ROWSCAN", "2") == "2" else "k_rowscan"
+    for pid, name in ((4, "k_rgb2gray"), (0, rs + "<plain>"), (1, rs + "<avg>"), (2, "k_colscan"),
                       (3, "k_blur_dog")):
         ms, by = pl.bench_pass(pid, B, 20)
         passes[name] = {"ms_per_launch": ms, "bytes_per_launch": by, "gbs": by / (ms * 1e-3) / 1e9}
@@ -236,7 +237,7 @@ def bench_ours(args):
     value = multi.aggregate_fps(K * B, world, t_max)
     e2e = multi.aggregate_fps(K * B, world, t_e2e_max)
     peak, peak_src = peaks()
-    dom = "k_rowscan<avg>"
+    dom = rs + "<avg>"
     roof = {"bound": "hbm", "kernel": dom, "achieved": passes[dom]["gbs"], "peak": peak, "unit": "GB/s",
             "frac": passes[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": passes[dom]["bytes_per_launch"],

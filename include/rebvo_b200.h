@@ -180,6 +180,24 @@ int rb_map_rescale_opt(rb_map *m, double s_rho_min, uint32_t match_num_min, int 
 /* global_tracker's FrameCount (global_tracker.cpp:356,816) of this slot */
 int rb_map_set_frame_count(rb_map *m, uint32_t fc);
 
+/* ---- IMU-mode tracker rows (config 3) -----------------------------------------
+ * global_tracker::TryVel<double> (global_tracker.cpp:829-934): one translation-only evaluation; residuals = K0
+ * doubles (|fi| per old keyline) read and updated in place (may be NULL). */
+int rb_try_vel(rb_map *fmap, rb_map *old, const double Vel[3], double match_thresh, double s_rho_min,
+               uint32_t match_num_thresh, double *residuals, double reweigth_distance, float min_mod,
+               double JtJ[9], double JtF[3], double *score);
+/* global_tracker::Minimizer_V<double> (global_tracker.cpp:1036-1093) */
+int rb_minimizer_v(rb_map *fmap, rb_map *old, double Vel[3], double RVel[9], double match_thresh, int iter_max,
+                   double s_rho_min, uint32_t match_num_thresh, double reweigth_distance, float min_mod,
+                   double *score);
+/* edge_tracker::ExtRotVel(vel, Wx, Rx, X, LocUncert, HubReweigth) (edge_tracker.cpp:1207-1301); *ok = 0 when the
+ * reference would return false (NaN estimate) */
+int rb_ext_rot_vel(rb_map *m, const double vel[3], double Wx[36], double Rx[36], double X[6],
+                   double loc_uncertainty, double hub_reweight, int *ok);
+/* edge_tracker::BiasCorrect (edge_tracker.cpp:1308-1338), host algebra, all arguments in/out like the reference */
+int rb_bias_correct(double X[6], double Wx[36], double Gb[3], double Wb[9], const double Rg[9],
+                    const double Rb[9]);
+
 /* ---- image_undistort --------------------------------------------------------
  * image_undistort::image_undistort + undistort<true>(Image<RGB24Pixel>&, Image<RGB24Pixel>&)
  * (src/VideoLib/image_undistort.cpp:29-94, include/VideoLib/image_undistort.h:63-123, call site

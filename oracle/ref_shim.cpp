@@ -255,3 +255,63 @@ extern "C" void ref_undistort_rgb(int w, int h, float ppx, float ppy, float zfx,
     Image<RGB24Pixel> i((RGB24Pixel *)in, cam.sz), o((RGB24Pixel *)out, cam.sz);
     und.undistort<true>(o, i);
 }
+
+// ---- IMU-mode rows ------------------------------------------------------------------
+extern "C" {
+// global_tracker::TryVel<double> (global_tracker.cpp:829-934); residuals: K0 doubles, updated in place
+double ref_try_vel(void *pn, void *po, const double *V, double match_thresh, double s_rho_min, unsigned mnt,
+                   double *residuals, double rw_dist, float min_mod, double *JtJ, double *JtF) {
+    RefMap *mn = (RefMap *)pn, *mo = (RefMap *)po;
+    Matrix<3, 3> jtj;
+    Vector<3> jtf;
+    double s = mn->gt->TryVel<double>(jtj, jtf, makeVector(V[0], V[1], V[2]), *mo->ef, match_thresh, s_rho_min, mnt,
+                                      residuals, rw_dist, min_mod);
+    M3out(jtj, JtJ);
+    for (int i = 0; i < 3; i++) JtF[i] = jtf[i];
+    return s;
+}
+// global_tracker::Minimizer_V<double> (global_tracker.cpp:1036-1093)
+double ref_minimizer_v(void *pn, void *po, double *V, double *RVel, double match_thresh, int iter_max, double s_rho_min,
+                       unsigned mnt, double rw_dist, float min_mod) {
+    RefMap *mn = (RefMap *)pn, *mo = (RefMap *)po;
+    Vector<3> v = makeVector(V[0], V[1], V[2]);
+    Matrix<3, 3> rv = Zeros;
+    double F = mn->gt->Minimizer_V<double>(v, rv, *mo->ef, match_thresh, iter_max, s_rho_min, mnt, rw_dist, min_mod);
+    for (int i = 0; i < 3; i++) V[i] = v[i];
+    M3out(rv, RVel);
+    return F;
+}
+// edge_tracker::ExtRotVel(vel, Wx, Rx, X, LocUncert, HubReweigth) (edge_tracker.cpp:1207-1301)
+int ref_ext_rot_vel(void *p, const double *V, double *Wx, double *Rx, double *X, double loc_unc, double hub) {
+    RefMap *m = (RefMap *)p;
+    Matrix<6, 6> wx = Zeros, rx = Zeros;
+    Vector<6> x = Zeros;
+    bool ok = m->ef->ExtRotVel(makeVector(V[0], V[1], V[2]), wx, rx, x, loc_unc, hub);
+    for (int i = 0; i < 6; i++) {
+        X[i] = x[i];
+        for (int j = 0; j < 6; j++) {
+            Wx[i * 6 + j] = wx(i, j);
+            Rx[i * 6 + j] = rx(i, j);
+        }
+    }
+    return ok ? 1 : 0;
+}
+// edge_tracker::BiasCorrect (edge_tracker.cpp:1308-1338)
+void ref_bias_correct(double *X, double *Wx, double *Gb, double *Wb, const double *Rg, const double *Rb) {
+    Vector<6> x;
+    Matrix<6, 6> wx;
+    for (int i = 0; i < 6; i++) {
+        x[i] = X[i];
+        for (int j = 0; j < 6; j++) wx(i, j) = Wx[i * 6 + j];
+    }
+    Vector<3> gb = makeVector(Gb[0], Gb[1], Gb[2]);
+    Matrix<3, 3> wb = M3(Wb);
+    edge_tracker::BiasCorrect(x, wx, gb, wb, M3(Rg), M3(Rb));
+    for (int i = 0; i < 6; i++) {
+        X[i] = x[i];
+        for (int j = 0; j < 6; j++) Wx[i * 6 + j] = wx(i, j);
+    }
+    for (int i = 0; i < 3; i++) Gb[i] = gb[i];
+    M3out(wb, Wb);
+}
+}

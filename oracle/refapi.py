@@ -169,6 +169,31 @@ class RefMap:
                                    _p(res_out), _p(JtJ), _p(JtF))
         return s, JtJ, JtF, res_out
 
+    def try_vel(self, old, V, match_thresh, s_rho_min, match_num_thresh, residuals, rw_dist, min_mod):
+        V = np.array(V, np.float64)
+        res = np.ascontiguousarray(residuals[:old.knum()], np.float64).copy()
+        JtJ, JtF = np.zeros((3, 3)), np.zeros(3)
+        self.L.ref_try_vel.restype = C.c_double
+        s = self.L.ref_try_vel(self.h_, old.h_, _p(V), C.c_double(match_thresh), C.c_double(s_rho_min),
+                               C.c_uint(match_num_thresh), _p(res), C.c_double(rw_dist), C.c_float(min_mod), _p(JtJ),
+                               _p(JtF))
+        return s, JtJ, JtF, res
+
+    def minimizer_v(self, old, V, match_thresh, iter_max, s_rho_min, match_num_thresh, rw_dist, min_mod):
+        V = np.array(V, np.float64)
+        RV = np.zeros((3, 3))
+        self.L.ref_minimizer_v.restype = C.c_double
+        F = self.L.ref_minimizer_v(self.h_, old.h_, _p(V), _p(RV), C.c_double(match_thresh), iter_max,
+                                   C.c_double(s_rho_min), C.c_uint(match_num_thresh), C.c_double(rw_dist),
+                                   C.c_float(min_mod))
+        return dict(F=F, V=V, RVel=RV)
+
+    def ext_rot_vel(self, V, loc_unc, hub):
+        V = np.array(V, np.float64)
+        Wx, Rx, X = np.zeros((6, 6)), np.zeros((6, 6)), np.zeros(6)
+        ok = self.L.ref_ext_rot_vel(self.h_, _p(V), _p(Wx), _p(Rx), _p(X), C.c_double(loc_unc), C.c_double(hub))
+        return bool(ok), Wx, Rx, X
+
     def forward_match(self, new):
         return self.L.ref_forward_match(self.h_, new.h_)
 

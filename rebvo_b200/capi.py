@@ -67,7 +67,8 @@ SYMBOLS = ["rb_ctx_create", "rb_ctx_destroy", "rb_last_error", "rb_ctx_sync", "r
            "rb_pipeline_map", "rb_pipeline_launch_count", "rb_pipeline_stage_ms", "rb_pipeline_stream",
            "rb_pipeline_event_record", "rb_pipeline_event_elapsed", "rb_pipeline_bench_pass",
            "rb_pipeline_stage_profile",
-           "rb_undistort_create", "rb_undistort_destroy", "rb_undistort_rgb", "rb_undistort_rgb_dev"]
+           "rb_undistort_create", "rb_undistort_destroy", "rb_undistort_rgb", "rb_undistort_rgb_dev",
+           "rb_try_vel", "rb_minimizer_v", "rb_ext_rot_vel", "rb_bias_correct"]
 
 _lib = None
 
@@ -287,6 +288,30 @@ class Map:
                                               C.byref(e1), C.byref(e2), C.c_double(max_s_rho),
                                               C.c_uint32(match_num_thresh), int(init_iter), _p(WX), C.byref(sc)))
         return dict(F=sc.value, V=V, W=W, RVel=RV, RW0=RW, W_X=WX, rel_err=e1.value, rel_err_score=e2.value)
+
+    def try_vel(self, old, V, match_thresh, s_rho_min, match_num_thresh, residuals, rw_dist, min_mod):
+        V = np.array(V, np.float64)
+        res = np.ascontiguousarray(residuals[:old.knum()], np.float64).copy()
+        JtJ, JtF, s = np.zeros((3, 3)), np.zeros(3), C.c_double(0)
+        self.ctx.check(self.L.rb_try_vel(self.h_, old.h_, _p(V), C.c_double(match_thresh), C.c_double(s_rho_min),
+                                         C.c_uint32(match_num_thresh), _p(res), C.c_double(rw_dist), C.c_float(min_mod),
+                                         _p(JtJ), _p(JtF), C.byref(s)))
+        return s.value, JtJ, JtF, res
+
+    def minimizer_v(self, old, V, match_thresh, iter_max, s_rho_min, match_num_thresh, rw_dist, min_mod):
+        V = np.array(V, np.float64)
+        RV, s = np.zeros((3, 3)), C.c_double(0)
+        self.ctx.check(self.L.rb_minimizer_v(self.h_, old.h_, _p(V), _p(RV), C.c_double(match_thresh), iter_max,
+                                             C.c_double(s_rho_min), C.c_uint32(match_num_thresh), C.c_double(rw_dist),
+                                             C.c_float(min_mod), C.byref(s)))
+        return dict(F=s.value, V=V, RVel=RV)
+
+    def ext_rot_vel(self, V, loc_unc, hub):
+        V = np.array(V, np.float64)
+        Wx, Rx, X, ok = np.zeros((6, 6)), np.zeros((6, 6)), np.zeros(6), C.c_int(0)
+        self.ctx.check(self.L.rb_ext_rot_vel(self.h_, _p(V), _p(Wx), _p(Rx), _p(X), C.c_double(loc_unc),
+                                             C.c_double(hub), C.byref(ok)))
+        return bool(ok.value), Wx, Rx, X
 
     def forward_match(self, new):
         n = C.c_int(0)

@@ -164,6 +164,8 @@ extern "C" int rb_ctx_create(rb_ctx **out, int device, const rb_camera *cam, dou
         const char *ds = getenv("REBVO_B200_DOG_SUB");
         c->dog_sub = ds ? atoi(ds) : 0;   // 0 = whole batch in one go (measured fastest: the passes are latency-bound)
         if (c->dog_sub < 0) c->dog_sub = 0;
+        const char *rs = getenv("REBVO_B200_ROWSCAN");
+        c->rowscan_mode = rs ? atoi(rs) : 2;   // cp.async ring measured 1.85x faster than register prefetch
     }
     // sspace::sspace (sspace.cpp:36-46): filter1 sigma = filter0.sigma_r * k_sigma
     box_plan_one(sigma0, 3, c->plan.d[0], &c->plan.sigma_r[0]);

@@ -91,6 +91,7 @@ struct rb_ctx {
     float *boxtab;       // 6 x 64 reciprocal clipped-area tables (iimage::build_average), see dog.cu
     bool counters_preset; // set by rb_pipeline: match / regularise counters are zeroed by k_frame_pre
     int dog_sub;         // frames per scale-space sub-batch, env REBVO_B200_DOG_SUB (0 = whole batch, the default)
+    int rowscan_mode;    // env REBVO_B200_ROWSCAN: 1 = register-prefetch kernel, 2 = cp.async shared-memory ring
 };
 // layout of rb_ctx::dev_small / pinned (byte offsets)
 #define RB_DS_REEST 0        // int[2 + nbins + 1]  reEstimateThresh min/max bits + histogram

@@ -233,8 +233,180 @@ int rb_dog_gray(rb_ctx *c, DogWS *ws, int nimg) {
     return RB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Row pass, asynchronous version: the raw input of a band is streamed into a per-warp shared-memory ring of
+// 32-column chunks with cp.async (16 B per lane, no registers, NS-3 chunks in flight ahead of the consumer), so the
+// sequential scan never waits for a DRAM round trip.  Tile t of a box-averaged pass needs the columns
+// [32t-d2-1, 32t+31+d2], i.e. chunks t-1, t, t+1 of the rows [y0-d2-1, y0+31+d2]; every integral value is fetched
+// from memory once and the four taps of iimage::average come from shared memory.  Same arithmetic and add order as
+// k_rowscan (bit-identical output).
+#define RING_NS 4          // ring slots: 3 live chunks + 1 in flight
+#define RING_WARPS 4
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, int src_bytes) {
+    const unsigned int s = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+template <bool AVG>
+__global__ void __launch_bounds__(32 * RING_WARPS) k_rowscan_ring(const float *__restrict__ in, float *__restrict__ out,
+                                                                  int w, int h, int nimg, int in_mod, int nper, int d_f0,
+                                                                  int d_f1, const float *__restrict__ tab_f0,
+                                                                  const float *__restrict__ tab_f1, int rmax) {
+    extern __shared__ __align__(16) float smem_ring[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * RING_WARPS + warp;
+    const int bands = (h + 31) >> 5;
+    const int img = gw / bands, band = gw - img * bands;
+    if (img >= nimg) return;
+    // per-warp carve-up: ring [RING_NS][rmax][32], tile [32][33], table [64]
+    float *ring = smem_ring + (size_t)warp * (RING_NS * rmax * 32 + 32 * 33 + BOX_TAB_N);
+    float(*tile)[33] = reinterpret_cast<float(*)[33]>(ring + RING_NS * rmax * 32);
+    float *tab = ring + RING_NS * rmax * 32 + 32 * 33;
+    const size_t N = (size_t)w * h;
+    const float *__restrict__ I = in + (size_t)(img % in_mod) * N;
+    float *__restrict__ O = out + (size_t)img * N;
+    const bool f1 = (img / nper) != 0;
+    const int d = AVG ? (f1 ? d_f1 : d_f0) : 1;
+    const int d2 = AVG ? d / 2 : 0;
+    const int R = AVG ? 32 + d : 32;                 // rows staged per chunk
+    const int yb0 = AVG ? band * 32 - d2 - 1 : band * 32;   // image row of ring row 0
+    if (AVG) {
+        const float *__restrict__ tg = f1 ? tab_f1 : tab_f0;
+        tab[lane] = tg[lane];
+        tab[lane + 32] = tg[lane + 32];
+    }
+    const int y0 = band * 32;
+    const bool band_interior = AVG && (y0 >= d2 + 1) && (y0 + 31 < h - d2);
+    const int nchunk = (w + 31) >> 5;
+    const int sub = lane >> 3, piece = lane & 7;   // 8 lanes x 16 B cover one 32-float row; 4 rows per instruction
+
+    auto issue_chunk = [&](int ci) {
+        if (ci >= 0 && ci < nchunk) {
+            float *dst0 = ring + (size_t)(ci % RING_NS) * rmax * 32;
+            const int gx = ci * 32 + piece * 4;
+            int bytes = (w - gx) * 4;
+            bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+            const int gxc = gx < w ? gx : 0;
+            for (int j = sub; j < R; j += 4) {
+                int gy = yb0 + j;
+                gy = gy < 0 ? 0 : (gy > h - 1 ? h - 1 : gy);
+                cp_async16(dst0 + j * 32 + piece * 4, I + (size_t)gy * w + gxc, bytes);
+            }
+        }
+        cp_async_commit();
+    };
+    // prologue: chunks 0 .. RING_NS-2
+#pragma unroll
+    for (int ci = 0; ci < RING_NS - 1; ci++) issue_chunk(ci);
+
+    float carry = 0.f;
+    for (int t = 0; t < nchunk; t++) {
+        cp_async_wait<RING_NS - 3>();   // chunks <= t+1 have landed (this lane's copies)
+        __syncwarp();                   // ... and everybody else's
+        const int x = t * 32 + lane;
+        const int xc = x < w ? x : w - 1;
+        if (AVG && band_interior && t * 32 >= d2 + 1 && t * 32 + 31 < w - d2) {
+            // centre region of iimage::average for the whole tile (80 % of the tiles): constant tap offsets, no selects
+            const int xr = x + d2, xl = x - d2 - 1;
+            const float *colr = ring + (size_t)((xr >> 5) % RING_NS) * rmax * 32 + (xr & 31);
+            const float *coll = ring + (size_t)((xl >> 5) % RING_NS) * rmax * 32 + (xl & 31);
+            const float *colr_b = colr + d * 32, *coll_b = coll + d * 32;   // bottom taps: ring row r + d
+            const float a = tab[d2 * BOX_TAB_W + d2];
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                float v = colr_b[r * 32] - coll_b[r * 32];   // A - B
+                v = v - colr[r * 32];                        //   - C
+                v = v + coll[r * 32];                        //   + D
+                tile[r][lane] = v * a;
+            }
+        } else if (AVG) {
+            const bool left = xc < d2 + 1, right = xc >= w - d2;
+            const int xr = right ? w - 1 : xc + d2, xl = left ? 0 : xc - d2 - 1;
+            const int cx = left ? xc + d2 + 1 : (right ? w - xc + d2 : d);
+            const float *colr = ring + (size_t)((xr >> 5) % RING_NS) * rmax * 32 + (xr & 31);
+            const float *coll = ring + (size_t)((xl >> 5) % RING_NS) * rmax * 32 + (xl & 31);
+            const float *tcol = tab + (cx - d2 - 1);
+#pragma unroll 8
+            for (int r = 0; r < 32; r++) {
+                const int y = y0 + r;
+                const int yc = y < h ? y : h - 1;
+                const bool top = yc < d2 + 1, bottom = yc >= h - d2;
+                const int jb = (bottom ? h - 1 : yc + d2) - yb0, jt = top ? 0 : yc - d2 - 1 - yb0;
+                const float A = colr[jb * 32], B = coll[jb * 32], C = colr[jt * 32], Dd = coll[jt * 32];
+                const float t1 = bottom ? C : B, t2 = bottom ? B : C;   // bottom band: A-C-B+D, elsewhere A-B-C+D
+                const bool h1 = bottom ? !top : !left, h2 = bottom ? !left : !top;
+                float v = A;
+                v = h1 ? v - t1 : v;
+                v = h2 ? v - t2 : v;
+                v = (!top && !left) ? v + Dd : v;
+                const int cy = top ? yc + d2 + 1 : (bottom ? h - yc + d2 : d);
+                v = v * tcol[(cy - d2 - 1) * BOX_TAB_W];
+                tile[r][lane] = (y < h && x < w) ? v : 0.f;
+            }
+        } else {
+            const float *col = ring + (size_t)(t % RING_NS) * rmax * 32 + lane;
+#pragma unroll 8
+            for (int r = 0; r < 32; r++) {
+                const float v = col[r * 32];
+                tile[r][lane] = (y0 + r < h && x < w) ? v : 0.f;
+            }
+        }
+        __syncwarp();
+        // the chunk t-1 (AVG) / t (plain) is no longer needed: refill its slot with the chunk RING_NS-1 ahead
+        issue_chunk(AVG ? t - 1 + RING_NS : t + RING_NS - 1);
+        float *row = tile[lane];
+#pragma unroll
+        for (int cidx = 0; cidx < 32; cidx++) {
+            carry = carry + row[cidx];  // I(x,y) = I(x-1,y) + in(x,y), iimage.cpp:56-60
+            row[cidx] = carry;
+        }
+        __syncwarp();
+        if (x < w) {
+#pragma unroll 8
+            for (int r = 0; r < 32; r++)
+                if (y0 + r < h) O[(size_t)(y0 + r) * w + x] = tile[r][lane];
+        }
+        __syncwarp();
+    }
+    cp_async_wait<0>();
+}
+
+static int rowscan_ring(rb_ctx *c, int stage, const float *in, float *out, int nimg, int in_mod, int nper) {
+    const int bands = (c->h + 31) / 32;
+    const int blocks = rb_div_up(nimg * bands, RING_WARPS);
+    const int dmax = stage >= 0 ? (c->plan.d[0][stage] > c->plan.d[1][stage] ? c->plan.d[0][stage] : c->plan.d[1][stage]) : 0;
+    const int rmax = 32 + dmax;
+    const size_t smem = (size_t)RING_WARPS * (RING_NS * rmax * 32 + 32 * 33 + BOX_TAB_N) * sizeof(float);
+    if (stage >= 0) {
+        static bool attr_avg = false;
+        if (!attr_avg) {
+            RB_CUDA(cudaFuncSetAttribute(k_rowscan_ring<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_avg = true;
+        }
+        k_rowscan_ring<true><<<blocks, 32 * RING_WARPS, smem, c->stream>>>(
+            in, out, c->w, c->h, nimg, in_mod, nper, c->plan.d[0][stage], c->plan.d[1][stage],
+            c->boxtab + (0 * 3 + stage) * BOX_TAB_N, c->boxtab + (1 * 3 + stage) * BOX_TAB_N, rmax);
+    } else {
+        static bool attr_plain = false;
+        if (!attr_plain) {
+            RB_CUDA(cudaFuncSetAttribute(k_rowscan_ring<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_plain = true;
+        }
+        k_rowscan_ring<false><<<blocks, 32 * RING_WARPS, smem, c->stream>>>(in, out, c->w, c->h, nimg, in_mod, nper, 1, 1,
+                                                                          nullptr, nullptr, rmax);
+    }
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
 // stage < 0: plain row scan of the input; stage 0..1: row scan of box `stage` of both filters
 static int rowscan(rb_ctx *c, int stage, const float *in, float *out, int nimg, int in_mod, int nper) {
+    if (c->rowscan_mode == 2) return rowscan_ring(c, stage, in, out, nimg, in_mod, nper);
     const int bands = (c->h + 31) / 32;
     const int warps = nimg * bands;
     const int blocks = rb_div_up(warps, 4);

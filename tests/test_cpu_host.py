@@ -108,3 +108,30 @@ def test_synthetic_stream_is_deterministic():
     assert np.array_equal(a, b) and a.dtype == np.uint8 and a.shape == (120, 160, 3)
     c = synth.Sequence(w=160, h=120, seed=4).frame(5)[1]
     assert not np.array_equal(a, c)
+
+
+def test_bias_correct_against_reference(built):
+    """edge_tracker::BiasCorrect (gyro-prior fusion, SURVEY.md 8(a) K13) is pure host algebra: rb_bias_correct must
+    reproduce the reference to rounding."""
+    from rebvo_b200 import capi
+    from oracle import refapi
+    if not refapi.available():
+        pytest.skip("oracle/_ref not built")
+    L, R = capi.lib(), refapi.lib()
+    rng = np.random.default_rng(4)
+    for _ in range(10):
+        J = rng.normal(size=(30, 6))
+        Wx = J.T @ J + np.eye(6)
+        X = rng.normal(size=6) * 1e-2
+        Gb = rng.normal(size=3) * 1e-3
+        A = rng.normal(size=(3, 3))
+        Wb = A @ A.T + np.eye(3) * 10
+        Rg = np.eye(3) * 1e-4 + 1e-6 * (A @ A.T)
+        Rb = np.eye(3) * 1e-8
+        a = [np.ascontiguousarray(v.copy()) for v in (X, Wx, Gb, Wb)]
+        b = [np.ascontiguousarray(v.copy()) for v in (X, Wx, Gb, Wb)]
+        Rg, Rb = np.ascontiguousarray(Rg), np.ascontiguousarray(Rb)
+        assert L.rb_bias_correct(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(Rg), _p(Rb)) == 0
+        R.ref_bias_correct(_p(b[0]), _p(b[1]), _p(b[2]), _p(b[3]), _p(Rg), _p(Rb))
+        for x, y in zip(a, b):
+            assert np.allclose(x, y, rtol=1e-9, atol=1e-12 * max(1.0, np.abs(y).max()))
