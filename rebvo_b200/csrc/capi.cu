@@ -164,6 +164,8 @@ extern "C" int rb_ctx_create(rb_ctx **out, int device, const rb_camera *cam, dou
         const char *ds = getenv("REBVO_B200_DOG_SUB");
         c->dog_sub = ds ? atoi(ds) : 0;   // 0 = whole batch in one go (measured fastest: the passes are latency-bound)
         if (c->dog_sub < 0) c->dog_sub = 0;
+        const char *mp = getenv("REBVO_B200_MIN_PERSIST");
+        c->min_persist = !(mp && atoi(mp) == 0);
         const char *rs = getenv("REBVO_B200_ROWSCAN");
         c->rowscan_mode = rs ? atoi(rs) : 2;   // cp.async ring measured 1.85x faster than register prefetch
     }
@@ -189,6 +191,7 @@ extern "C" int rb_ctx_create(rb_ctx **out, int device, const rb_camera *cam, dou
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    c->min_resident = rb_minimizer_resident_blocks(c->sm_count);
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->nseg = c->h * rb_div_up(c->w, 32);
     CK(cudaMalloc(&c->seg_cnt, sizeof(int) * c->nseg));

@@ -91,6 +91,8 @@ struct rb_ctx {
     float *boxtab;       // 6 x 64 reciprocal clipped-area tables (iimage::build_average), see dog.cu
     bool counters_preset; // set by rb_pipeline: match / regularise counters are zeroed by k_frame_pre
     int dog_sub;         // frames per scale-space sub-batch, env REBVO_B200_DOG_SUB (0 = whole batch, the default)
+    bool min_persist;    // whole Minimizer_RV in one persistent launch (env REBVO_B200_MIN_PERSIST=0 disables)
+    int min_resident;    // blocks of that kernel the device keeps resident at once
     int rowscan_mode;    // env REBVO_B200_ROWSCAN: 1 = register-prefetch kernel, 2 = cp.async shared-memory ring
 };
 // layout of rb_ctx::dev_small / pinned (byte offsets)
@@ -132,6 +134,8 @@ struct TrackState {
     double *partials;     // per block x 28 reduction partials
     double *carry;        // [3][256]: per residual buffer and block, the stale-fi value its leading misses inherit
     int nblk;
+    struct MinCtl *ctl;   // request slots / sequence base of the persistent minimiser kernel
+    unsigned long long *ll;   // its per-block partial-sum slots
     // scratch for FordwardMatch / Regularize_1_iter
     unsigned long long *fm_best;
     int *fm_idx;

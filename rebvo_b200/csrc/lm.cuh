@@ -31,8 +31,10 @@ RB_HD void so3_exp(const double w[3], double R[9]) {
         A = 1.0 - theta_sq * one_6th * (1.0 - one_20th * theta_sq);
     } else {
         const double inv_theta = 1.0 / theta;
-        A = sin(theta) * inv_theta;
-        B = (1 - cos(theta)) * (inv_theta * inv_theta);
+        double sn, cs;
+        sincos(theta, &sn, &cs);   // one argument reduction for both
+        A = sn * inv_theta;
+        B = (1 - cs) * (inv_theta * inv_theta);
     }
     const double wx2 = w[0] * w[0], wy2 = w[1] * w[1], wz2 = w[2] * w[2];
     R[0] = 1.0 - B * (wy2 + wz2);

@@ -507,6 +507,16 @@ static int push_impl(rb_pipeline *pl, const uint8_t *rgb, bool on_device, const 
         pl->pframes += n;
     }
     if (nav_out) memcpy(nav_out, pl->nav_pin, sizeof(rb_nav) * n);
+    if (pl->nav_pin[n - 1].Pos[0] != pl->nav_pin[n - 1].Pos[0]) {   // NaN pose: did the persistent minimiser abort?
+        for (int k = 0; k < 2; k++) {
+            int ab = 0;
+            cudaMemcpy(&ab, &pl->maps[k]->ts_host.ctl->abort, sizeof(int), cudaMemcpyDeviceToHost);
+            if (ab) {
+                snprintf(c->err, sizeof(c->err), "Minimizer_RV: persistent kernel timed out waiting for its grid");
+                return RB_ERR_CUDA;
+            }
+        }
+    }
     float ms;
     cudaEventElapsedTime(&ms, pl->ev[0], pl->ev[1]);
     pl->stage_ms[0] = ms;   // copies (+ gray when not replayed as a graph)

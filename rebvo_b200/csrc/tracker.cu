@@ -13,6 +13,17 @@
 #define TVR_T 256
 #define RES_SENTINEL 0x7FF8DEADBEEF0001ull
 
+// Cycle stamps of one evaluation kernel (build with -DRB_TVR_PROF, see scratch tooling); compiled out of the product.
+#ifdef RB_TVR_PROF
+__device__ long long g_tvr_prof[256 * 16];
+#define TVR_STAMP(k) do { if (threadIdx.x == 0) g_tvr_prof[blockIdx.x * 16 + (k)] = clock64(); } while (0)
+extern "C" int rb_debug_fetch(long long *out) {
+    return (int)cudaMemcpyFromSymbol(out, g_tvr_prof, sizeof(long long) * 256 * 16);
+}
+#else
+#define TVR_STAMP(k) do { } while (0)
+#endif
+
 struct CamC {
     double zfm, inv_zf;
     float ppx, ppy;
@@ -42,6 +53,10 @@ int rb_track_state_alloc(rb_ctx *c, rb_map *m) {
     RB_CUDA(cudaMalloc(&host.partials, sizeof(double) * 28 * TVR_T));
     RB_CUDA(cudaMalloc(&host.carry, sizeof(double) * 3 * TVR_T));
     RB_CUDA(cudaMemsetAsync(host.carry, 0, sizeof(double) * 3 * TVR_T, c->stream));
+    RB_CUDA(cudaMalloc(&host.ctl, sizeof(MinCtl)));
+    RB_CUDA(cudaMemsetAsync(host.ctl, 0, sizeof(MinCtl), c->stream));
+    RB_CUDA(cudaMalloc(&host.ll, sizeof(unsigned long long) * 64 * TVR_T));
+    RB_CUDA(cudaMemsetAsync(host.ll, 0, sizeof(unsigned long long) * 64 * TVR_T, c->stream));
     RB_CUDA(cudaMalloc(&host.fm_best, sizeof(unsigned long long) * K));
     RB_CUDA(cudaMalloc(&host.fm_idx, sizeof(int) * K));
     RB_CUDA(cudaMalloc(&host.reg_r, sizeof(double) * K));
@@ -61,6 +76,8 @@ void rb_track_state_free(rb_map *m) {
     cudaFree(h.blk_last_fi);
     cudaFree(h.partials);
     cudaFree(h.carry);
+    cudaFree(h.ctl);
+    cudaFree(h.ll);
     cudaFree(h.fm_best);
     cudaFree(h.fm_idx);
     cudaFree(h.reg_r);
@@ -177,6 +194,7 @@ __device__ void lm_build_api(const LMState &s, double *A, double *rhs) {
 // generic chol6_* of lm.cuh share their arrays with the Jacobi fallback and end up in local memory, which made this
 // serial step the longest part of an evaluation).  Same operations in the same order as TooN's do_compute/backsub;
 // returns the smallest / largest pivot for the conditioning test of the SVD-replacement path.
+template <bool RECIP_SCALE = false>   // true: y *= 1/diag (TooN's matrix backsub, used by get_inverse); false: y /= diag
 __device__ __forceinline__ void chol6_solve_reg(const double (&M)[36], const double (&v)[6], double (&x)[6],
                                                 double &dmin, double &dmax) {
     double a[36];
@@ -215,7 +233,10 @@ __device__ __forceinline__ void chol6_solve_reg(const double (&M)[36], const dou
         y[i] = val;
     }
 #pragma unroll
-    for (int i = 0; i < 6; i++) y[i] /= a[i * 6 + i];
+    for (int i = 0; i < 6; i++) {
+        if (RECIP_SCALE) y[i] *= 1 / a[i * 6 + i];
+        else y[i] /= a[i * 6 + i];
+    }
 #pragma unroll
     for (int i = 5; i >= 0; i--) {
         double val = y[i];
@@ -317,18 +338,29 @@ __device__ void lm_after_prior_pass(LMState &s) {  // :734-747
     s.iR = t;
     lm_request(s, s.X, s.iR, s.iRN);
 }
-__device__ void lm_finalize(LMState &s, MapState *fst) {   // :793-816
-    Chol6 ch;
-    chol6_compute(s.JtJ, &ch);
-    double RRV[36];
-    chol6_inverse(&ch, RRV);
+// RRV = Cholesky<6>(JtJ).get_inverse() (:795-801): column c = backsub(e_c) with the matrix overload's y *= 1/diag.
+// Threads 0..5 of the calling block each factorise (registers) and solve one column.
+__device__ __forceinline__ void lm_finalize_cov(LMState &s, int tid) {
+    if (tid < 6) {
+        double A[36], ec[6], x[6], dmin, dmax;
+#pragma unroll
+        for (int i = 0; i < 36; i++) A[i] = s.JtJ[i];
+#pragma unroll
+        for (int i = 0; i < 6; i++) ec[i] = (i == tid) ? 1.0 : 0.0;
+        chol6_solve_reg<true>(A, ec, x, dmin, dmax);
+        if (tid < 3) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) s.RVel[i * 3 + tid] = x[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; i++) s.RW0[i * 3 + (tid - 3)] = x[3 + i];
+        }
+    }
+}
+__device__ void lm_finalize(LMState &s, MapState *fst) {   // :793-816; RVel / RW0 come from lm_finalize_cov
     for (int i = 0; i < 3; i++) {
         s.Vel[i] = s.X[i];
         s.W0[i] = s.X[3 + i];
-        for (int j = 0; j < 3; j++) {
-            s.RVel[i * 3 + j] = RRV[i * 6 + j];
-            s.RW0[i * 3 + j] = RRV[(i + 3) * 6 + (j + 3)];
-        }
     }
     for (int i = 0; i < 36; i++) s.W_X[i] = s.JtJ[i];
     if (s.eff_steps > 0) {
@@ -417,48 +449,69 @@ struct ResPtrs {
     double *r[3];
 };
 
-// Sum 28 per-thread values over the block in a fixed order: two rounds of 14 columns through shared memory (each
-// warp adds its column's 8 lane-strided entries, then one 5-level shuffle tree) -- 8x fewer shuffles than reducing
-// every value with its own tree.  dst[k * dst_stride] receives sum k (written by one lane).
+// Sum 28 per-thread values over the block in a fixed order.  Inside a warp: a transposing butterfly -- at distance
+// 16, 8, .. 1 every lane keeps one half of its values and trades the other half with its partner, so after 5 steps
+// (16+8+4+2+1 = 31 exchanges instead of 28 x 5) lane l holds the warp's sum of value l.  Across warps: one
+// shared-memory hop, thread k < 28 adds the warps' sums of value k in warp order.  dst[k * dst_stride] = sum k.
+struct Red28Smem {
+    double part[TVR_T / 32][32];
+};
+__device__ __forceinline__ double warp_transpose_sum28(const double (&acc)[28], int lane) {
+    double v[16];
+    {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const double hi = (k + 16 < 28) ? acc[k + 16] : 0.0;
+            const double keep = up ? hi : acc[k], send = up ? acc[k] : hi;
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int k = 0; k < o; k++) {
+            const double keep = up ? v[k + o] : v[k], send = up ? v[k] : v[k + o];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0];
+}
 template <bool PJ>
-__device__ __forceinline__ void reduce28(const double (&acc)[28], double (*s_acc)[TVR_T], int tid, int lane, int wid,
+__device__ __forceinline__ void reduce28(const double (&acc)[28], Red28Smem &rs, int tid, int lane, int wid,
                                          double *dst, int dst_stride) {
     if (PJ) {
+        const double w = warp_transpose_sum28(acc, lane);
+        __syncthreads();   // the previous user of rs is done
+        rs.part[wid][lane] = w;
+        __syncthreads();
+        if (tid < 28) {
+            double t = rs.part[0][tid];
 #pragma unroll
-        for (int half = 0; half < 2; half++) {
-            __syncthreads();
-#pragma unroll
-            for (int k = 0; k < 14; k++) s_acc[k][tid] = acc[half * 14 + k];
-            __syncthreads();
-            for (int k = wid; k < 14; k += TVR_T / 32) {
-                double v = 0;
-#pragma unroll
-                for (int j = 0; j < TVR_T / 32; j++) v += s_acc[k][lane + 32 * j];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) dst[(half * 14 + k) * dst_stride] = v;
-            }
+            for (int ww = 1; ww < TVR_T / 32; ww++) t += rs.part[ww][tid];
+            dst[tid * dst_stride] = t;
         }
     } else {
         double v = acc[27];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         __syncthreads();
-        if (lane == 0) s_acc[0][wid] = v;
+        if (lane == 0) rs.part[0][wid] = v;
         __syncthreads();
         if (tid == 0) {
             double t = 0;
 #pragma unroll
-            for (int ww = 0; ww < TVR_T / 32; ww++) t += s_acc[0][ww];
+            for (int ww = 0; ww < TVR_T / 32; ww++) t += rs.part[0][ww];
             dst[27 * dst_stride] = t;
         }
     }
 }
 
-__global__ void k_lm_begin(TrackState *ts, const MapState *old_st, const MapState *f_st, const double *VW,
-                           rb_minimizer_args a, double max_r, double max_s_rho, int s_rho_from_state,
-                           unsigned int frame_count, int fc_from_state) {
-    LMState &s = ts->lm;
+// Minimizer_RV preamble (global_tracker.cpp:596-650): configuration, LM variables, request of the first evaluation
+__device__ void lm_begin(LMState &s, const MapState *old_st, const MapState *f_st, const double *VW,
+                         const rb_minimizer_args &a, double max_r, double max_s_rho, int s_rho_from_state,
+                         unsigned int frame_count, int fc_from_state) {
     s.max_r = max_r;
     s.match_thresh = a.match_thresh;
     s.k_huber = a.reweight_distance;
@@ -495,21 +548,335 @@ __global__ void k_lm_begin(TrackState *ts, const MapState *old_st, const MapStat
         lm_request(s, s.X, -1, s.iRt);
     }
 }
+__global__ void k_lm_begin(TrackState *ts, const MapState *old_st, const MapState *f_st, const double *VW,
+                           rb_minimizer_args a, double max_r, double max_s_rho, int s_rho_from_state,
+                           unsigned int frame_count, int fc_from_state) {
+    lm_begin(ts->lm, old_st, f_st, VW, a, max_r, max_s_rho, s_rho_from_state, frame_count, fc_from_state);
+}
 
-// One TryVelRot evaluation (global_tracker.cpp:285-543) + the LM step that follows it.
+// ---- pieces of one TryVelRot evaluation (global_tracker.cpp:285-543), shared by the one-launch-per-evaluation
+// kernel and by the persistent whole-minimisation kernel -------------------------------------------------------
+struct TvrConst {          // constants of one minimisation
+    double max_r, match_thresh, s_rho_min, k_huber;
+    unsigned int mnt;      // min(match_num_thresh, FrameCount)
+};
+struct KlOp {              // operands of one old keyline; x0/y0/z0 do not depend on the evaluated pose
+    float2 m;
+    double x0, y0, z0, s_rho;
+    int m_num;
+    float n_m;
+};
+__device__ __forceinline__ KlOp load_klop(const KLSoA &old, int i, const CamC &cam) {
+    KlOp o;
+    const float2 pm = old.p_m[i];
+    const double rho = old.rho[i];
+    o.s_rho = old.s_rho[i];
+    o.m_num = old.m_num[i];
+    o.m = old.m_m[i];
+    o.n_m = old.n_m[i];
+    // KltoI3PMatrix + ProyI3Pto3PMatrix (global_tracker.cpp:552-570, ne10wrapper.h:413-424)
+    o.z0 = 1 / rho;
+    const double pz_zf0 = cam.inv_zf * o.z0;
+    o.x0 = pz_zf0 * (double)pm.x;
+    o.y0 = pz_zf0 * (double)pm.y;
+    return o;
+}
+// a / b given y = RN(1/b): q = RN(a*y), one exact remainder, one correction -> RN(a/b) (Markstein); the seven
+// divisions by q_rho of a keyline share one reciprocal.  Checked against IEEE division on 4e8 random and adversarial
+// operand pairs (no mismatch); the only difference is the sign of a zero quotient of a negative zero.
+__device__ __forceinline__ double div_with_rcp(double a, double b, double y) {
+    const double q = a * y;
+    const double r = fma(-b, q, a);
+    return fma(r, y, q);
+}
+struct TvrSmem {
+    Red28Smem red;
+    double wlast[TVR_T / 32];
+    int whas[TVR_T / 32];
+};
+struct TrackPtrs {         // the pointers inside TrackState, passed by value (no dependent load to reach them)
+    LMState *lm;
+    int *blk_has;
+    double *blk_last_fi, *partials, *carry;
+    struct MinCtl *ctl;
+    unsigned long long *ll;   // [MIN_LL_WORDS][TVR_T] self-validating partial-sum slots of the persistent kernel
+};
+
+// per-keyline part: projection, field lookup, residual, Jacobian products
+template <bool RW, bool PJ>
+__device__ __forceinline__ void tvr_body(const KlOp &o, bool has_rin, double r_prev, const double *sR,
+                                         const double *sV, const double *sRM, const TvrConst &tc, const CamC &cam,
+                                         const unsigned long long *__restrict__ field,
+                                         const float4 *__restrict__ fpack, double *__restrict__ rout,
+                                         int *__restrict__ m_id_f, int i, double (&acc)[28], bool &matched,
+                                         bool &need, double &fi_own, bool &wrote, double &r_w) {
+    const double max_r = tc.max_r;
+    const double x0 = o.x0, y0 = o.y0, z0 = o.z0;
+    // SE3on3PMatrix (ne10wrapper.h:375-405): MulC, MlAc, MlAc, then Vel + .
+    double px = sR[0] * x0;
+    px = px + sR[1] * y0;
+    px = px + sR[2] * z0;
+    px = sV[0] + px;
+    double py = sR[3] * x0;
+    py = py + sR[4] * y0;
+    py = py + sR[5] * z0;
+    py = sV[1] + py;
+    double pz = sR[6] * x0;
+    pz = pz + sR[7] * y0;
+    pz = pz + sR[8] * z0;
+    pz = sV[2] + pz;
+    // ProyP3toI3PMatrix (ne10wrapper.h:429-445)
+    const double rho_p = 1 / pz;
+    const double pz_zf = cam.zfm * rho_p;
+    const double qx = pz_zf * px, qy = pz_zf * py;
+    double f = 0, dfx = 0, dfy = 0;
+    int mid_f = -1;
+    const bool skip = (o.s_rho > tc.s_rho_min) || ((unsigned int)o.m_num < tc.mnt);   // :356
+    if (!skip) {
+        const double pix = qx + (double)cam.ppx, piy = qy + (double)cam.ppy;   // cam_mod.Hom2Img
+        const int x = (int)(pix + 0.5), y = (int)(piy + 0.5);                   // util::round2int_positive
+        double weight = 1;
+        if (RW && has_rin) {
+            const double r = fabs(r_prev);
+            if (r > tc.k_huber) weight = tc.k_huber / r;                       // :370-372
+        }
+        if (x < 1 || y < 1 || x >= cam.w - 1 || y >= cam.h - 1) {               // :376
+            f = max_r;
+            if (RW) f *= weight;
+            rout[i] = max_r;
+            wrote = true;
+            r_w = max_r;
+        } else {
+            const float mrx = (float)(sRM[0] * (double)o.m.x + sRM[1] * (double)o.m.y);   // :386-388
+            const float mry = (float)(sRM[2] * (double)o.m.x + sRM[3] * (double)o.m.y);
+            const unsigned long long key = field[(size_t)y * cam.w + x];
+            bool hit = false;
+            if (key != ~0ull) {
+                const int ikl = (int)(0xFFFFFFFFu - (unsigned int)(key & 0xFFFFFFFFull));
+                const float4 a = fpack[2 * ikl], b = fpack[2 * ikl + 1];
+                const double p_n2 = (double)(o.n_m * o.n_m);                   // Test_f_k (global_tracker.h:89-104)
+                const double p_esc = (double)(mrx * a.x + mry * a.y);
+                if (!(fabs(p_esc - p_n2) > tc.match_thresh * p_n2)) {
+                    const double dx = pix - (double)a.z, dy = piy - (double)a.w;   // Calc_f_J2 :254-262
+                    const double fi = dx * (double)b.x + dy * (double)b.y;
+                    dfx = (double)b.x;
+                    dfy = (double)b.y;
+                    f = fi;
+                    matched = true;
+                    fi_own = fi;
+                    mid_f = ikl;
+                    hit = true;
+                }
+            }
+            if (!hit) {
+                f = max_r;
+                need = true;
+            }
+            if (RW) {
+                f *= weight;
+                dfx *= weight;
+                dfy *= weight;
+            }
+        }
+    }
+    m_id_f[i] = mid_f;
+    // Jacobians (:419-449) and the 1/q_rho scaling (:452-463)
+    const double qvel = (cam.zfm * dfx * sV[0] + cam.zfm * dfy * sV[1]) + (qx * dfx + qy * dfy) * sV[2];
+    double q_rho = sqrt(o.s_rho * qvel * o.s_rho * qvel + 1);
+    if (!RW) q_rho = o.s_rho;
+    if (PJ) {
+        double t0 = cam.zfm * rho_p;
+        double J0 = t0 * dfx, J1 = t0 * dfy;
+        t0 = rho_p * qx;
+        double J2 = t0 * dfx;
+        t0 = rho_p * qy;
+        J2 = J2 + t0 * dfy;
+        double J3 = J1 * pz;
+        J3 = J3 + J2 * py;
+        double J4 = J0 * pz;
+        J4 = J4 + J2 * px;
+        t0 = J0 * py;
+        double J5 = -1.0 * t0;
+        J5 = J5 + J1 * px;
+        const double iq = 1 / q_rho;
+        double J[6] = {div_with_rcp(J0, q_rho, iq), div_with_rcp(J1, q_rho, iq), div_with_rcp(J2, q_rho, iq),
+                       div_with_rcp(J3, q_rho, iq), div_with_rcp(J4, q_rho, iq), div_with_rcp(J5, q_rho, iq)};
+        f = div_with_rcp(f, q_rho, iq);
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int b = a; b < 6; b++) acc[k++] = J[a] * J[b];
+#pragma unroll
+        for (int a = 0; a < 6; a++) acc[21 + a] = J[a] * f;
+    } else {
+        f = f / q_rho;
+    }
+    acc[27] = f * f;
+}
+
+// "DResidualNew[ikl]=fi" keeps the fi of the last matched keyline before ikl (fi is a function-level variable,
+// :341,399-408): in-block scan here; misses that precede the block's first match get RES_SENTINEL and are resolved
+// lazily by whoever reads the buffer, from the per-(buffer, block) carry table.  Then the block's 28 sums go to
+// partials[k][vb] in a fixed order, and its "has a match / last matched fi" summary to blk_has / blk_last_fi.
+template <bool PJ>
+__device__ __forceinline__ void tvr_block_tail(bool active, bool matched, bool need, double fi_own,
+                                               double *__restrict__ rout, int i, const double (&acc)[28],
+                                               TvrSmem &sm, double *dst, int dst_stride, int *has_out,
+                                               double *last_out, int tid, int lane, int wid, bool &wrote,
+                                               double &r_w) {
+    const unsigned int bal = __ballot_sync(0xffffffffu, matched);
+    const unsigned int lower = bal & ((1u << lane) - 1u);
+    const int src = lower ? 31 - __clz(lower) : 0;
+    const double prev_fi = __shfl_sync(0xffffffffu, fi_own, src);
+    const int hi = bal ? 31 - __clz(bal) : 0;
+    const double wl = __shfl_sync(0xffffffffu, fi_own, hi);
+    __syncthreads();   // the previous user of sm is done
+    if (lane == 0) {
+        sm.whas[wid] = bal != 0;
+        sm.wlast[wid] = wl;
+    }
+    __syncthreads();
+    if (active) {
+        if (matched) {
+            rout[i] = fi_own;
+            wrote = true;
+            r_w = fi_own;
+        } else if (need) {
+            double v = prev_fi;
+            bool found = lower != 0;
+            if (!found) {
+                for (int ww = wid - 1; ww >= 0; ww--)
+                    if (sm.whas[ww]) {
+                        v = sm.wlast[ww];
+                        found = true;
+                        break;
+                    }
+            }
+            if (!found) v = __longlong_as_double((long long)RES_SENTINEL);
+            reinterpret_cast<unsigned long long *>(rout)[i] = (unsigned long long)__double_as_longlong(v);
+            wrote = true;
+            r_w = v;
+        }
+    }
+    if (tid == 0) {
+        int has = 0;
+        double lastv = 0;
+        for (int ww = 0; ww < TVR_T / 32; ww++)
+            if (sm.whas[ww]) {
+                has = 1;
+                lastv = sm.wlast[ww];
+            }
+        *has_out = has;
+        *last_out = lastv;
+    }
+    reduce28<PJ>(acc, sm.red, tid, lane, wid, dst, dst_stride);
+}
+
+// grid reduction of the per-block partials (layout [28][TVR_T], nb <= TVR_T blocks) in a fixed order: warp w owns sums
+// w, w+8, ...; its lanes add the lane-strided entries (every load in flight at once), then one xor tree per sum.
+// The caller synchronises before reading s_tot.
+template <bool PJ>
+__device__ __forceinline__ void tvr_grid_reduce(const double *partials, int nb, double *s_tot, int lane, int wid) {
+    constexpr int NW = TVR_T / 32;
+    if (PJ) {
+        double v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = wid + NW * q;
+            double x[NW];
+#pragma unroll
+            for (int j = 0; j < NW; j++) {
+                const int b = lane + 32 * j;
+                x[j] = (k < 28 && b < nb) ? __ldcg(partials + k * TVR_T + b) : 0.0;
+            }
+            double t = x[0];
+#pragma unroll
+            for (int j = 1; j < NW; j++) t += x[j];
+            v[q] = t;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int q = 0; q < 4; q++) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+        if (lane == 0)
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (wid + NW * q < 28) s_tot[wid + NW * q] = v[q];
+    } else if (wid == 0) {
+        double t = 0;
+#pragma unroll
+        for (int j = 0; j < NW; j++) {
+            const int b = lane + 32 * j;
+            t += (b < nb) ? __ldcg(partials + 27 * TVR_T + b) : 0.0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) s_tot[27] = t;
+    }
+}
+
+// stale-fi carries: block b inherits the last matched fi of the nearest earlier block that has one (0 at the start);
+// one ballot per warp finds it.  blockDim.x == TVR_T >= nb; thread b brings block b's summary (0 beyond nb).
+__device__ __forceinline__ double tvr_carries(int has, double lastv, double *carry_out, int nb, double *s_blast,
+                                            unsigned int *s_wmask, int tid, int lane, int wid) {
+    const unsigned int mask = __ballot_sync(0xffffffffu, has != 0);
+    s_blast[tid] = lastv;
+    if (lane == 0) s_wmask[wid] = mask;
+    __syncthreads();
+    double cy = 0;
+    if (tid < nb) {
+        const unsigned int lower = mask & ((1u << lane) - 1u);
+        if (lower) {
+            cy = s_blast[wid * 32 + 31 - __clz(lower)];
+        } else {
+            for (int ww = wid - 1; ww >= 0; ww--) {
+                const unsigned int mm = s_wmask[ww];
+                if (mm) {
+                    cy = s_blast[ww * 32 + 31 - __clz(mm)];
+                    break;
+                }
+            }
+        }
+        carry_out[tid] = cy;
+    }
+    return cy;
+}
+
+// totals -> JtJn / JtFn / score of the evaluation (sign fix-ups :484-490)
+template <bool PJ>
+__device__ __forceinline__ void lm_ingest(LMState &L, const double *s_tot) {
+    if (PJ) {
+        int k = 0;
+        for (int a = 0; a < 6; a++)
+            for (int b = a; b < 6; b++) L.JtJn[a * 6 + b] = s_tot[k++];
+        for (int a = 0; a < 6; a++) L.JtFn[a] = s_tot[21 + a];
+        for (int a = 0; a < 2; a++) {
+            L.JtFn[a + 2] = -L.JtFn[a + 2];
+            for (int b = 0; b < 2; b++) {
+                L.JtJn[(a + 0) * 6 + (b + 2)] = -L.JtJn[(a + 0) * 6 + (b + 2)];
+                L.JtJn[(a + 2) * 6 + (b + 4)] = -L.JtJn[(a + 2) * 6 + (b + 4)];
+            }
+        }
+        for (int a = 0; a < 6; a++)
+            for (int b = a + 1; b < 6; b++) L.JtJn[b * 6 + a] = L.JtJn[a * 6 + b];
+    }
+    L.last_score = s_tot[27];
+    L.n_eval++;
+}
+
+// One TryVelRot evaluation + the LM step that follows it, one launch per evaluation (stage-level API rb_try_vel_rot,
+// and minimisations whose keyline capacity exceeds what the persistent kernel below can keep co-resident).
 template <bool RW, bool PJ>
 __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *__restrict__ old_st,
                                                     const unsigned long long *__restrict__ field,
-                                                    const float4 *__restrict__ fpack, MapState *f_st,
-                                                    TrackState *ts, ResPtrs res, unsigned int *ticket, CamC cam,
-                                                    int step) {
+                                                    const float4 *__restrict__ fpack, MapState *f_st, TrackPtrs tp,
+                                                    ResPtrs res, unsigned int *ticket, CamC cam, int step) {
     __shared__ double sR[9], sV[3], sRM[4];
-    __shared__ double s_acc[14][TVR_T];
-    __shared__ int s_whas[TVR_T / 32], s_wfirst[TVR_T / 32];
-    __shared__ double s_wlast[TVR_T / 32];
+    __shared__ TvrSmem sm;
     __shared__ double s_tot[28];
     __shared__ bool s_last;
-    LMState &lm = ts->lm;
+    LMState &lm = *tp.lm;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) {   // the two exponentials run on two warps side by side (each is a serial sin/cos chain)
         double X[6];
@@ -526,8 +893,12 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
     }
     __syncthreads();
     const int res_in = lm.res_in, res_out = lm.res_out;
-    const double max_r = lm.max_r, match_thresh = lm.match_thresh, s_rho_min = lm.s_rho_min, k_huber = lm.k_huber;
-    const unsigned int mnt = lm.match_num_thresh < lm.frame_count ? lm.match_num_thresh : lm.frame_count;
+    TvrConst tc;
+    tc.max_r = lm.max_r;
+    tc.match_thresh = lm.match_thresh;
+    tc.s_rho_min = lm.s_rho_min;
+    tc.k_huber = lm.k_huber;
+    tc.mnt = lm.match_num_thresh < lm.frame_count ? lm.match_num_thresh : lm.frame_count;
     const double *__restrict__ rin = (RW && res_in >= 0) ? res.r[res_in] : nullptr;
     double *__restrict__ rout = res.r[res_out];
 
@@ -537,175 +908,18 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
     double acc[28];
 #pragma unroll
     for (int k = 0; k < 28; k++) acc[k] = 0;
-    bool matched = false, need = false;
-    double fi_own = 0;
+    bool matched = false, need = false, wrote = false;
+    double fi_own = 0, r_w = 0;
     if (active) {
-        const float2 pm = old.p_m[i];
-        const double rho = old.rho[i], s_rho = old.s_rho[i];
-        const int m_num = old.m_num[i];
-        const float2 m = old.m_m[i];          // all streamed operands are requested up front
-        const float n_m = old.n_m[i];
+        const KlOp o = load_klop(old, i, cam);
         double r_prev = (RW && rin) ? rin[i] : 0.0;
         if (RW && rin && (unsigned long long)__double_as_longlong(r_prev) == RES_SENTINEL)
-            r_prev = ts->carry[res_in * TVR_T + blockIdx.x];   // stale-fi carry of the evaluation that wrote rin
-        // KltoI3PMatrix + ProyI3Pto3PMatrix (global_tracker.cpp:552-570, ne10wrapper.h:413-424)
-        const double z0 = 1 / rho;
-        const double pz_zf0 = cam.inv_zf * z0;
-        const double x0 = pz_zf0 * (double)pm.x, y0 = pz_zf0 * (double)pm.y;
-        // SE3on3PMatrix (ne10wrapper.h:375-405): MulC, MlAc, MlAc, then Vel + .
-        double px = sR[0] * x0;
-        px = px + sR[1] * y0;
-        px = px + sR[2] * z0;
-        px = sV[0] + px;
-        double py = sR[3] * x0;
-        py = py + sR[4] * y0;
-        py = py + sR[5] * z0;
-        py = sV[1] + py;
-        double pz = sR[6] * x0;
-        pz = pz + sR[7] * y0;
-        pz = pz + sR[8] * z0;
-        pz = sV[2] + pz;
-        // ProyP3toI3PMatrix (ne10wrapper.h:429-445)
-        const double rho_p = 1 / pz;
-        const double pz_zf = cam.zfm * rho_p;
-        const double qx = pz_zf * px, qy = pz_zf * py;
-        double f = 0, dfx = 0, dfy = 0;
-        int mid_f = -1;
-        const bool skip = (s_rho > s_rho_min) || ((unsigned int)m_num < mnt);   // :356
-        if (!skip) {
-            const double pix = qx + (double)cam.ppx, piy = qy + (double)cam.ppy;   // cam_mod.Hom2Img
-            const int x = (int)(pix + 0.5), y = (int)(piy + 0.5);                   // util::round2int_positive
-            double weight = 1;
-            if (RW && rin) {
-                const double r = fabs(r_prev);
-                if (r > k_huber) weight = k_huber / r;                             // :370-372
-            }
-            if (x < 1 || y < 1 || x >= cam.w - 1 || y >= cam.h - 1) {               // :376
-                f = max_r;
-                if (RW) f *= weight;
-                rout[i] = max_r;
-            } else {
-                const float mrx = (float)(sRM[0] * (double)m.x + sRM[1] * (double)m.y);   // :386-388
-                const float mry = (float)(sRM[2] * (double)m.x + sRM[3] * (double)m.y);
-                const unsigned long long key = field[(size_t)y * cam.w + x];
-                bool hit = false;
-                if (key != ~0ull) {
-                    const int ikl = (int)(0xFFFFFFFFu - (unsigned int)(key & 0xFFFFFFFFull));
-                    const float4 a = fpack[2 * ikl], b = fpack[2 * ikl + 1];
-                    const double p_n2 = (double)(n_m * n_m);                       // Test_f_k (global_tracker.h:89-104)
-                    const double p_esc = (double)(mrx * a.x + mry * a.y);
-                    if (!(fabs(p_esc - p_n2) > match_thresh * p_n2)) {
-                        const double dx = pix - (double)a.z, dy = piy - (double)a.w;   // Calc_f_J2 :254-262
-                        const double fi = dx * (double)b.x + dy * (double)b.y;
-                        dfx = (double)b.x;
-                        dfy = (double)b.y;
-                        f = fi;
-                        matched = true;
-                        fi_own = fi;
-                        mid_f = ikl;
-                        hit = true;
-                    }
-                }
-                if (!hit) {
-                    f = max_r;
-                    need = true;
-                }
-                if (RW) {
-                    f *= weight;
-                    dfx *= weight;
-                    dfy *= weight;
-                }
-            }
-        }
-        old.m_id_f[i] = mid_f;
-        // Jacobians (:419-449) and the 1/q_rho scaling (:452-463)
-        const double qvel = (cam.zfm * dfx * sV[0] + cam.zfm * dfy * sV[1]) + (qx * dfx + qy * dfy) * sV[2];
-        double q_rho = sqrt(s_rho * qvel * s_rho * qvel + 1);
-        if (!RW) q_rho = s_rho;
-        if (PJ) {
-            double t0 = cam.zfm * rho_p;
-            double J0 = t0 * dfx, J1 = t0 * dfy;
-            t0 = rho_p * qx;
-            double J2 = t0 * dfx;
-            t0 = rho_p * qy;
-            J2 = J2 + t0 * dfy;
-            double J3 = J1 * pz;
-            J3 = J3 + J2 * py;
-            double J4 = J0 * pz;
-            J4 = J4 + J2 * px;
-            t0 = J0 * py;
-            double J5 = -1.0 * t0;
-            J5 = J5 + J1 * px;
-            double J[6] = {J0 / q_rho, J1 / q_rho, J2 / q_rho, J3 / q_rho, J4 / q_rho, J5 / q_rho};
-            f = f / q_rho;
-            int k = 0;
-#pragma unroll
-            for (int a = 0; a < 6; a++)
-#pragma unroll
-                for (int b = a; b < 6; b++) acc[k++] = J[a] * J[b];
-#pragma unroll
-            for (int a = 0; a < 6; a++) acc[21 + a] = J[a] * f;
-        } else {
-            f = f / q_rho;
-        }
-        acc[27] = f * f;
+            r_prev = tp.carry[res_in * TVR_T + blockIdx.x];   // stale-fi carry of the evaluation that wrote rin
+        tvr_body<RW, PJ>(o, rin != nullptr, r_prev, sR, sV, sRM, tc, cam, field, fpack, rout, old.m_id_f, i, acc,
+                         matched, need, fi_own, wrote, r_w);
     }
-    // ---- "DResidualNew[ikl]=fi" keeps the fi of the last matched keyline before ikl (fi is a function-level
-    // variable, :341,399-408): in-block scan, cross-block part resolved by the last block --------------
-    const unsigned int bal = __ballot_sync(0xffffffffu, matched);
-    const unsigned int lower = bal & ((1u << lane) - 1u);
-    const int src = lower ? 31 - __clz(lower) : 0;
-    const double prev_fi = __shfl_sync(0xffffffffu, fi_own, src);
-    if (lane == 0) {
-        s_whas[wid] = bal != 0;
-        s_wfirst[wid] = bal ? (wid * 32 + __ffs(bal) - 1) : TVR_T;
-    }
-    {
-        const int hi = bal ? 31 - __clz(bal) : 0;
-        const double wl = __shfl_sync(0xffffffffu, fi_own, hi);
-        if (lane == 0) s_wlast[wid] = wl;
-    }
-    __syncthreads();
-    int wrote_sentinel = 0;
-    if (active) {
-        if (matched) {
-            rout[i] = fi_own;
-        } else if (need) {
-            double v;
-            bool found = lower != 0;
-            v = prev_fi;
-            if (!found) {
-                for (int ww = wid - 1; ww >= 0; ww--)
-                    if (s_whas[ww]) {
-                        v = s_wlast[ww];
-                        found = true;
-                        break;
-                    }
-            }
-            if (found) rout[i] = v;
-            else {
-                reinterpret_cast<unsigned long long *>(rout)[i] = RES_SENTINEL;
-                wrote_sentinel = 1;
-            }
-        }
-    }
-    const int any_sentinel = __syncthreads_or(wrote_sentinel);
-    // ---- block reduction of the 28 sums (fixed order) straight into the per-block partials, layout [28][TVR_T]
-    reduce28<PJ>(acc, s_acc, tid, lane, wid, ts->partials + blockIdx.x, TVR_T);
-    if (tid == 0) {
-        int first = TVR_T, has = 0;
-        double lastv = 0;
-        for (int ww = 0; ww < TVR_T / 32; ww++) {
-            if (s_whas[ww]) {
-                if (!has) first = s_wfirst[ww];
-                has = 1;
-                lastv = s_wlast[ww];
-            }
-        }
-        ts->blk_first[blockIdx.x] = any_sentinel ? first : 0;   // how many leading entries the last block must patch
-        ts->blk_has[blockIdx.x] = has;
-        ts->blk_last_fi[blockIdx.x] = lastv;
-    }
+    tvr_block_tail<PJ>(active, matched, need, fi_own, rout, i, acc, sm, tp.partials + blockIdx.x, TVR_T,
+                       tp.blk_has + blockIdx.x, tp.blk_last_fi + blockIdx.x, tid, lane, wid, wrote, r_w);
     __threadfence();
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
@@ -714,45 +928,18 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
     // ================= last block: grid reduction, stale-fi carries, LM step ==========================
     __threadfence();
     const int nb = gridDim.x;   // <= TVR_T (checked by the host)
-    // grid reduction in a fixed order: thread b owns block b's partials (independent L2 loads, all in flight at
-    // once), then the same warp-shuffle / cross-warp tree as inside a block
+    tvr_grid_reduce<PJ>(tp.partials, nb, s_tot, lane, wid);
+    __shared__ double s_blast[TVR_T];
+    __shared__ unsigned int s_wmask[TVR_T / 32];
     {
-        double pv[28];
-#pragma unroll
-        for (int k = 0; k < 28; k++) pv[k] = 0;
+        int has = 0;
+        double lastv = 0;
         if (tid < nb) {
-            const double *part = ts->partials + tid;   // coalesced: thread b reads block b's entry of every sum
-            if (PJ) {
-#pragma unroll
-                for (int k = 0; k < 28; k++) pv[k] = __ldcg(part + k * TVR_T);
-            } else {
-                pv[27] = __ldcg(part + 27 * TVR_T);
-            }
+            has = __ldcg(tp.blk_has + tid);
+            lastv = __ldcg(tp.blk_last_fi + tid);
         }
-        reduce28<PJ>(pv, s_acc, tid, lane, wid, s_tot, 1);
+        tvr_carries(has, lastv, tp.carry + res_out * TVR_T, nb, s_blast, s_wmask, tid, lane, wid);
     }
-    // carries: block b inherits the last matched fi of the nearest earlier block that has one (0 at start)
-    __shared__ double s_carry[TVR_T], s_blast[TVR_T];
-    __shared__ int s_bhas[TVR_T], s_bfirst[TVR_T];
-    if (tid < nb) {
-        s_bhas[tid] = __ldcg(ts->blk_has + tid);
-        s_blast[tid] = __ldcg(ts->blk_last_fi + tid);
-        s_bfirst[tid] = __ldcg(ts->blk_first + tid);
-    }
-    __syncthreads();
-    if (tid < nb) {   // nearest earlier block with a match (almost always the previous one)
-        double carry = 0;
-        for (int b = tid - 1; b >= 0; b--)
-            if (s_bhas[b]) {
-                carry = s_blast[b];
-                break;
-            }
-        s_carry[tid] = carry;
-    }
-    __syncthreads();
-    // leading misses of block b (those before its first match) hold RES_SENTINEL in the residual buffer; they are
-    // resolved lazily by the reader (next evaluation / k_resolve_res) from this per-buffer carry table
-    if (tid < nb) ts->carry[res_out * TVR_T + tid] = s_carry[tid];
     // the serial LM step works on a shared-memory copy of the state (global round trips would dominate it)
     __shared__ LMState s_lm;
     {
@@ -762,33 +949,317 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
     }
     __syncthreads();
     if (tid == 0) {
-        LMState &L = s_lm;
-        if (PJ) {
-            int k = 0;
-            for (int a = 0; a < 6; a++)
-                for (int b = a; b < 6; b++) L.JtJn[a * 6 + b] = s_tot[k++];
-            for (int a = 0; a < 6; a++) L.JtFn[a] = s_tot[21 + a];
-            for (int a = 0; a < 2; a++) {              // sign fix-ups (:484-490)
-                L.JtFn[a + 2] = -L.JtFn[a + 2];
-                for (int b = 0; b < 2; b++) {
-                    L.JtJn[(a + 0) * 6 + (b + 2)] = -L.JtJn[(a + 0) * 6 + (b + 2)];
-                    L.JtJn[(a + 2) * 6 + (b + 4)] = -L.JtJn[(a + 2) * 6 + (b + 4)];
-                }
-            }
-            for (int a = 0; a < 6; a++)
-                for (int b = a + 1; b < 6; b++) L.JtJn[b * 6 + a] = L.JtJn[a * 6 + b];
-        }
-        L.last_score = s_tot[27];
-        L.n_eval++;
-        lm_step(L, step, f_st);
+        lm_ingest<PJ>(s_lm, s_tot);
+        lm_step(s_lm, step, f_st);
         *ticket = 0;
     }
     __syncthreads();
+    if (step == STEP_MAIN_LAST || (step == STEP_MAIN_FIRST && s_lm.iter_max <= 0)) {
+        lm_finalize_cov(s_lm, tid);
+        __syncthreads();
+    }
     {
         const double *src = reinterpret_cast<const double *>(&s_lm);
         double *dst = reinterpret_cast<double *>(&lm);
         for (int k = tid; k < (int)(sizeof(LMState) / sizeof(double)); k += TVR_T) dst[k] = src[k];
     }
+}
+
+// =====================================================================================================
+// Whole Minimizer_RV in ONE launch.  The ~12 evaluations of a frame are strictly dependent (each request comes out
+// of the LM step on the previous sums), so with one launch per evaluation a frame pays 12x (launch + operand
+// re-load + last-block hand-over through L2).  Here the blocks stay resident: block b keeps the operands of
+// keylines [256b, 256b+256) in registers, block 0 ("master") additionally owns the LM state in shared memory.
+// Per evaluation: the master publishes the request {R, V, RotM, res_in, res_out} through 8-byte {data32, seq32}
+// slots (one L2 trip: a poller that sees the sequence number has the payload, the NCCL-LL idea); every block
+// evaluates its keylines and writes its 28 partial sums; workers bump an arrival counter; the master reduces,
+// computes the stale-fi carries, runs the LM step and publishes the next request.  Only blocks that own keylines
+// (b < ceil(kn/256)) take part, the rest exit at once.  All spins are bounded (MIN_SPIN_LIMIT cycles): a stuck grid
+// aborts with ctl->abort set instead of hanging the device.  Requires all blocks co-resident (checked at alloc).
+// =====================================================================================================
+#define MIN_MAX_EVALS 32
+#define MIN_REQ_WORDS 34           // 32-bit words: R[9] V[3] RotM[4] as doubles, then res_in, res_out
+#define MIN_LL_WORDS 59            // per block: 28 sums as doubles, has-a-match, last matched fi
+#define MIN_SPIN_LIMIT (1ll << 31)
+struct MinPlan {
+    int n;
+    unsigned char step[MIN_MAX_EVALS];
+};
+struct MinSetup {
+    rb_minimizer_args a;
+    double max_r, max_s_rho;
+    const double *VW;
+    unsigned int frame_count;
+    int s_rho_from_state, fc_from_state;
+};
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(TVR_T, 2) k_minimizer_persist(KLSoA old, const MapState *__restrict__ old_st,
+                                                                const unsigned long long *__restrict__ field,
+                                                                const float4 *__restrict__ fpack, MapState *f_st,
+                                                                TrackPtrs tp, ResPtrs res, CamC cam, MinPlan plan,
+                                                                MinSetup su) {
+    __shared__ TvrSmem sm;
+    __shared__ __align__(8) unsigned int s_req[MIN_REQ_WORDS + 2];
+    __shared__ double s_carry[3];       // this block's stale-fi carry per residual buffer (block 0: always 0)
+    __shared__ double s_tot[28];        // this block's sums (every block), then the grid's (master)
+    __shared__ double s_lastfi;
+    __shared__ int s_has;
+    __shared__ double s_blast[TVR_T];
+    __shared__ unsigned int s_wmask[TVR_T / 32];
+    __shared__ LMState s_lm;
+    __shared__ int s_abort;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int K0 = old_st->kn;
+    const int n_act = K0 > 0 ? (K0 + TVR_T - 1) / TVR_T : 1;
+    if ((int)blockIdx.x >= n_act) return;
+    const bool master = blockIdx.x == 0;
+    MinCtl *ctl = tp.ctl;
+    const unsigned int seq0 = __ldcg(&ctl->gen);   // sequence numbers of this minimisation: seq0 + 1 + evaluation
+    const int i = blockIdx.x * TVR_T + tid;
+    const bool active = i < K0;
+    KlOp o;
+    o.m = make_float2(0.f, 0.f);
+    o.x0 = o.y0 = o.z0 = o.s_rho = 1;
+    o.m_num = 0;
+    o.n_m = 0;
+    if (active) {
+        o = load_klop(old, i, cam);
+        res.r[0][i] = 0.0;   // for (auto &r : Residual) r = 0   (:625)
+    }
+    double rr0 = 0.0, rr1 = 0.0, rr2 = 0.0;   // this keyline's entry of Res0 / Res1 / Rest; Residual starts at 0 (:625)
+    TvrConst tc;
+    tc.max_r = su.max_r;
+    tc.match_thresh = su.a.match_thresh;
+    tc.k_huber = su.a.reweight_distance;
+    tc.s_rho_min = su.s_rho_from_state ? old_st->s_rho_q : su.max_s_rho;
+    {
+        const unsigned int fc = su.fc_from_state ? f_st->frame_count : su.frame_count;
+        tc.mnt = su.a.match_num_thresh < fc ? su.a.match_num_thresh : fc;
+    }
+    int prev_out = 0;
+    if (tid == 0) {
+        s_abort = 0;
+        s_carry[0] = s_carry[1] = s_carry[2] = 0;
+        if (master)
+            lm_begin(s_lm, old_st, f_st, su.VW, su.a, su.max_r, su.max_s_rho, su.s_rho_from_state, su.frame_count,
+                     su.fc_from_state);
+    }
+    __syncthreads();
+    const double *rq = reinterpret_cast<const double *>(s_req);
+    const double *sR = rq, *sV = rq + 9, *sRM = rq + 12;
+
+    for (int e = 0; e < plan.n; e++) {
+        const int step = plan.step[e];
+        const bool RW = step >= STEP_MAIN_FIRST;
+        const bool PJ = !(step == STEP_INIT_LAST_ZERO || step == STEP_INIT_LAST_PRIOR);
+        const unsigned int seq = seq0 + 1u + (unsigned int)e;
+        TVR_STAMP(0);
+        // ---- request of this evaluation -------------------------------------------------------------
+        if (master) {
+            double *wq = reinterpret_cast<double *>(s_req);
+            if (tid == 0) {   // the two exponentials run on two warps side by side
+                so3_exp(s_lm.Xeval + 3, wq);                    // SO3<> RotW0(VelRot.slice<3,3>())
+                for (int k = 0; k < 3; k++) wq[9 + k] = s_lm.Xeval[k];
+                s_req[32] = (unsigned int)s_lm.res_in;
+                s_req[33] = (unsigned int)s_lm.res_out;
+            } else if (tid == 32) {
+                double wz[3] = {0, 0, s_lm.Xeval[5]}, RMf[9];
+                so3_exp(wz, RMf);                               // SO3<> RotM(makeVector(0,0,VelRot[5]))
+                wq[12] = RMf[0];
+                wq[13] = RMf[1];
+                wq[14] = RMf[3];
+                wq[15] = RMf[4];
+            }
+            __syncthreads();
+            if (tid < MIN_REQ_WORDS && n_act > 1) {
+                st_volatile_u64(&ctl->slot[tid], ((unsigned long long)seq << 32) | s_req[tid]);
+            }
+        } else if (tid < MIN_REQ_WORDS + 2) {
+            // words 34, 35: this block's stale-fi carry of the previous evaluation, published with the request
+            const unsigned long long *src = tid < MIN_REQ_WORDS
+                                                ? &ctl->slot[tid]
+                                                : tp.ll + (size_t)(MIN_LL_WORDS + tid - MIN_REQ_WORDS) * TVR_T + blockIdx.x;
+            if (tid < MIN_REQ_WORDS || e > 0) {
+                const long long t0 = clock64();
+                unsigned long long v;
+                while ((unsigned int)((v = ld_volatile_u64(src)) >> 32) != seq) {
+                    if (clock64() - t0 > MIN_SPIN_LIMIT) {
+                        s_abort = 1;
+                        break;
+                    }
+                }
+                s_req[tid] = (unsigned int)v;
+            }
+        }
+        __syncthreads();
+        if (s_abort) break;
+        TVR_STAMP(1);
+        if (!master && e > 0 && tid == 0)
+            s_carry[prev_out] = __hiloint2double((int)s_req[MIN_REQ_WORDS + 1], (int)s_req[MIN_REQ_WORDS]);
+        const int res_in = (int)s_req[32], res_out = (int)s_req[33];
+        prev_out = res_out;
+        if (!master && e > 0) __syncthreads();
+        const bool has_rin = RW && res_in >= 0;
+        double *rout = res.r[res_out];
+        // ---- keylines ---------------------------------------------------------------------------------
+        double acc[28];
+#pragma unroll
+        for (int k = 0; k < 28; k++) acc[k] = 0;
+        bool matched = false, need = false, wrote = false;
+        double fi_own = 0, r_w = 0;
+        if (active) {
+            double r_prev = has_rin ? (res_in == 0 ? rr0 : res_in == 1 ? rr1 : rr2) : 0.0;
+            if (has_rin && (unsigned long long)__double_as_longlong(r_prev) == RES_SENTINEL)
+                r_prev = s_carry[res_in];
+            if (RW)
+                tvr_body<true, true>(o, has_rin, r_prev, sR, sV, sRM, tc, cam, field, fpack, rout, old.m_id_f, i, acc,
+                                     matched, need, fi_own, wrote, r_w);
+            else if (PJ)
+                tvr_body<false, true>(o, false, 0.0, sR, sV, sRM, tc, cam, field, fpack, rout, old.m_id_f, i, acc,
+                                      matched, need, fi_own, wrote, r_w);
+            else
+                tvr_body<false, false>(o, false, 0.0, sR, sV, sRM, tc, cam, field, fpack, rout, old.m_id_f, i, acc,
+                                       matched, need, fi_own, wrote, r_w);
+        }
+        TVR_STAMP(2);
+        if (PJ)
+            tvr_block_tail<true>(active, matched, need, fi_own, rout, i, acc, sm, s_tot, 1, &s_has, &s_lastfi, tid,
+                                 lane, wid, wrote, r_w);
+        else
+            tvr_block_tail<false>(active, matched, need, fi_own, rout, i, acc, sm, s_tot, 1, &s_has, &s_lastfi, tid,
+                                  lane, wid, wrote, r_w);
+        if (wrote) {   // the register copy of the residual entry follows the buffer
+            if (res_out == 0) rr0 = r_w;
+            else if (res_out == 1) rr1 = r_w;
+            else rr2 = r_w;
+        }
+        __syncthreads();
+        // ---- this block's sums + stale-fi summary -> self-validating 8-byte slots (no fence, no counter) ---------
+        if (tid < MIN_LL_WORDS) {
+            unsigned int w;
+            if (tid < 56) {
+                const double v = s_tot[tid >> 1];
+                w = (tid & 1) ? (unsigned int)__double2hiint(v) : (unsigned int)__double2loint(v);
+            } else if (tid == 56) {
+                w = (unsigned int)s_has;
+            } else {
+                w = (tid == 57) ? (unsigned int)__double2loint(s_lastfi) : (unsigned int)__double2hiint(s_lastfi);
+            }
+            st_volatile_u64(tp.ll + (size_t)tid * TVR_T + blockIdx.x, ((unsigned long long)seq << 32) | w);
+        }
+        TVR_STAMP(3);
+        if (!master) continue;
+        // ---- master: gather (thread b polls block b's slots), carries, grid sums, LM step ------------------
+        double pv[28];
+#pragma unroll
+        for (int k = 0; k < 28; k++) pv[k] = 0;
+        int has = 0;
+        double lastv = 0;
+        if (tid < n_act) {
+            const unsigned long long *src = tp.ll + tid;
+            const long long t0 = clock64();
+            bool ok;
+            do {
+                ok = true;
+                if (PJ) {
+#pragma unroll
+                    for (int k = 0; k < 27; k++) {
+                        const unsigned long long lo = ld_volatile_u64(src + (size_t)(2 * k) * TVR_T);
+                        const unsigned long long hi = ld_volatile_u64(src + (size_t)(2 * k + 1) * TVR_T);
+                        ok = ok && (unsigned int)(lo >> 32) == seq && (unsigned int)(hi >> 32) == seq;
+                        pv[k] = __hiloint2double((int)(unsigned int)hi, (int)(unsigned int)lo);
+                    }
+                }
+                const unsigned long long lo = ld_volatile_u64(src + (size_t)54 * TVR_T);
+                const unsigned long long hi = ld_volatile_u64(src + (size_t)55 * TVR_T);
+                const unsigned long long wh = ld_volatile_u64(src + (size_t)56 * TVR_T);
+                const unsigned long long l0 = ld_volatile_u64(src + (size_t)57 * TVR_T);
+                const unsigned long long l1 = ld_volatile_u64(src + (size_t)58 * TVR_T);
+                ok = ok && (unsigned int)(lo >> 32) == seq && (unsigned int)(hi >> 32) == seq &&
+                     (unsigned int)(wh >> 32) == seq && (unsigned int)(l0 >> 32) == seq &&
+                     (unsigned int)(l1 >> 32) == seq;
+                pv[27] = __hiloint2double((int)(unsigned int)hi, (int)(unsigned int)lo);
+                has = (int)(unsigned int)wh;
+                lastv = __hiloint2double((int)(unsigned int)l1, (int)(unsigned int)l0);
+                if (!ok && clock64() - t0 > MIN_SPIN_LIMIT) {
+                    s_abort = 1;
+                    break;
+                }
+            } while (!ok);
+        }
+        TVR_STAMP(4);
+        {
+            const double cy = tvr_carries(has, lastv, tp.carry + res_out * TVR_T, n_act, s_blast, s_wmask, tid, lane, wid);
+            if (tid < n_act && tid > 0) {   // travels with the next request (same sequence number), no fence needed
+                const unsigned long long sq = (unsigned long long)(seq + 1u) << 32;
+                st_volatile_u64(tp.ll + (size_t)MIN_LL_WORDS * TVR_T + tid, sq | (unsigned int)__double2loint(cy));
+                st_volatile_u64(tp.ll + (size_t)(MIN_LL_WORDS + 1) * TVR_T + tid, sq | (unsigned int)__double2hiint(cy));
+            }
+        }
+        TVR_STAMP(5);
+        if (PJ) reduce28<true>(pv, sm.red, tid, lane, wid, s_tot, 1);
+        else reduce28<false>(pv, sm.red, tid, lane, wid, s_tot, 1);
+        __syncthreads();
+        if (s_abort) break;
+        TVR_STAMP(6);
+        if (tid == 0) {
+            if (PJ) lm_ingest<true>(s_lm, s_tot);
+            else lm_ingest<false>(s_lm, s_tot);
+            lm_step(s_lm, step, f_st);
+        }
+        __syncthreads();
+        if (step == STEP_MAIN_LAST || (step == STEP_MAIN_FIRST && plan.n == e + 1)) {
+            lm_finalize_cov(s_lm, tid);   // the six columns of Cholesky<6>(JtJ).get_inverse() side by side
+            __syncthreads();
+        }
+        TVR_STAMP(7);
+    }
+    if (!master) return;
+    // ---- master epilogue: results to global, next minimisation gets fresh sequence numbers --------------------
+    __syncthreads();
+    if (s_abort) {
+        if (tid == 0) {
+            ctl->abort = 1;
+            for (int k = 0; k < 3; k++) s_lm.Vel[k] = s_lm.W0[k] = __longlong_as_double(0x7FF8000000000000ll);
+        }
+        __syncthreads();
+    }
+    {
+        const double *src = reinterpret_cast<const double *>(&s_lm);
+        double *dst = reinterpret_cast<double *>(tp.lm);
+        for (int k = tid; k < (int)(sizeof(LMState) / sizeof(double)); k += TVR_T) dst[k] = src[k];
+    }
+    if (tid == 0) ctl->gen = seq0 + MIN_MAX_EVALS + 1u;
+    TVR_STAMP(8);
+#ifdef RB_TVR_PROF
+    if (tid == 0) g_tvr_prof[255 * 16 + 15] = n_act;
+#endif
+}
+
+static TrackPtrs track_ptrs(const rb_map *fmap) {
+    TrackPtrs tp;
+    tp.lm = &fmap->ts->lm;
+    tp.blk_has = fmap->ts_host.blk_has;
+    tp.blk_last_fi = fmap->ts_host.blk_last_fi;
+    tp.partials = fmap->ts_host.partials;
+    tp.carry = fmap->ts_host.carry;
+    tp.ctl = fmap->ts_host.ctl;
+    tp.ll = fmap->ts_host.ll;
+    return tp;
 }
 
 template <bool RW, bool PJ>
@@ -797,9 +1268,21 @@ static int launch_eval(rb_ctx *c, rb_map *fmap, rb_map *old, int step) {
     for (int i = 0; i < 3; i++) rp.r[i] = fmap->res[i];
     const int nblk = fmap->ts_host.nblk;
     k_tvr_eval<RW, PJ><<<nblk, TVR_T, 0, c->stream>>>(old->kl, old->st, fmap->field, fmap->kl.pack, fmap->st,
-                                                     fmap->ts, rp, c->ticket + 1, make_cam(c), step);
+                                                     track_ptrs(fmap), rp, c->ticket + 1, make_cam(c), step);
     RB_LAUNCH_CHECK();
     return RB_OK;
+}
+static int launch_eval_step(rb_ctx *c, rb_map *fmap, rb_map *old, int step) {
+    if (step >= STEP_MAIN_FIRST) return launch_eval<true, true>(c, fmap, old, step);
+    if (step == STEP_INIT_LAST_ZERO || step == STEP_INIT_LAST_PRIOR) return launch_eval<false, false>(c, fmap, old, step);
+    return launch_eval<false, true>(c, fmap, old, step);
+}
+
+// how many 256-thread blocks of the persistent kernel the device keeps resident at once
+int rb_minimizer_resident_blocks(int sm_count) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minimizer_persist, TVR_T, 0) != cudaSuccess) return 0;
+    return per_sm * sm_count;
 }
 
 int rb_minimizer_enqueue(rb_ctx *c, rb_map *fmap, rb_map *old, const double *VW_dev, const rb_minimizer_args *a,
@@ -808,30 +1291,47 @@ int rb_minimizer_enqueue(rb_ctx *c, rb_map *fmap, rb_map *old, const double *VW_
         snprintf(c->err, sizeof(c->err), "Minimizer_RV before build_field");
         return RB_ERR_STATE;
     }
-    if (fmap->ts_host.nblk > 256) return RB_ERR_ARG;
+    const int nblk = fmap->ts_host.nblk;
+    if (nblk > TVR_T) return RB_ERR_ARG;
+    // the evaluation sequence of Minimizer_RV (global_tracker.cpp:640-791) is fixed by the configuration
+    const int n = a->init_iter, m = a->iter_max;
+    int steps[2 * MIN_MAX_EVALS], ns = 0;
+    if (n < 0 || m < 0 || 2 * (n + 1) + m + 1 > 2 * MIN_MAX_EVALS) return RB_ERR_ARG;
+    if (a->init_type != 0 && a->init_type != 1) {
+        steps[ns++] = STEP_INIT_FIRST_ZERO;
+        for (int i = 0; i < n; i++) steps[ns++] = i == n - 1 ? STEP_INIT_LAST_ZERO : STEP_INIT_ITER_ZERO;
+        steps[ns++] = STEP_INIT_FIRST_PRIOR;
+        for (int i = 0; i < n; i++) steps[ns++] = i == n - 1 ? STEP_INIT_LAST_PRIOR : STEP_INIT_ITER_PRIOR;
+    }
+    steps[ns++] = STEP_MAIN_FIRST;
+    for (int j = 0; j < m; j++) steps[ns++] = j == m - 1 ? STEP_MAIN_LAST : STEP_MAIN_ITER;
     int r;
+    if (c->min_persist && ns <= MIN_MAX_EVALS && nblk <= c->min_resident) {
+        MinPlan plan;
+        memset(&plan, 0, sizeof(plan));
+        plan.n = ns;
+        for (int i = 0; i < ns; i++) plan.step[i] = (unsigned char)steps[i];
+        MinSetup su;
+        su.a = *a;
+        su.max_r = (double)fmap->field_radius;
+        su.max_s_rho = max_s_rho;
+        su.VW = VW_dev;
+        su.frame_count = frame_count;
+        su.s_rho_from_state = s_rho_from_state ? 1 : 0;
+        su.fc_from_state = fc_from_state ? 1 : 0;
+        ResPtrs rp;
+        for (int i = 0; i < 3; i++) rp.r[i] = fmap->res[i];
+        k_minimizer_persist<<<nblk, TVR_T, 0, c->stream>>>(old->kl, old->st, fmap->field, fmap->kl.pack, fmap->st,
+                                                          track_ptrs(fmap), rp, make_cam(c), plan, su);
+        RB_LAUNCH_CHECK();
+        return RB_OK;
+    }
     RB_CUDA(cudaMemsetAsync(fmap->res[0], 0, sizeof(double) * (size_t)c->kcap, c->stream));   // Residual[i]=0 (:625)
     k_lm_begin<<<1, 1, 0, c->stream>>>(fmap->ts, old->st, fmap->st, VW_dev, *a, (double)fmap->field_radius,
                                        max_s_rho, s_rho_from_state ? 1 : 0, frame_count, fc_from_state ? 1 : 0);
     RB_LAUNCH_CHECK();
-    const int n = a->init_iter, m = a->iter_max;
-    if (a->init_type != 0 && a->init_type != 1) {
-        if ((r = launch_eval<false, true>(c, fmap, old, STEP_INIT_FIRST_ZERO))) return r;
-        for (int i = 0; i < n; i++) {
-            if (i == n - 1) r = launch_eval<false, false>(c, fmap, old, STEP_INIT_LAST_ZERO);
-            else r = launch_eval<false, true>(c, fmap, old, STEP_INIT_ITER_ZERO);
-            if (r) return r;
-        }
-        if ((r = launch_eval<false, true>(c, fmap, old, STEP_INIT_FIRST_PRIOR))) return r;
-        for (int i = 0; i < n; i++) {
-            if (i == n - 1) r = launch_eval<false, false>(c, fmap, old, STEP_INIT_LAST_PRIOR);
-            else r = launch_eval<false, true>(c, fmap, old, STEP_INIT_ITER_PRIOR);
-            if (r) return r;
-        }
-    }
-    if ((r = launch_eval<true, true>(c, fmap, old, STEP_MAIN_FIRST))) return r;
-    for (int j = 0; j < m; j++)
-        if ((r = launch_eval<true, true>(c, fmap, old, j == m - 1 ? STEP_MAIN_LAST : STEP_MAIN_ITER))) return r;
+    for (int i = 0; i < ns; i++)
+        if ((r = launch_eval_step(c, fmap, old, steps[i]))) return r;
     return RB_OK;
 }
 

@@ -15,6 +15,14 @@ enum LMStep {
     STEP_MAIN_LAST          // last iteration + uncertainties / outputs (:793-816)
 };
 
+// control block of the persistent Minimizer_RV kernel (tracker.cu), one per TrackState, in device memory
+struct MinCtl {
+    unsigned long long slot[40];   // {hi: sequence number, lo: payload word}; all zero between minimisations
+    unsigned int gen;              // base of the sequence numbers of the next minimisation
+    int abort;                     // sticky: a spin timed out
+};
+
+int rb_minimizer_resident_blocks(int sm_count);
 int rb_track_state_alloc(rb_ctx *c, rb_map *m);
 void rb_track_state_free(rb_map *m);
 
