@@ -136,6 +136,7 @@ struct TrackState {
     int nblk;
     struct MinCtl *ctl;   // request slots / sequence base of the persistent minimiser kernel
     unsigned long long *ll;   // its per-block partial-sum slots
+    unsigned long long *ll2;  // same for the persistent rescaling kernel
     // scratch for FordwardMatch / Regularize_1_iter
     unsigned long long *fm_best;
     int *fm_idx;

@@ -11,30 +11,46 @@
 #include "common.cuh"
 #include "lm.cuh"
 #include "tracker.cuh"
+#include "frame.cuh"
 
 int rb_map_alloc(rb_ctx *c, rb_map **out, bool with_ws);
 
 // SecondThread locals (rebvo_second_t.cpp:57-66, 167-169)
-struct FrameState {
-    double V[3], W[3], Pos[3];
-    double R[9], Pose[9];
-    double P_V[9], P_W[9];
-    double Kp, K, P_Kp;
-    double VW[6];       // minimiser priors (V, W of the previous frame)
-    double R0[9];       // forward rotation exp(W)
-    DMatchArgs dm;
-    int do_match, do_map, est_ok;
-    int klm_num;
-    int n_frame;
-    int pad;
-};
+#define RB_NMAPS 3
+
+// Device-side timeline for profiling builds (-DRB_TVR_PROF): marker kernels stamp %globaltimer, so that the overlap of
+// the two streams can be read back from a graph replay (no nsys in this image).  Compiled out of the product.
+#ifdef RB_TVR_PROF
+__device__ unsigned long long g_trace[8192];
+__device__ unsigned int g_trace_n;
+__global__ void k_trace_mark(int tag) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    const unsigned int k = atomicAdd(&g_trace_n, 1u);
+    if (k < 8192) g_trace[k] = ((unsigned long long)tag << 56) | (t & 0x00FFFFFFFFFFFFFFull);
+}
+extern "C" int rb_debug_fetch_trace(unsigned long long *out, unsigned int *n) {
+    cudaMemcpyFromSymbol(n, g_trace_n, sizeof(unsigned int));
+    cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * 8192);
+    unsigned int z = 0;
+    return (int)cudaMemcpyToSymbol(g_trace_n, &z, sizeof(z));
+}
+#define RB_TRACE(stream, tag) k_trace_mark<<<1, 1, 0, stream>>>(tag)
+#else
+#define RB_TRACE(stream, tag) do { } while (0)
+#endif
 
 struct rb_pipeline {
     rb_ctx *c;
     rb_params p;
     int max_batch;
     DogWS ws;
-    rb_map *maps[2];
+    rb_map *maps[RB_NMAPS];   // ring: frame f lives in maps[f % RB_NMAPS]
+    // detector stream: detect(f+1) (+ reEstimateThresh) runs beside the tracker/mapper of frame f; the third map is
+    // what lets it write while frame f still reads map f-1
+    cudaStream_t det_stream;
+    cudaEvent_t ev_dog, *ev_det, *ev_trk;
+    bool overlap;
     DetChain *chain;      // device
     FrameState *fs;       // device
     rb_nav *nav_dev;
@@ -48,7 +64,7 @@ struct rb_pipeline {
     struct FrameArgs *fa_dev, *fa_pin;
     // one instantiated CUDA graph per (batch size, parity of the first frame): the kernel sequence of a batch is
     // static once the per-frame scalars live in fa_dev
-    cudaGraphExec_t *gexec;       // [2 * (max_batch + 1)]
+    cudaGraphExec_t *gexec;       // [RB_NMAPS * (max_batch + 1)]
     int *glaunches;               // kernel launches inside each graph
     bool use_graph;
     // optional in-situ stage profile (REBVO_B200_STAGE_PROF=1, forces eager launches): CUDA events between stages
@@ -75,140 +91,14 @@ static void set_eye(double *M, double v) {
     M[0] = M[4] = M[8] = v;
 }
 
-__device__ void d_eye(double *M, double v) {
-    for (int i = 0; i < 9; i++) M[i] = 0;
-    M[0] = M[4] = M[8] = v;
-}
-
-// per-frame scalars that change from push to push; kept in device memory so that the kernel arguments of a batch
-// are constant and the whole batch can be replayed as one CUDA graph
-struct FrameArgs {
-    double t, dt;
-    unsigned int frame_count;   // global_tracker::FrameCount of the reference ring slot serving this frame
-    int pad;
-};
-
-// start of the SecondThread loop body (:167-169) + minimiser priors
-__global__ void k_frame_pre(FrameState *fs, const FrameArgs *fa, MapState *nst) {
-    nst->frame_count = fa->frame_count;
-    nst->fwd_match = 0;   // counters of FordwardMatch / directed_matching / Regularize_1_iter
-    nst->nmatch = 0;
-    nst->reg_num = 0;
-    d_eye(fs->P_V, 1e50);
-    d_eye(fs->P_W, 1e50);
-    d_eye(fs->R, 1);
-    for (int i = 0; i < 3; i++) {
-        fs->VW[i] = fs->V[i];
-        fs->VW[3 + i] = fs->W[i];
-    }
-    fs->est_ok = 1;
-    fs->do_match = 0;
-    fs->do_map = 0;
-    fs->klm_num = 0;
-}
-
-// after Minimizer_RV (:346-398): outputs, R0 = exp(W), R.T() = R0*R.T(), NaN guard, directed-matching args
-__global__ void k_frame_post_min(FrameState *fs, const TrackState *ts) {
-    const LMState &lm = ts->lm;
-    for (int i = 0; i < 3; i++) {
-        fs->V[i] = lm.Vel[i];
-        fs->W[i] = lm.W0[i];
-    }
-    for (int i = 0; i < 9; i++) {
-        fs->P_V[i] = lm.RVel[i];
-        fs->P_W[i] = lm.RW0[i];
-    }
-    so3_exp(fs->W, fs->R0);                 // SO3<> R0(W)
-    double Rt[9], RtT[9];
-    for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 3; c++) RtT[r * 3 + c] = fs->R[c * 3 + r];
-    mat3_mul(fs->R0, RtT, Rt);              // R.T() = R0*R.T()
-    for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 3; c++) fs->R[r * 3 + c] = Rt[c * 3 + r];
-    bool nan = false;
-    for (int i = 0; i < 3; i++) nan = nan || isnan(fs->V[i]) || isnan(fs->W[i]);
-    if (nan) {                              // :387-398
-        d_eye(fs->P_V, 1e50);
-        for (int i = 0; i < 3; i++) fs->V[i] = 0;
-        fs->Kp = 1;
-        fs->P_Kp = 1e50;
-        fs->est_ok = 0;
-        fs->do_match = 0;
-    } else {
-        fs->do_match = 1;
-        // directed_matching prologue (edge_tracker.cpp:324-325): Vel=BackRot*Vel; RVel=BackRot*RVel*BackRot.T()
-        mat3_vec(fs->R, fs->V, fs->dm.Vel);
-        double t[9];
-        mat3_mul(fs->R, fs->P_V, t);
-        mat3_mul_bt(t, fs->R, fs->dm.RVel);
-        for (int i = 0; i < 9; i++) fs->dm.BackRot[i] = fs->R[i];
-    }
-}
-
-// after directed_matching (:410-423)
+__global__ void k_frame_pre(FrameState *fs, const FrameArgs *fa, MapState *nst) { d_frame_pre(fs, fa, nst); }
+__global__ void k_frame_post_min(FrameState *fs, const TrackState *ts) { d_frame_post_min(fs, ts->lm); }
 __global__ void k_frame_post_match(FrameState *fs, const MapState *nst, int match_threshold) {
-    if (!fs->do_match) {
-        fs->do_map = 0;
-        return;
-    }
-    fs->klm_num = nst->nmatch;
-    if (fs->klm_num < match_threshold) {
-        d_eye(fs->P_V, 1e50);
-        for (int i = 0; i < 3; i++) fs->V[i] = 0;
-        fs->Kp = 1;
-        fs->P_Kp = 10;
-        fs->est_ok = 0;
-        fs->do_map = 0;
-    } else {
-        fs->do_map = 1;
-    }
+    d_frame_post_match(fs, nst, match_threshold);
 }
-
-// pose integration + NavData (:545-585)
 __global__ void k_frame_finish(FrameState *fs, const MapState *nst, const MapState *ost, const TrackState *ts,
                                rb_nav *nav, const FrameArgs *fa) {
-    const double t = fa->t, dt_frame = fa->dt;
-    if (fs->do_map) {
-        fs->Kp = nst->Kp;      // Kp=EstimateReScalingOpt(P_Kp,...)
-        fs->P_Kp = nst->RKp;
-    }
-    const double K = fs->K;
-    double Pose[9];
-    mat3_mul(fs->Pose, fs->R, Pose);          // Pose=Pose*R
-    for (int i = 0; i < 9; i++) fs->Pose[i] = Pose[i];
-    double nP[9], pv[3];
-    for (int i = 0; i < 9; i++) nP[i] = -Pose[i];
-    mat3_vec(nP, fs->V, pv);                  // Pos+=-Pose*V*K
-    for (int i = 0; i < 3; i++) fs->Pos[i] = fs->Pos[i] + pv[i] * K;
-    rb_nav o;
-    o.t = t;
-    o.dt = dt_frame;
-    for (int i = 0; i < 9; i++) {
-        o.Rot[i] = fs->R[i];
-        o.Pose[i] = fs->Pose[i];
-    }
-    so3_ln_of_matrix(fs->R, o.RotLie);
-    so3_ln_of_matrix(fs->Pose, o.PoseLie);
-    for (int i = 0; i < 3; i++) {
-        o.Vel[i] = (-fs->V[i]) * K / dt_frame;
-        o.Pos[i] = fs->Pos[i];
-        o.V[i] = fs->V[i];
-        o.W[i] = fs->W[i];
-    }
-    o.K = K;
-    o.Kp = fs->Kp;
-    o.RKp = fs->P_Kp;
-    o.s_rho_p = ost->s_rho_q;
-    o.score = ts->lm.score;
-    o.kn = nst->kn;
-    o.matches = fs->klm_num;
-    o.fwd_matches = nst->fwd_match;
-    o.estimation_ok = fs->est_ok;
-    o.thresh = nst->thresh_used;
-    o.retuned_thresh = nst->retuned;
-    *nav = o;
-    for (int i = 0; i < 9; i++) fs->P_V[i] = fs->P_V[i] / (dt_frame * dt_frame);   // P_V/=dt_frame*dt_frame
-    fs->n_frame++;
+    d_frame_finish(fs, nst, ost, ts->lm.score, nav, fa);
 }
 
 // record for the very first frame (it only initialises the ring, :109-121)
@@ -274,7 +164,7 @@ extern "C" int rb_pipeline_create(rb_pipeline **out, int device, const rb_params
     pl->max_batch = max_batch;
     *out = pl;
     if ((r = rb_dogws_alloc(c, &pl->ws, max_batch))) return r;
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < RB_NMAPS; i++)
         if ((r = rb_map_alloc(c, &pl->maps[i], false))) return r;
     RB_CUDA(cudaMalloc(&pl->chain, sizeof(DetChain)));
     RB_CUDA(cudaMalloc(&pl->fs, sizeof(FrameState)));
@@ -282,10 +172,10 @@ extern "C" int rb_pipeline_create(rb_pipeline **out, int device, const rb_params
     RB_CUDA(cudaMallocHost(&pl->nav_pin, sizeof(rb_nav) * max_batch));
     RB_CUDA(cudaMalloc(&pl->fa_dev, sizeof(FrameArgs) * max_batch));
     RB_CUDA(cudaMallocHost(&pl->fa_pin, sizeof(FrameArgs) * max_batch));
-    pl->gexec = new (std::nothrow) cudaGraphExec_t[2 * (max_batch + 1)];
-    pl->glaunches = new (std::nothrow) int[2 * (max_batch + 1)];
+    pl->gexec = new (std::nothrow) cudaGraphExec_t[RB_NMAPS * (max_batch + 1)];
+    pl->glaunches = new (std::nothrow) int[RB_NMAPS * (max_batch + 1)];
     if (!pl->gexec || !pl->glaunches) return RB_ERR_ARG;
-    for (int i = 0; i < 2 * (max_batch + 1); i++) {
+    for (int i = 0; i < RB_NMAPS * (max_batch + 1); i++) {
         pl->gexec[i] = nullptr;
         pl->glaunches[i] = 0;
     }
@@ -301,6 +191,21 @@ extern "C" int rb_pipeline_create(rb_pipeline **out, int device, const rb_params
         if (!pl->pev || !pl->ptag) return RB_ERR_ARG;
         for (int i = 0; i < pl->pcap; i++) RB_CUDA(cudaEventCreate(&pl->pev[i]));
     }
+    {
+        const char *ov = getenv("REBVO_B200_OVERLAP");
+        pl->overlap = !(ov && ov[0] == '0') && !pl->prof_on;
+        pl->ev_det = new (std::nothrow) cudaEvent_t[max_batch];
+        pl->ev_trk = new (std::nothrow) cudaEvent_t[max_batch];
+        if (!pl->ev_det || !pl->ev_trk) return RB_ERR_ARG;
+        memset(pl->ev_det, 0, sizeof(cudaEvent_t) * max_batch);
+        memset(pl->ev_trk, 0, sizeof(cudaEvent_t) * max_batch);
+        RB_CUDA(cudaStreamCreateWithFlags(&pl->det_stream, cudaStreamNonBlocking));
+        RB_CUDA(cudaEventCreateWithFlags(&pl->ev_dog, cudaEventDisableTiming));
+        for (int i = 0; i < max_batch; i++) {
+            RB_CUDA(cudaEventCreateWithFlags(&pl->ev_det[i], cudaEventDisableTiming));
+            RB_CUDA(cudaEventCreateWithFlags(&pl->ev_trk[i], cudaEventDisableTiming));
+        }
+    }
     for (int i = 0; i < 4; i++) RB_CUDA(cudaEventCreate(&pl->ev[i]));
     for (int i = 0; i < 8; i++) RB_CUDA(cudaEventCreate(&pl->user_ev[i]));
     if ((r = pl_reset_state(pl))) return r;
@@ -313,8 +218,17 @@ extern "C" void rb_pipeline_destroy(rb_pipeline *pl) {
     rb_ctx *c = pl->c;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (int i = 0; i < 2; i++)
+    if (pl->det_stream) cudaStreamSynchronize(pl->det_stream);
+    for (int i = 0; i < RB_NMAPS; i++)
         if (pl->maps[i]) rb_map_destroy(pl->maps[i]);
+    if (pl->ev_dog) cudaEventDestroy(pl->ev_dog);
+    for (int i = 0; i < pl->max_batch; i++) {
+        if (pl->ev_det && pl->ev_det[i]) cudaEventDestroy(pl->ev_det[i]);
+        if (pl->ev_trk && pl->ev_trk[i]) cudaEventDestroy(pl->ev_trk[i]);
+    }
+    delete[] pl->ev_det;
+    delete[] pl->ev_trk;
+    if (pl->det_stream) cudaStreamDestroy(pl->det_stream);
     rb_dogws_free(&pl->ws);
     cudaFree(pl->chain);
     cudaFree(pl->fs);
@@ -323,7 +237,7 @@ extern "C" void rb_pipeline_destroy(rb_pipeline *pl) {
     cudaFree(pl->fa_dev);
     if (pl->fa_pin) cudaFreeHost(pl->fa_pin);
     if (pl->gexec) {
-        for (int i = 0; i < 2 * (pl->max_batch + 1); i++)
+        for (int i = 0; i < RB_NMAPS * (pl->max_batch + 1); i++)
             if (pl->gexec[i]) cudaGraphExecDestroy(pl->gexec[i]);
         delete[] pl->gexec;
     }
@@ -341,7 +255,7 @@ extern "C" int64_t rb_pipeline_launch_count(const rb_pipeline *pl) { return pl->
 extern "C" void *rb_pipeline_stream(rb_pipeline *pl) { return (void *)pl->c->stream; }
 extern "C" rb_map *rb_pipeline_map(rb_pipeline *pl, int age) {
     if (age < 0 || age > 1 || pl->n_pushed <= age) return nullptr;
-    return pl->maps[(pl->n_pushed - 1 - age) & 1];
+    return pl->maps[(pl->n_pushed - 1 - age) % RB_NMAPS];
 }
 extern "C" int rb_pipeline_stage_ms(const rb_pipeline *pl, float out[6]) {
     memcpy(out, pl->stage_ms, sizeof(float) * 6);
@@ -354,19 +268,21 @@ extern "C" int rb_pipeline_reset(rb_pipeline *pl) {
     return pl_reset_state(pl);
 }
 
-// one frame of the tracker/mapper stage: new = maps[idx&1] (already detected), old = the other map
+// one frame of the tracker/mapper stage: new = maps[f % RB_NMAPS] (already detected), old = the map of frame f-1
 static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, const FrameArgs *fa, rb_nav *nav_slot) {
     rb_ctx *c = pl->c;
     const rb_params &p = pl->p;
     int r;
-    k_frame_pre<<<1, 1, 0, c->stream>>>(pl->fs, fa, neu->st);
-    RB_LAUNCH_CHECK();
-    // :172  s_rho_q = old_buf.ef->EstimateQuantile(RHO_MIN,RHO_MAX,QCutOffQuantile,QCutOffNumBins)
-    if ((r = rb_quantile_enqueue(c, old, RB_RHO_MIN, RB_RHO_MAX, p.QCutOffQuantile, p.QCutOffNumBins))) return r;
-    // :177  new_buf.gt->build_field(*new_buf.ef,SearchRange,new_buf.ef->getThresh())
-    if ((r = rb_build_field_enqueue(c, neu, p.SearchRange, 0.f, true))) return r;
+    RB_TRACE(c->stream, 1);
+    // :167-169 loop-body start (folded into the quantile kernel) ; :172  s_rho_q = old_buf.ef->EstimateQuantile(...)
+    if ((r = rb_quantile_enqueue(c, old, RB_RHO_MIN, RB_RHO_MAX, p.QCutOffQuantile, p.QCutOffNumBins, pl->fs, fa,
+                                 neu->st)))
+        return r;
+    // :177  new_buf.gt->build_field(...) only needs the new edge map: enqueue_batch runs it on the detector stream
+    if (!pl->overlap)
+        if ((r = rb_build_field_enqueue(c, neu, p.SearchRange, 0.f, true))) return r;
     prof_mark(pl, ST_FIELD);
-    // :346  Minimizer_RV<double>(V,W,P_V,P_W,*old_buf.ef,...)
+    // :346  Minimizer_RV<double>(V,W,P_V,P_W,*old_buf.ef,...) ; :346-398 outputs / NaN guard folded into its last block
     rb_minimizer_args a;
     a.match_thresh = p.TrackerMatchThresh;
     a.iter_max = p.TrackerIterNum;
@@ -374,30 +290,43 @@ static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, const FrameArg
     a.init_iter = p.TrackerInitIterNum;
     a.reweight_distance = p.ReweigthDistance;
     a.match_num_thresh = p.MatchNumThresh;
-    // FrameCount comes from fa (written into neu->st by k_frame_pre)
-    if ((r = rb_minimizer_enqueue(c, neu, old, pl->fs->VW, &a, 0.0, true, 0, true))) return r;
+    // FrameCount comes from fa (written into neu->st by the folded loop-body start)
+    RB_TRACE(c->stream, 2);
+    bool folded = false;
+    if ((r = rb_minimizer_enqueue(c, neu, old, pl->fs->VW, &a, 0.0, true, 0, true, pl->fs, &folded))) return r;
+    RB_TRACE(c->stream, 3);
     prof_mark(pl, ST_MINIM);
-    k_frame_post_min<<<1, 1, 0, c->stream>>>(pl->fs, neu->ts);
-    RB_LAUNCH_CHECK();
+    if (!folded) {
+        k_frame_post_min<<<1, 1, 0, c->stream>>>(pl->fs, neu->ts);
+        RB_LAUNCH_CHECK();
+    }
     // :354  FordwardMatch ; :369 rotate_keylines(R0)
-    if ((r = rb_forward_match_enqueue(c, old, neu))) return r;
+    if ((r = rb_forward_match_enqueue(c, old, neu, pl->overlap))) return r;
     if ((r = rb_rotate_enqueue(c, old, pl->fs->R0))) return r;
     prof_mark(pl, ST_FWD_ROT);
     // :410  directed_matching(V,P_V,R,old_buf.ef,...)
     if ((r = rb_directed_matching_enqueue(c, neu, old, &pl->fs->dm, p.MatchThreshModule, p.MatchThreshAngle,
                                           (double)p.SearchRange, p.LocationUncertaintyMatch, &pl->fs->do_match)))
         return r;
-    k_frame_post_match<<<1, 1, 0, c->stream>>>(pl->fs, neu->st, p.MatchThreshold);
-    RB_LAUNCH_CHECK();
+    RB_TRACE(c->stream, 4);
     prof_mark(pl, ST_DMATCH);
-    // :452-487  Regularize_1_iter, UpdateInverseDepthKalman, EstimateReScalingOpt
-    if ((r = rb_regularize_enqueue(c, neu, p.RegularizeThresh, &pl->fs->do_map))) return r;
-    if ((r = rb_ekf_enqueue(c, neu, pl->fs->V, p.ReshapeQAbsolute, p.LocationUncertainty, &pl->fs->do_map))) return r;
+    // :410-423 match-count gate (folded into the first regularisation kernel) ; :452-487 Regularize_1_iter,
+    // UpdateInverseDepthKalman (write-back half of the former fused with the latter), EstimateReScalingOpt
+    if ((r = rb_regularize_a_enqueue(c, neu, p.RegularizeThresh, pl->fs, p.MatchThreshold))) return r;
+    if ((r = rb_regb_ekf_enqueue(c, neu, pl->fs->V, p.ReshapeQAbsolute, p.LocationUncertainty, &pl->fs->do_map)))
+        return r;
     prof_mark(pl, ST_REG_EKF);
-    if ((r = rb_rescale_enqueue(c, neu, RB_RHO_MAX, 1, p.DoReScaling > 0 ? 1 : 0, &pl->fs->do_map))) return r;
+    // :545-585 pose integration + NavData folded into the rescaling kernel's block 0
+    folded = false;
+    if ((r = rb_rescale_enqueue(c, neu, RB_RHO_MAX, 1, p.DoReScaling > 0 ? 1 : 0, &pl->fs->do_map, pl->fs, old->st,
+                                nav_slot, fa, &folded)))
+        return r;
     prof_mark(pl, ST_RESCALE);
-    k_frame_finish<<<1, 1, 0, c->stream>>>(pl->fs, neu->st, old->st, neu->ts, nav_slot, fa);
-    RB_LAUNCH_CHECK();
+    if (!folded) {
+        k_frame_finish<<<1, 1, 0, c->stream>>>(pl->fs, neu->st, old->st, neu->ts, nav_slot, fa);
+        RB_LAUNCH_CHECK();
+    }
+    RB_TRACE(c->stream, 5);
     prof_mark(pl, ST_FINISH);
     return RB_OK;
 }
@@ -414,21 +343,47 @@ static int enqueue_batch(rb_pipeline *pl, int n, long long first_frame, bool wit
     if ((r = rb_dog_build_batch(c, &pl->ws, n))) return r;
     prof_mark(pl, ST_DOG);
     if (with_events) RB_CUDA(cudaEventRecord(pl->ev[2], c->stream));
+    // Two streams, like the reference's first and second thread: the detector of frame f+1 only needs the scale space
+    // and the previous detector state (threshold chain), so it runs on det_stream while the main stream tracks
+    // frame f.  detect(f) overwrites the map of frame f-3, which track(f-2) was the last to read.
+    cudaStream_t main_stream = c->stream;
+    const bool ov = pl->overlap;
+    if (ov) {
+        RB_CUDA(cudaEventRecord(pl->ev_dog, main_stream));
+        RB_CUDA(cudaStreamWaitEvent(pl->det_stream, pl->ev_dog, 0));
+    }
     for (int i = 0; i < n; i++) {
         const long long fr = first_frame + i;
-        rb_map *neu = pl->maps[fr & 1], *old = pl->maps[(fr + 1) & 1];
+        rb_map *neu = pl->maps[fr % RB_NMAPS], *old = pl->maps[(fr + RB_NMAPS - 1) % RB_NMAPS];
         const float *img0 = pl->ws.img0 + (size_t)i * c->N, *dog = pl->ws.dog + (size_t)i * c->N;
         // FirstThr: detect + reEstimateThresh (rebvo_first_t.cpp:266-272)
-        if ((r = rb_detect_enqueue(c, neu, img0, dog, &p.det, pl->chain))) return r;
+        if (ov) {
+            if (i >= 2) RB_CUDA(cudaStreamWaitEvent(pl->det_stream, pl->ev_trk[i - 2], 0));
+            c->stream = pl->det_stream;
+        }
+        RB_TRACE(c->stream, 6);
+        r = rb_detect_enqueue(c, neu, img0, dog, &p.det, pl->chain);
         prof_mark(pl, ST_DETECT);
-        if ((r = rb_reestimate_enqueue(c, neu, p.TrackPoints, p.QCutOffNumBins))) return r;
+        if (!r) r = rb_reestimate_enqueue(c, neu, p.TrackPoints, p.QCutOffNumBins);
         prof_mark(pl, ST_REEST);
+        if (ov && fr > 0) {   // tracker inputs that only depend on the new edge map: distance field, arg-max scratch
+            if (!r) r = rb_build_field_enqueue(c, neu, p.SearchRange, 0.f, true);
+            if (!r) r = rb_forward_match_init_enqueue(c, neu);
+        }
+        RB_TRACE(c->stream, 7);
+        c->stream = main_stream;
+        if (r) return r;
+        if (ov) {
+            RB_CUDA(cudaEventRecord(pl->ev_det[i], pl->det_stream));
+            RB_CUDA(cudaStreamWaitEvent(main_stream, pl->ev_det[i], 0));
+        }
         if (fr == 0) {
             k_frame_first<<<1, 1, 0, c->stream>>>(pl->fs, neu->st, pl->nav_dev + i, pl->fa_dev + i);
             RB_LAUNCH_CHECK();
         } else {
             if ((r = track_frame(pl, neu, old, pl->fa_dev + i, pl->nav_dev + i))) return r;
         }
+        if (ov && i + 2 < n) RB_CUDA(cudaEventRecord(pl->ev_trk[i], main_stream));
     }
     return RB_OK;
 }
@@ -461,7 +416,7 @@ static int push_impl(rb_pipeline *pl, const uint8_t *rgb, bool on_device, const 
     if (!graph_ok) {
         if ((r = enqueue_batch(pl, n, first, true))) return r;
     } else {
-        const int key = (int)(first & 1) * (pl->max_batch + 1) + n;
+        const int key = (int)(first % RB_NMAPS) * (pl->max_batch + 1) + n;
         if (!pl->gexec[key]) {
             // capture the batch once; replays only differ through fa_dev / ws.rgb contents
             cudaGraph_t g = nullptr;
@@ -508,7 +463,7 @@ static int push_impl(rb_pipeline *pl, const uint8_t *rgb, bool on_device, const 
     }
     if (nav_out) memcpy(nav_out, pl->nav_pin, sizeof(rb_nav) * n);
     if (pl->nav_pin[n - 1].Pos[0] != pl->nav_pin[n - 1].Pos[0]) {   // NaN pose: did the persistent minimiser abort?
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < RB_NMAPS; k++) {
             int ab = 0;
             cudaMemcpy(&ab, &pl->maps[k]->ts_host.ctl->abort, sizeof(int), cudaMemcpyDeviceToHost);
             if (ab) {

@@ -9,6 +9,7 @@
 // reference's pairwise tree, so they agree to rounding (tests use rel 1e-11), not bitwise.
 #include "tracker.cuh"
 #include "lm.cuh"
+#include "frame.cuh"
 
 #define TVR_T 256
 #define RES_SENTINEL 0x7FF8DEADBEEF0001ull
@@ -55,6 +56,8 @@ int rb_track_state_alloc(rb_ctx *c, rb_map *m) {
     RB_CUDA(cudaMemsetAsync(host.carry, 0, sizeof(double) * 3 * TVR_T, c->stream));
     RB_CUDA(cudaMalloc(&host.ctl, sizeof(MinCtl)));
     RB_CUDA(cudaMemsetAsync(host.ctl, 0, sizeof(MinCtl), c->stream));
+    RB_CUDA(cudaMalloc(&host.ll2, sizeof(unsigned long long) * 4 * TVR_T));
+    RB_CUDA(cudaMemsetAsync(host.ll2, 0, sizeof(unsigned long long) * 4 * TVR_T, c->stream));
     RB_CUDA(cudaMalloc(&host.ll, sizeof(unsigned long long) * 64 * TVR_T));
     RB_CUDA(cudaMemsetAsync(host.ll, 0, sizeof(unsigned long long) * 64 * TVR_T, c->stream));
     RB_CUDA(cudaMalloc(&host.fm_best, sizeof(unsigned long long) * K));
@@ -78,6 +81,7 @@ void rb_track_state_free(rb_map *m) {
     cudaFree(h.carry);
     cudaFree(h.ctl);
     cudaFree(h.ll);
+    cudaFree(h.ll2);
     cudaFree(h.fm_best);
     cudaFree(h.fm_idx);
     cudaFree(h.reg_r);
@@ -91,8 +95,10 @@ void rb_track_state_free(rb_map *m) {
 // =====================================================================================================
 __global__ void __launch_bounds__(256) k_quantile(const double *__restrict__ s_rho, MapState *st,
                                                   int *__restrict__ histo, unsigned int *ticket, double smin,
-                                                  double smax, double perc, int n) {
+                                                  double smax, double perc, int n, FrameState *fs,
+                                                  const FrameArgs *fa, MapState *nst) {
     extern __shared__ int sh[];
+    if (fs && blockIdx.x == 0 && threadIdx.x == 0) d_frame_pre(fs, fa, nst);   // folded one-thread stage
     const int kn = st->kn;
     for (int i = threadIdx.x; i < n; i += blockDim.x) sh[i] = 0;
     __syncthreads();
@@ -131,11 +137,12 @@ __global__ void __launch_bounds__(256) k_quantile(const double *__restrict__ s_r
     }
 }
 
-int rb_quantile_enqueue(rb_ctx *c, rb_map *m, double smin, double smax, double perc, int nbins) {
+int rb_quantile_enqueue(rb_ctx *c, rb_map *m, double smin, double smax, double perc, int nbins, FrameState *fs,
+                        const FrameArgs *fa, MapState *nst) {
     if (nbins < 1 || nbins > 4096) return RB_ERR_ARG;
     int *histo = (int *)((char *)c->dev_small + RB_DS_QHISTO);  // zeroed at creation and by the kernel's tail
     k_quantile<<<64, 256, sizeof(int) * nbins, c->stream>>>(m->kl.s_rho, m->st, histo, c->ticket + 2, smin, smax,
-                                                            perc, nbins);
+                                                            perc, nbins, fs, fa, nst);
     RB_LAUNCH_CHECK();
     return RB_OK;
 }
@@ -1011,7 +1018,7 @@ __global__ void __launch_bounds__(TVR_T, 2) k_minimizer_persist(KLSoA old, const
                                                                 const unsigned long long *__restrict__ field,
                                                                 const float4 *__restrict__ fpack, MapState *f_st,
                                                                 TrackPtrs tp, ResPtrs res, CamC cam, MinPlan plan,
-                                                                MinSetup su) {
+                                                                MinSetup su, FrameState *post_fs) {
     __shared__ TvrSmem sm;
     __shared__ __align__(8) unsigned int s_req[MIN_REQ_WORDS + 2];
     __shared__ double s_carry[3];       // this block's stale-fi carry per residual buffer (block 0: always 0)
@@ -1243,7 +1250,10 @@ __global__ void __launch_bounds__(TVR_T, 2) k_minimizer_persist(KLSoA old, const
         double *dst = reinterpret_cast<double *>(tp.lm);
         for (int k = tid; k < (int)(sizeof(LMState) / sizeof(double)); k += TVR_T) dst[k] = src[k];
     }
-    if (tid == 0) ctl->gen = seq0 + MIN_MAX_EVALS + 1u;
+    if (tid == 0) {
+        ctl->gen = seq0 + MIN_MAX_EVALS + 1u;
+        if (post_fs) d_frame_post_min(post_fs, s_lm);   // folded one-thread stage of the per-frame pipeline
+    }
     TVR_STAMP(8);
 #ifdef RB_TVR_PROF
     if (tid == 0) g_tvr_prof[255 * 16 + 15] = n_act;
@@ -1286,7 +1296,9 @@ int rb_minimizer_resident_blocks(int sm_count) {
 }
 
 int rb_minimizer_enqueue(rb_ctx *c, rb_map *fmap, rb_map *old, const double *VW_dev, const rb_minimizer_args *a,
-                         double max_s_rho, bool s_rho_from_state, unsigned int frame_count, bool fc_from_state) {
+                         double max_s_rho, bool s_rho_from_state, unsigned int frame_count, bool fc_from_state,
+                         FrameState *post_fs, bool *post_folded) {
+    if (post_folded) *post_folded = false;
     if (fmap->field_radius <= 0) {
         snprintf(c->err, sizeof(c->err), "Minimizer_RV before build_field");
         return RB_ERR_STATE;
@@ -1322,8 +1334,9 @@ int rb_minimizer_enqueue(rb_ctx *c, rb_map *fmap, rb_map *old, const double *VW_
         ResPtrs rp;
         for (int i = 0; i < 3; i++) rp.r[i] = fmap->res[i];
         k_minimizer_persist<<<nblk, TVR_T, 0, c->stream>>>(old->kl, old->st, fmap->field, fmap->kl.pack, fmap->st,
-                                                          track_ptrs(fmap), rp, make_cam(c), plan, su);
+                                                          track_ptrs(fmap), rp, make_cam(c), plan, su, post_fs);
         RB_LAUNCH_CHECK();
+        if (post_folded) *post_folded = post_fs != nullptr;
         return RB_OK;
     }
     RB_CUDA(cudaMemsetAsync(fmap->res[0], 0, sizeof(double) * (size_t)c->kcap, c->stream));   // Residual[i]=0 (:625)
@@ -1423,15 +1436,23 @@ __global__ void __launch_bounds__(256) k_fm_apply(KLSoA old, KLSoA neu, MapState
 }
 __global__ void k_set_int(int *p, int v) { *p = v; }
 
-int rb_forward_match_enqueue(rb_ctx *c, rb_map *old, rb_map *neu) {
+// the arg-max scratch of a map only depends on its keyline count: the pipeline clears it on the detector stream
+int rb_forward_match_init_enqueue(rb_ctx *c, rb_map *neu) {
+    k_fm_init<<<rb_div_up(c->kcap, 256), 256, 0, c->stream>>>(neu->ts_host.fm_best, neu->ts_host.fm_idx, neu->st);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+int rb_forward_match_enqueue(rb_ctx *c, rb_map *old, rb_map *neu, bool scratch_ready) {
     const int nb = rb_div_up(c->kcap, 256);
     TrackState &t = neu->ts_host;
     if (!c->counters_preset) {   // the per-frame pipeline zeroes the counters in k_frame_pre
         k_set_int<<<1, 1, 0, c->stream>>>(&neu->st->fwd_match, 0);
         RB_LAUNCH_CHECK();
     }
-    k_fm_init<<<nb, 256, 0, c->stream>>>(t.fm_best, t.fm_idx, neu->st);
-    RB_LAUNCH_CHECK();
+    if (!scratch_ready) {
+        int r = rb_forward_match_init_enqueue(c, neu);
+        if (r) return r;
+    }
     k_fm_pass1<<<nb, 256, 0, c->stream>>>(old->kl, old->st, neu->st, t.fm_best);
     RB_LAUNCH_CHECK();
     k_fm_pass2<<<nb, 256, 0, c->stream>>>(old->kl, old->st, neu->st, t.fm_best, t.fm_idx);
@@ -1608,8 +1629,15 @@ int rb_directed_matching_enqueue(rb_ctx *c, rb_map *neu, rb_map *old, const DMat
 // =====================================================================================================
 __global__ void __launch_bounds__(256) k_regularize_a(KLSoA kl, MapState *st, double *__restrict__ r,
                                                       double *__restrict__ s, unsigned char *__restrict__ set,
-                                                      double thresh, const int *enable) {
-    if (enable && !*enable) return;
+                                                      double thresh, const int *enable, FrameState *fs,
+                                                      int match_threshold) {
+    if (fs) {   // per-frame pipeline: the "after directed_matching" glue is folded in (block 0 publishes it)
+        const bool en = fs->do_match && st->nmatch >= match_threshold;
+        if (blockIdx.x == 0 && threadIdx.x == 0) d_frame_post_match(fs, st, match_threshold);
+        if (!en) return;
+    } else if (enable && !*enable) {
+        return;
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool did = false;
     if (i < st->kn) {
@@ -1653,6 +1681,15 @@ __global__ void __launch_bounds__(256) k_regularize_b(KLSoA kl, const MapState *
     kl.s_rho[i] = s[i];
 }
 
+// first half of Regularize_1_iter alone (the pipeline runs the write-back half fused with the EKF, see k_regb_ekf)
+int rb_regularize_a_enqueue(rb_ctx *c, rb_map *m, double thresh, FrameState *fs, int match_threshold) {
+    TrackState &t = m->ts_host;
+    k_regularize_a<<<rb_div_up(c->kcap, 256), 256, 0, c->stream>>>(m->kl, m->st, t.reg_r, t.reg_s, t.reg_set, thresh,
+                                                                  nullptr, fs, match_threshold);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
 int rb_regularize_enqueue(rb_ctx *c, rb_map *m, double thresh, const int *enable_dev) {
     TrackState &t = m->ts_host;
     const int nb = rb_div_up(c->kcap, 256);
@@ -1660,7 +1697,7 @@ int rb_regularize_enqueue(rb_ctx *c, rb_map *m, double thresh, const int *enable
         k_set_int<<<1, 1, 0, c->stream>>>(&m->st->reg_num, 0);
         RB_LAUNCH_CHECK();
     }
-    k_regularize_a<<<nb, 256, 0, c->stream>>>(m->kl, m->st, t.reg_r, t.reg_s, t.reg_set, thresh, enable_dev);
+    k_regularize_a<<<nb, 256, 0, c->stream>>>(m->kl, m->st, t.reg_r, t.reg_s, t.reg_set, thresh, enable_dev, nullptr, 0);
     RB_LAUNCH_CHECK();
     k_regularize_b<<<nb, 256, 0, c->stream>>>(m->kl, m->st, t.reg_r, t.reg_s, t.reg_set, enable_dev);
     RB_LAUNCH_CHECK();
@@ -1670,14 +1707,9 @@ int rb_regularize_enqueue(rb_ctx *c, rb_map *m, double thresh, const int *enable
 // =====================================================================================================
 // UpdateInverseDepthKalman -> UpdateInverseDepthKalmanARLU (edge_tracker.cpp:695-724, 954-1055)
 // =====================================================================================================
-__global__ void __launch_bounds__(256) k_ekf(KLSoA kl, const MapState *st, const double *__restrict__ velp, double zf,
-                                             double q_abs, double loc_unc, const int *enable) {
-    if (enable && !*enable) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= st->kn) return;
-    if (kl.m_id[i] < 0) return;
+__device__ __forceinline__ void d_ekf(const KLSoA &kl, int i, double rho, double s_rho,
+                                      const double *__restrict__ velp, double zf, double q_abs, double loc_unc) {
     const double vel0 = velp[0], vel1 = velp[1], vel2 = velp[2];
-    double rho = kl.rho[i], s_rho = kl.s_rho[i];
     kl.s_rho0[i] = s_rho;
     const float2 pm = kl.p_m[i], pm0 = kl.p_m_0[i], mm0 = kl.m_m0[i];
     const double n_m0 = kl.n_m0[i];
@@ -1711,6 +1743,45 @@ __global__ void __launch_bounds__(256) k_ekf(KLSoA kl, const MapState *st, const
     }
     kl.rho[i] = rho;
     kl.s_rho[i] = s_rho;
+}
+__global__ void __launch_bounds__(256) k_ekf(KLSoA kl, const MapState *st, const double *__restrict__ velp, double zf,
+                                             double q_abs, double loc_unc, const int *enable) {
+    if (enable && !*enable) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st->kn) return;
+    if (kl.m_id[i] < 0) return;
+    d_ekf(kl, i, kl.rho[i], kl.s_rho[i], velp, zf, q_abs, loc_unc);
+}
+// write-back half of Regularize_1_iter + UpdateInverseDepthKalman in one pass: both only touch the thread's own
+// keyline, so the EKF can take the regularised (rho, s_rho) straight from registers
+__global__ void __launch_bounds__(256) k_regb_ekf(KLSoA kl, const MapState *st, const double *__restrict__ r,
+                                                  const double *__restrict__ s,
+                                                  const unsigned char *__restrict__ set,
+                                                  const double *__restrict__ velp, double zf, double q_abs,
+                                                  double loc_unc, const int *enable) {
+    if (enable && !*enable) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st->kn) return;
+    double rho, s_rho;
+    if (set[i]) {
+        rho = r[i];
+        s_rho = s[i];
+        kl.rho[i] = rho;
+        kl.s_rho[i] = s_rho;
+    } else {
+        rho = kl.rho[i];
+        s_rho = kl.s_rho[i];
+    }
+    if (kl.m_id[i] < 0) return;
+    d_ekf(kl, i, rho, s_rho, velp, zf, q_abs, loc_unc);
+}
+int rb_regb_ekf_enqueue(rb_ctx *c, rb_map *m, const double *vel_dev, double q_abs, double loc_unc,
+                        const int *enable_dev) {
+    TrackState &t = m->ts_host;
+    k_regb_ekf<<<rb_div_up(c->kcap, 256), 256, 0, c->stream>>>(m->kl, m->st, t.reg_r, t.reg_s, t.reg_set, vel_dev,
+                                                              c->zfm, q_abs, loc_unc, enable_dev);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
 }
 
 int rb_ekf_enqueue(rb_ctx *c, rb_map *m, const double *vel_dev, double q_abs, double loc_unc, const int *enable_dev) {
@@ -1797,9 +1868,135 @@ __global__ void __launch_bounds__(256) k_rescale_apply(KLSoA kl, const MapState 
     kl.s_rho[i] = kl.s_rho[i] / Kp;
 }
 
+// The same five fixed-point iterations in ONE launch: block b keeps its keylines' operands in registers; after every
+// iteration the blocks exchange their two partial sums through self-validating 8-byte slots (every block polls every
+// block: an all-gather, so each block gets the new Kp without a second hop) and reduce them in a fixed order.  The
+// optional tail (block 0) is the per-frame pipeline's pose integration / nav record, folded in to save its launch.
+// Needs all blocks that own keylines co-resident, like k_minimizer_persist; bounded spins.
+__global__ void __launch_bounds__(256) k_rescale_persist(KLSoA kl, MapState *st, unsigned long long *ll2, MinCtl *ctl,
+                                                         double s_rho_min, unsigned int mnm, int re_escale,
+                                                         const int *enable, FrameState *fs, const MapState *ost,
+                                                         const LMState *lm, rb_nav *nav, const FrameArgs *fa) {
+    __shared__ double sa[8], sb[8], ga[8], gb[8];
+    __shared__ int s_abort;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const bool en = !enable || *enable;
+    const int kn = st->kn;
+    const int n_act = (en && kn > 0) ? (kn + 255) / 256 : 1;
+    if ((int)blockIdx.x >= n_act) return;
+    if (en) {
+        const unsigned int seq0 = __ldcg(&ctl->gen2);
+        if (tid == 0) s_abort = 0;
+        const int i = blockIdx.x * 256 + tid;
+        bool valid = false;
+        double rho = 0, s = 0, s0 = 0, r2 = 0, r02 = 0, s2 = 0;
+        if (i < kn) {
+            s0 = kl.s_rho0[i];
+            s = kl.s_rho[i];
+            rho = kl.rho[i];
+            if (!((unsigned int)kl.m_num[i] < mnm || s0 <= 0 || s > s_rho_min)) {
+                valid = true;
+                const double r0 = kl.rho0[i];
+                r2 = rho * rho;
+                r02 = r0 * r0;
+                s2 = s * s;
+            }
+        }
+        double Kp = 1.0, RKp = 0;
+        __syncthreads();
+        for (int iter = 0; iter < 5; iter++) {
+            const unsigned int seq = seq0 + 1u + (unsigned int)iter;
+            double a = 0, b = 0;
+            if (valid) {
+                const double den = s2 + Kp * Kp * s0 * s0;
+                a = r2 / den;
+                b = r02 / den;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                b += __shfl_xor_sync(0xffffffffu, b, o);
+            }
+            if (lane == 0) {
+                sa[wid] = a;
+                sb[wid] = b;
+            }
+            __syncthreads();
+            if (tid < 4) {
+                double x = 0;
+                const double *src = (tid < 2) ? sa : sb;
+                for (int k = 0; k < 8; k++) x += src[k];
+                const unsigned int w = (tid & 1) ? (unsigned int)__double2hiint(x) : (unsigned int)__double2loint(x);
+                st_volatile_u64(ll2 + (size_t)tid * 256 + blockIdx.x, ((unsigned long long)seq << 32) | w);
+            }
+            double pa = 0, pb = 0;
+            if (tid < n_act) {
+                const unsigned long long *src = ll2 + tid;
+                const long long t0 = clock64();
+                for (;;) {
+                    const unsigned long long w0 = ld_volatile_u64(src), w1 = ld_volatile_u64(src + 256);
+                    const unsigned long long w2 = ld_volatile_u64(src + 512), w3 = ld_volatile_u64(src + 768);
+                    if ((unsigned int)(w0 >> 32) == seq && (unsigned int)(w1 >> 32) == seq &&
+                        (unsigned int)(w2 >> 32) == seq && (unsigned int)(w3 >> 32) == seq) {
+                        pa = __hiloint2double((int)(unsigned int)w1, (int)(unsigned int)w0);
+                        pb = __hiloint2double((int)(unsigned int)w3, (int)(unsigned int)w2);
+                        break;
+                    }
+                    if (clock64() - t0 > MIN_SPIN_LIMIT) {
+                        s_abort = 1;
+                        break;
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                pa += __shfl_xor_sync(0xffffffffu, pa, o);
+                pb += __shfl_xor_sync(0xffffffffu, pb, o);
+            }
+            if (lane == 0) {
+                ga[wid] = pa;
+                gb[wid] = pb;
+            }
+            __syncthreads();
+            double rTr = 0, rTr0 = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                rTr += ga[k];
+                rTr0 += gb[k];
+            }
+            if (kn > 0) {
+                Kp = rTr0 > 0 ? sqrt(rTr / rTr0) : 1;
+                RKp = 1 / rTr0;
+            }
+            if (s_abort) break;
+        }
+        if (s_abort) Kp = __longlong_as_double(0x7FF8000000000000ll);
+        if (re_escale && i < kn) {
+            kl.rho[i] = rho / Kp;
+            kl.s_rho[i] = s / Kp;
+        }
+        if (blockIdx.x == 0 && tid == 0) {
+            st->Kp = Kp;              // "if(kn<=0) return 1;" leaves RKp alone
+            if (kn > 0) st->RKp = RKp;
+            ctl->gen2 = seq0 + 8u;
+            if (s_abort) ctl->abort = 1;
+        }
+    }
+    if (fs && blockIdx.x == 0 && tid == 0) d_frame_finish(fs, st, ost, lm->score, nav, fa);
+}
+
 int rb_rescale_enqueue(rb_ctx *c, rb_map *m, double s_rho_min, unsigned int match_num_min, int re_escale,
-                       const int *enable_dev) {
+                       const int *enable_dev, FrameState *fs, const MapState *ost, rb_nav *nav, const FrameArgs *fa,
+                       bool *finish_folded) {
     const int nb = m->ts_host.nblk;
+    if (finish_folded) *finish_folded = false;
+    if (c->min_persist && nb <= c->min_resident && nb <= 256) {
+        k_rescale_persist<<<nb, 256, 0, c->stream>>>(m->kl, m->st, m->ts_host.ll2, m->ts_host.ctl, s_rho_min,
+                                                     match_num_min, re_escale, enable_dev, fs, ost, &m->ts->lm, nav, fa);
+        RB_LAUNCH_CHECK();
+        if (finish_folded) *finish_folded = fs != nullptr;
+        return RB_OK;
+    }
     for (int iter = 0; iter < 5; iter++) {
         k_rescale_iter<<<nb, 256, 0, c->stream>>>(m->kl, m->st, m->ts_host.partials, c->ticket + 3, s_rho_min,
                                                   match_num_min, iter, enable_dev);

@@ -19,6 +19,7 @@ enum LMStep {
 struct MinCtl {
     unsigned long long slot[40];   // {hi: sequence number, lo: payload word}; all zero between minimisations
     unsigned int gen;              // base of the sequence numbers of the next minimisation
+    unsigned int gen2;             // same for the persistent rescaling kernel
     int abort;                     // sticky: a spin timed out
 };
 
@@ -35,12 +36,19 @@ struct rb_minimizer_args {
 
 // Enqueue the whole Minimizer_RV on c->stream.  Vel/W0 priors are read from dev pointers VW_dev[6]
 // (V then W); max_s_rho is read from old->st->s_rho_q when s_rho_from_state, else from the argument.
+// The optional FrameState / FrameArgs / rb_nav arguments below belong to the per-frame pipeline (frame.cuh): when given,
+// the one-thread glue stage next to the kernel runs inside it instead of as its own launch.
+struct FrameState;
+struct FrameArgs;
 int rb_minimizer_enqueue(rb_ctx *c, rb_map *fmap, rb_map *old, const double *VW_dev,
                          const rb_minimizer_args *a, double max_s_rho, bool s_rho_from_state,
-                         unsigned int frame_count, bool frame_count_from_state);
-int rb_quantile_enqueue(rb_ctx *c, rb_map *m, double smin, double smax, double perc, int nbins);
+                         unsigned int frame_count, bool frame_count_from_state, FrameState *post_fs = nullptr,
+                         bool *post_folded = nullptr);
+int rb_quantile_enqueue(rb_ctx *c, rb_map *m, double smin, double smax, double perc, int nbins,
+                        FrameState *fs = nullptr, const FrameArgs *fa = nullptr, MapState *nst = nullptr);
 int rb_build_field_enqueue(rb_ctx *c, rb_map *m, int radius, float min_mod, bool min_mod_from_state);
-int rb_forward_match_enqueue(rb_ctx *c, rb_map *old, rb_map *neu);
+int rb_forward_match_init_enqueue(rb_ctx *c, rb_map *neu);
+int rb_forward_match_enqueue(rb_ctx *c, rb_map *old, rb_map *neu, bool scratch_ready = false);
 int rb_rotate_enqueue(rb_ctx *c, rb_map *m, const double *R_dev);
 struct DMatchArgs {       // device-resident arguments of directed_matching (after the back-rotation)
     double Vel[3];        // BackRot*Vel
@@ -51,8 +59,12 @@ int rb_directed_matching_enqueue(rb_ctx *c, rb_map *neu, rb_map *old, const DMat
                                  double min_thr_mod, double min_thr_ang, double max_radius,
                                  double loc_uncertainty, const int *enable_dev);
 int rb_regularize_enqueue(rb_ctx *c, rb_map *m, double thresh, const int *enable_dev);
+int rb_regularize_a_enqueue(rb_ctx *c, rb_map *m, double thresh, FrameState *fs, int match_threshold);
+int rb_regb_ekf_enqueue(rb_ctx *c, rb_map *m, const double *vel_dev, double q_abs, double loc_unc,
+                        const int *enable_dev);
 int rb_ekf_enqueue(rb_ctx *c, rb_map *m, const double *vel_dev, double q_abs, double loc_unc,
                    const int *enable_dev);
 int rb_rescale_enqueue(rb_ctx *c, rb_map *m, double s_rho_min, unsigned int match_num_min, int re_escale,
-                       const int *enable_dev);
+                       const int *enable_dev, FrameState *fs = nullptr, const MapState *ost = nullptr,
+                       rb_nav *nav = nullptr, const FrameArgs *fa = nullptr, bool *finish_folded = nullptr);
 int rb_read_map_state(rb_map *m, MapState *host);
