@@ -164,6 +164,8 @@ extern "C" int rb_ctx_create(rb_ctx **out, int device, const rb_camera *cam, dou
         const char *ds = getenv("REBVO_B200_DOG_SUB");
         c->dog_sub = ds ? atoi(ds) : 0;   // 0 = whole batch in one go (measured fastest: the passes are latency-bound)
         if (c->dog_sub < 0) c->dog_sub = 0;
+        const char *pd = getenv("REBVO_B200_PDL");
+        c->pdl = !(pd && atoi(pd) == 0);
         const char *mp = getenv("REBVO_B200_MIN_PERSIST");
         c->min_persist = !(mp && atoi(mp) == 0);
         const char *rs = getenv("REBVO_B200_ROWSCAN");

@@ -91,6 +91,7 @@ struct rb_ctx {
     float *boxtab;       // 6 x 64 reciprocal clipped-area tables (iimage::build_average), see dog.cu
     bool counters_preset; // set by rb_pipeline: match / regularise counters are zeroed by k_frame_pre
     int dog_sub;         // frames per scale-space sub-batch, env REBVO_B200_DOG_SUB (0 = whole batch, the default)
+    bool pdl;            // programmatic dependent launch of the per-frame chain (env REBVO_B200_PDL=0 disables)
     bool min_persist;    // whole Minimizer_RV in one persistent launch (env REBVO_B200_MIN_PERSIST=0 disables)
     int min_resident;    // blocks of that kernel the device keeps resident at once
     int rowscan_mode;    // env REBVO_B200_ROWSCAN: 1 = register-prefetch kernel, 2 = cp.async shared-memory ring
@@ -183,6 +184,43 @@ struct rb_map {
     } while (0)
 
 static inline int rb_div_up(int a, int b) { return (a + b - 1) / b; }
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------
+// The per-frame chain is ~10 short dependent kernels; with plain stream order each pays the full launch latency after
+// its predecessor drains.  Kernels of the chain start with pdl_wait() + pdl_launch(): launched through RB_KLAUNCH
+// (programmatic stream serialization), the next grid is set up and resident while this one runs and only waits at
+// griddepcontrol.wait for this grid to complete (memory flushed).  Without the launch attribute both instructions
+// are no-ops, so the stage-level API can launch the same kernels the ordinary way.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t rb_klaunch(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#define RB_KLAUNCH(kernel, grid, block, smem, ...)                                                  \
+    do {                                                                                            \
+        c->launches++;                                                                              \
+        cudaError_t e__ = rb_klaunch(c->pdl, kernel, dim3(grid), dim3(block), smem, c->stream, __VA_ARGS__); \
+        if (e__ != cudaSuccess) {                                                                   \
+            snprintf(c->err, sizeof(c->err), "%s:%d launch: %s", __FILE__, __LINE__,                \
+                     cudaGetErrorString(e__));                                                      \
+            return RB_ERR_CUDA;                                                                     \
+        }                                                                                           \
+    } while (0)
+#endif
 
 // ---- stage entry points (host side, enqueue on c->stream) ------------------------------------------
 // dog.cu

@@ -302,7 +302,9 @@ static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, const FrameArg
     }
     // :354  FordwardMatch ; :369 rotate_keylines(R0)
     if ((r = rb_forward_match_enqueue(c, old, neu, pl->overlap))) return r;
+    RB_TRACE(c->stream, 10);
     if ((r = rb_rotate_enqueue(c, old, pl->fs->R0))) return r;
+    RB_TRACE(c->stream, 11);
     prof_mark(pl, ST_FWD_ROT);
     // :410  directed_matching(V,P_V,R,old_buf.ef,...)
     if ((r = rb_directed_matching_enqueue(c, neu, old, &pl->fs->dm, p.MatchThreshModule, p.MatchThreshAngle,
@@ -310,22 +312,14 @@ static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, const FrameArg
         return r;
     RB_TRACE(c->stream, 4);
     prof_mark(pl, ST_DMATCH);
-    // :410-423 match-count gate (folded into the first regularisation kernel) ; :452-487 Regularize_1_iter,
-    // UpdateInverseDepthKalman (write-back half of the former fused with the latter), EstimateReScalingOpt
-    if ((r = rb_regularize_a_enqueue(c, neu, p.RegularizeThresh, pl->fs, p.MatchThreshold))) return r;
-    if ((r = rb_regb_ekf_enqueue(c, neu, pl->fs->V, p.ReshapeQAbsolute, p.LocationUncertainty, &pl->fs->do_map)))
+    // :410-423 match-count gate, :452-487 Regularize_1_iter / UpdateInverseDepthKalman / EstimateReScalingOpt and
+    // :545-585 pose integration + NavData: one cluster kernel (tracker.cu, k_map_update)
+    if ((r = rb_map_update_enqueue(c, neu, p.RegularizeThresh, pl->fs->V, p.ReshapeQAbsolute, p.LocationUncertainty,
+                                   RB_RHO_MAX, 1, p.DoReScaling > 0 ? 1 : 0, pl->fs, p.MatchThreshold, old->st,
+                                   nav_slot, fa)))
         return r;
     prof_mark(pl, ST_REG_EKF);
-    // :545-585 pose integration + NavData folded into the rescaling kernel's block 0
-    folded = false;
-    if ((r = rb_rescale_enqueue(c, neu, RB_RHO_MAX, 1, p.DoReScaling > 0 ? 1 : 0, &pl->fs->do_map, pl->fs, old->st,
-                                nav_slot, fa, &folded)))
-        return r;
     prof_mark(pl, ST_RESCALE);
-    if (!folded) {
-        k_frame_finish<<<1, 1, 0, c->stream>>>(pl->fs, neu->st, old->st, neu->ts, nav_slot, fa);
-        RB_LAUNCH_CHECK();
-    }
     RB_TRACE(c->stream, 5);
     prof_mark(pl, ST_FINISH);
     return RB_OK;
@@ -417,12 +411,16 @@ static int push_impl(rb_pipeline *pl, const uint8_t *rgb, bool on_device, const 
         if ((r = enqueue_batch(pl, n, first, true))) return r;
     } else {
         const int key = (int)(first % RB_NMAPS) * (pl->max_batch + 1) + n;
-        if (!pl->gexec[key]) {
-            // capture the batch once; replays only differ through fa_dev / ws.rgb contents
+        // capture the batch once per ring phase; replays only differ through fa_dev / ws.rgb contents.  All phases of
+        // this batch size are instantiated together, so that no later push pays for a capture.
+        const bool build = !pl->gexec[key];
+        for (int ph = 0; ph < RB_NMAPS && build; ph++) {
+            const int k = ph * (pl->max_batch + 1) + n;
+            if (pl->gexec[k]) continue;
             cudaGraph_t g = nullptr;
             const int64_t l0 = c->launches;
             RB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-            r = enqueue_batch(pl, n, first, false);
+            r = enqueue_batch(pl, n, ph == 0 ? RB_NMAPS : ph, false);   // any first frame > 0 of that phase
             cudaError_t e = cudaStreamEndCapture(c->stream, &g);
             if (r) {
                 if (g) cudaGraphDestroy(g);
@@ -432,12 +430,12 @@ static int push_impl(rb_pipeline *pl, const uint8_t *rgb, bool on_device, const 
                 snprintf(c->err, sizeof(c->err), "graph capture: %s", cudaGetErrorString(e));
                 return RB_ERR_CUDA;
             }
-            pl->glaunches[key] = (int)(c->launches - l0);
+            pl->glaunches[k] = (int)(c->launches - l0);
             c->launches = l0;
-            e = cudaGraphInstantiate(&pl->gexec[key], g, 0);
+            e = cudaGraphInstantiate(&pl->gexec[k], g, 0);
             cudaGraphDestroy(g);
             if (e != cudaSuccess) {
-                pl->gexec[key] = nullptr;
+                pl->gexec[k] = nullptr;
                 snprintf(c->err, sizeof(c->err), "graph instantiate: %s", cudaGetErrorString(e));
                 return RB_ERR_CUDA;
             }

@@ -97,6 +97,8 @@ __global__ void __launch_bounds__(256) k_quantile(const double *__restrict__ s_r
                                                   int *__restrict__ histo, unsigned int *ticket, double smin,
                                                   double smax, double perc, int n, FrameState *fs,
                                                   const FrameArgs *fa, MapState *nst) {
+    pdl_wait();
+    pdl_launch();
     extern __shared__ int sh[];
     if (fs && blockIdx.x == 0 && threadIdx.x == 0) d_frame_pre(fs, fa, nst);   // folded one-thread stage
     const int kn = st->kn;
@@ -141,9 +143,8 @@ int rb_quantile_enqueue(rb_ctx *c, rb_map *m, double smin, double smax, double p
                         const FrameArgs *fa, MapState *nst) {
     if (nbins < 1 || nbins > 4096) return RB_ERR_ARG;
     int *histo = (int *)((char *)c->dev_small + RB_DS_QHISTO);  // zeroed at creation and by the kernel's tail
-    k_quantile<<<64, 256, sizeof(int) * nbins, c->stream>>>(m->kl.s_rho, m->st, histo, c->ticket + 2, smin, smax,
-                                                            perc, nbins, fs, fa, nst);
-    RB_LAUNCH_CHECK();
+    RB_KLAUNCH(k_quantile, 64, 256, sizeof(int) * nbins, m->kl.s_rho, m->st, histo, c->ticket + 2, smin, smax, perc,
+               nbins, fs, fa, nst);
     return RB_OK;
 }
 
@@ -1019,6 +1020,8 @@ __global__ void __launch_bounds__(TVR_T, 2) k_minimizer_persist(KLSoA old, const
                                                                 const float4 *__restrict__ fpack, MapState *f_st,
                                                                 TrackPtrs tp, ResPtrs res, CamC cam, MinPlan plan,
                                                                 MinSetup su, FrameState *post_fs) {
+    pdl_wait();
+    pdl_launch();
     __shared__ TvrSmem sm;
     __shared__ __align__(8) unsigned int s_req[MIN_REQ_WORDS + 2];
     __shared__ double s_carry[3];       // this block's stale-fi carry per residual buffer (block 0: always 0)
@@ -1333,9 +1336,8 @@ int rb_minimizer_enqueue(rb_ctx *c, rb_map *fmap, rb_map *old, const double *VW_
         su.fc_from_state = fc_from_state ? 1 : 0;
         ResPtrs rp;
         for (int i = 0; i < 3; i++) rp.r[i] = fmap->res[i];
-        k_minimizer_persist<<<nblk, TVR_T, 0, c->stream>>>(old->kl, old->st, fmap->field, fmap->kl.pack, fmap->st,
-                                                          track_ptrs(fmap), rp, make_cam(c), plan, su, post_fs);
-        RB_LAUNCH_CHECK();
+        RB_KLAUNCH(k_minimizer_persist, nblk, TVR_T, 0, old->kl, old->st, fmap->field, fmap->kl.pack, fmap->st,
+                   track_ptrs(fmap), rp, make_cam(c), plan, su, post_fs);
         if (post_folded) *post_folded = post_fs != nullptr;
         return RB_OK;
     }
@@ -1404,6 +1406,8 @@ __global__ void __launch_bounds__(256) k_fm_init(unsigned long long *best, int *
 }
 __global__ void __launch_bounds__(256) k_fm_pass1(KLSoA old, const MapState *ost, const MapState *nst,
                                                   unsigned long long *best) {
+    pdl_wait();
+    pdl_launch();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ost->kn) return;
     const int f = old.m_id_f[i];
@@ -1412,6 +1416,8 @@ __global__ void __launch_bounds__(256) k_fm_pass1(KLSoA old, const MapState *ost
 }
 __global__ void __launch_bounds__(256) k_fm_pass2(KLSoA old, const MapState *ost, const MapState *nst,
                                                   const unsigned long long *best, int *idx) {
+    pdl_wait();
+    pdl_launch();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ost->kn) return;
     const int f = old.m_id_f[i];
@@ -1419,6 +1425,8 @@ __global__ void __launch_bounds__(256) k_fm_pass2(KLSoA old, const MapState *ost
     if (dbl_key(old.rho[i]) == best[f]) atomicMax(&idx[f], i);
 }
 __global__ void __launch_bounds__(256) k_fm_apply(KLSoA old, KLSoA neu, MapState *nst, const int *idx) {
+    pdl_wait();
+    pdl_launch();
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = f < nst->kn;
     int i = valid ? idx[f] : -1;
@@ -1453,12 +1461,9 @@ int rb_forward_match_enqueue(rb_ctx *c, rb_map *old, rb_map *neu, bool scratch_r
         int r = rb_forward_match_init_enqueue(c, neu);
         if (r) return r;
     }
-    k_fm_pass1<<<nb, 256, 0, c->stream>>>(old->kl, old->st, neu->st, t.fm_best);
-    RB_LAUNCH_CHECK();
-    k_fm_pass2<<<nb, 256, 0, c->stream>>>(old->kl, old->st, neu->st, t.fm_best, t.fm_idx);
-    RB_LAUNCH_CHECK();
-    k_fm_apply<<<nb, 256, 0, c->stream>>>(old->kl, neu->kl, neu->st, t.fm_idx);
-    RB_LAUNCH_CHECK();
+    RB_KLAUNCH(k_fm_pass1, nb, 256, 0, old->kl, old->st, neu->st, t.fm_best);
+    RB_KLAUNCH(k_fm_pass2, nb, 256, 0, old->kl, old->st, neu->st, t.fm_best, t.fm_idx);
+    RB_KLAUNCH(k_fm_apply, nb, 256, 0, old->kl, neu->kl, neu->st, t.fm_idx);
     return RB_OK;
 }
 
@@ -1467,6 +1472,8 @@ int rb_forward_match_enqueue(rb_ctx *c, rb_map *old, rb_map *neu, bool scratch_r
 // =====================================================================================================
 __global__ void __launch_bounds__(256) k_rotate(KLSoA kl, const MapState *st, const double *__restrict__ Rp,
                                                 double zf) {
+    pdl_wait();
+    pdl_launch();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= st->kn) return;
     double R[9];
@@ -1497,8 +1504,7 @@ __global__ void __launch_bounds__(256) k_rotate(KLSoA kl, const MapState *st, co
 }
 
 int rb_rotate_enqueue(rb_ctx *c, rb_map *m, const double *R_dev) {
-    k_rotate<<<rb_div_up(c->kcap, 256), 256, 0, c->stream>>>(m->kl, m->st, R_dev, c->zfm);
-    RB_LAUNCH_CHECK();
+    RB_KLAUNCH(k_rotate, rb_div_up(c->kcap, 256), 256, 0, m->kl, m->st, R_dev, c->zfm);
     return RB_OK;
 }
 
@@ -1509,6 +1515,8 @@ __global__ void __launch_bounds__(128) k_directed_match(KLSoA neu, MapState *nst
                                                         const int *__restrict__ omask, const DMatchArgs *__restrict__ ap,
                                                         CamC cam, double min_thr_mod, double cang_min_edge,
                                                         double max_radius, double loc_unc, const int *enable) {
+    pdl_wait();
+    pdl_launch();
     if (enable && !*enable) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool got = false;
@@ -1617,57 +1625,52 @@ int rb_directed_matching_enqueue(rb_ctx *c, rb_map *neu, rb_map *old, const DMat
         k_set_int<<<1, 1, 0, c->stream>>>(&neu->st->nmatch, 0);
         RB_LAUNCH_CHECK();
     }
-    k_directed_match<<<rb_div_up(c->kcap, 128), 128, 0, c->stream>>>(neu->kl, neu->st, old->kl, old->mask, args_dev,
-                                                                    make_cam(c), min_thr_mod, cang_min_edge,
-                                                                    max_radius, loc_uncertainty, enable_dev);
-    RB_LAUNCH_CHECK();
+    RB_KLAUNCH(k_directed_match, rb_div_up(c->kcap, 128), 128, 0, neu->kl, neu->st, old->kl, old->mask, args_dev,
+               make_cam(c), min_thr_mod, cang_min_edge, max_radius, loc_uncertainty, enable_dev);
     return RB_OK;
 }
 
 // =====================================================================================================
 // Regularize_1_iter (edge_tracker.cpp:87-148), double buffered like the reference
 // =====================================================================================================
-__global__ void __launch_bounds__(256) k_regularize_a(KLSoA kl, MapState *st, double *__restrict__ r,
-                                                      double *__restrict__ s, unsigned char *__restrict__ set,
-                                                      double thresh, const int *enable, FrameState *fs,
-                                                      int match_threshold) {
-    if (fs) {   // per-frame pipeline: the "after directed_matching" glue is folded in (block 0 publishes it)
-        const bool en = fs->do_match && st->nmatch >= match_threshold;
-        if (blockIdx.x == 0 && threadIdx.x == 0) d_frame_post_match(fs, st, match_threshold);
-        if (!en) return;
-    } else if (enable && !*enable) {
-        return;
-    }
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// first half of Regularize_1_iter for keyline i: smoothed (rho, s_rho) into r / s, set[i] says whether it applies
+__device__ __forceinline__ bool d_reg_a(const KLSoA &kl, int i, double *__restrict__ r, double *__restrict__ s,
+                                        unsigned char *__restrict__ set, double thresh) {
     bool did = false;
-    if (i < st->kn) {
-        unsigned char sv = 0;
-        const int ni = kl.n_id[i], pi = kl.p_id[i];
-        if (ni >= 0 && pi >= 0) {
-            const double krho = kl.rho[i], ks = kl.s_rho[i];
-            const double nrho = kl.rho[ni], ns = kl.s_rho[ni];
-            const double prho = kl.rho[pi], ps = kl.s_rho[pi];
-            const double d = nrho - prho;
-            if (!(d * d > ns * ns + ps * ps)) {
-                const float2 nm = kl.m_m[ni], pmv = kl.m_m[pi];
-                const float nnm = kl.n_m[ni], pnm = kl.n_m[pi];
-                // floats: (kn.m_m.x*kp.m_m.x+kn.m_m.y*kp.m_m.y)/(kn.n_m*kp.n_m) evaluates in float
-                double alpha = (double)((nm.x * pmv.x + nm.y * pmv.y) / (nnm * pnm));
-                if (!(alpha - thresh < 0)) {
-                    alpha = (alpha - thresh) / (1 - thresh);
-                    alpha /= fabs(nrho - prho) / (ns + ps) + 1;
-                    const double wr = 1 / (ks * ks);
-                    const double wrn = alpha / (ns * ns);
-                    const double wrp = alpha / (ps * ps);
-                    r[i] = (krho * wr + nrho * wrn + prho * wrp) / (wr + wrn + wrp);
-                    s[i] = (ks * wr + ns * wrn + ps * wrp) / (wr + wrn + wrp);
-                    sv = 1;
-                    did = true;
-                }
+    unsigned char sv = 0;
+    const int ni = kl.n_id[i], pi = kl.p_id[i];
+    if (ni >= 0 && pi >= 0) {
+        const double krho = kl.rho[i], ks = kl.s_rho[i];
+        const double nrho = kl.rho[ni], ns = kl.s_rho[ni];
+        const double prho = kl.rho[pi], ps = kl.s_rho[pi];
+        const double d = nrho - prho;
+        if (!(d * d > ns * ns + ps * ps)) {
+            const float2 nm = kl.m_m[ni], pmv = kl.m_m[pi];
+            const float nnm = kl.n_m[ni], pnm = kl.n_m[pi];
+            // floats: (kn.m_m.x*kp.m_m.x+kn.m_m.y*kp.m_m.y)/(kn.n_m*kp.n_m) evaluates in float
+            double alpha = (double)((nm.x * pmv.x + nm.y * pmv.y) / (nnm * pnm));
+            if (!(alpha - thresh < 0)) {
+                alpha = (alpha - thresh) / (1 - thresh);
+                alpha /= fabs(nrho - prho) / (ns + ps) + 1;
+                const double wr = 1 / (ks * ks);
+                const double wrn = alpha / (ns * ns);
+                const double wrp = alpha / (ps * ps);
+                r[i] = (krho * wr + nrho * wrn + prho * wrp) / (wr + wrn + wrp);
+                s[i] = (ks * wr + ns * wrn + ps * wrp) / (wr + wrn + wrp);
+                sv = 1;
+                did = true;
             }
         }
-        set[i] = sv;
     }
+    set[i] = sv;
+    return did;
+}
+__global__ void __launch_bounds__(256) k_regularize_a(KLSoA kl, MapState *st, double *__restrict__ r,
+                                                      double *__restrict__ s, unsigned char *__restrict__ set,
+                                                      double thresh, const int *enable) {
+    if (enable && !*enable) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool did = i < st->kn ? d_reg_a(kl, i, r, s, set, thresh) : false;
     const unsigned int bal = __ballot_sync(0xffffffffu, did);
     if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&st->reg_num, __popc(bal));
 }
@@ -1681,15 +1684,6 @@ __global__ void __launch_bounds__(256) k_regularize_b(KLSoA kl, const MapState *
     kl.s_rho[i] = s[i];
 }
 
-// first half of Regularize_1_iter alone (the pipeline runs the write-back half fused with the EKF, see k_regb_ekf)
-int rb_regularize_a_enqueue(rb_ctx *c, rb_map *m, double thresh, FrameState *fs, int match_threshold) {
-    TrackState &t = m->ts_host;
-    k_regularize_a<<<rb_div_up(c->kcap, 256), 256, 0, c->stream>>>(m->kl, m->st, t.reg_r, t.reg_s, t.reg_set, thresh,
-                                                                  nullptr, fs, match_threshold);
-    RB_LAUNCH_CHECK();
-    return RB_OK;
-}
-
 int rb_regularize_enqueue(rb_ctx *c, rb_map *m, double thresh, const int *enable_dev) {
     TrackState &t = m->ts_host;
     const int nb = rb_div_up(c->kcap, 256);
@@ -1697,7 +1691,7 @@ int rb_regularize_enqueue(rb_ctx *c, rb_map *m, double thresh, const int *enable
         k_set_int<<<1, 1, 0, c->stream>>>(&m->st->reg_num, 0);
         RB_LAUNCH_CHECK();
     }
-    k_regularize_a<<<nb, 256, 0, c->stream>>>(m->kl, m->st, t.reg_r, t.reg_s, t.reg_set, thresh, enable_dev, nullptr, 0);
+    k_regularize_a<<<nb, 256, 0, c->stream>>>(m->kl, m->st, t.reg_r, t.reg_s, t.reg_set, thresh, enable_dev);
     RB_LAUNCH_CHECK();
     k_regularize_b<<<nb, 256, 0, c->stream>>>(m->kl, m->st, t.reg_r, t.reg_s, t.reg_set, enable_dev);
     RB_LAUNCH_CHECK();
@@ -1752,259 +1746,242 @@ __global__ void __launch_bounds__(256) k_ekf(KLSoA kl, const MapState *st, const
     if (kl.m_id[i] < 0) return;
     d_ekf(kl, i, kl.rho[i], kl.s_rho[i], velp, zf, q_abs, loc_unc);
 }
-// write-back half of Regularize_1_iter + UpdateInverseDepthKalman in one pass: both only touch the thread's own
-// keyline, so the EKF can take the regularised (rho, s_rho) straight from registers
-__global__ void __launch_bounds__(256) k_regb_ekf(KLSoA kl, const MapState *st, const double *__restrict__ r,
-                                                  const double *__restrict__ s,
-                                                  const unsigned char *__restrict__ set,
-                                                  const double *__restrict__ velp, double zf, double q_abs,
-                                                  double loc_unc, const int *enable) {
-    if (enable && !*enable) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= st->kn) return;
-    double rho, s_rho;
-    if (set[i]) {
-        rho = r[i];
-        s_rho = s[i];
-        kl.rho[i] = rho;
-        kl.s_rho[i] = s_rho;
-    } else {
-        rho = kl.rho[i];
-        s_rho = kl.s_rho[i];
-    }
-    if (kl.m_id[i] < 0) return;
-    d_ekf(kl, i, rho, s_rho, velp, zf, q_abs, loc_unc);
-}
-int rb_regb_ekf_enqueue(rb_ctx *c, rb_map *m, const double *vel_dev, double q_abs, double loc_unc,
-                        const int *enable_dev) {
-    TrackState &t = m->ts_host;
-    k_regb_ekf<<<rb_div_up(c->kcap, 256), 256, 0, c->stream>>>(m->kl, m->st, t.reg_r, t.reg_s, t.reg_set, vel_dev,
-                                                              c->zfm, q_abs, loc_unc, enable_dev);
-    RB_LAUNCH_CHECK();
-    return RB_OK;
-}
-
 int rb_ekf_enqueue(rb_ctx *c, rb_map *m, const double *vel_dev, double q_abs, double loc_unc, const int *enable_dev) {
     k_ekf<<<rb_div_up(c->kcap, 256), 256, 0, c->stream>>>(m->kl, m->st, vel_dev, c->zfm, q_abs, loc_unc, enable_dev);
     RB_LAUNCH_CHECK();
     return RB_OK;
 }
 
+
 // =====================================================================================================
-// EstimateReScalingOpt (edge_tracker.cpp:1104-1140): 5 fixed-point iterations, one block
+// Map update of a frame in ONE thread-block cluster: Regularize_1_iter (edge_tracker.cpp:87-148),
+// UpdateInverseDepthKalman (:695-724, 954-1055), EstimateReScalingOpt (:1104-1140) and the rescaling itself.
+//
+// These stages are light per keyline but separated by grid-wide dependencies (the smoothing reads neighbours, each
+// of the five rescaling iterations needs sums over all keylines): as separate kernels, or as one kernel exchanging
+// through L2, a frame paid ~40 us of launch / hand-over latency for ~3 us of arithmetic.  A cluster of 8 CTAs holds
+// the whole edge map (thread t of CTA r owns keylines (j*8 + r)*MU_T + t), synchronises with barrier.cluster and
+// all-reduces the two sums of an iteration through distributed shared memory: every CTA stores its pair into every
+// CTA's slot table, one cluster barrier, every CTA adds the 8 pairs in rank order.  One launch, ~6 cluster barriers.
+// Sums: per thread in keyline order, warp xor-tree, warps in order, ranks in order -- fixed, not the reference's
+// sequential order (parity to rounding, as for every other reduction here).
+// The optional head / tail are the per-frame pipeline's scalar glue (frame.cuh), folded in to save their launches.
 // =====================================================================================================
-// one fixed-point iteration over the whole grid; the last block to finish folds the per-block partials in a fixed
-// order and publishes Kp / RKp for the next launch (iter 0 starts from Kp = 1)
-__global__ void __launch_bounds__(256) k_rescale_iter(KLSoA kl, MapState *st, double *__restrict__ part,
-                                                      unsigned int *ticket, double s_rho_min, unsigned int mnm,
-                                                      int iter, const int *enable) {
-    if (enable && !*enable) return;
-    __shared__ double sa[8], sb[8];
-    __shared__ double pa[256], pb[256];
-    __shared__ bool last;
-    const int kn = st->kn;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const double Kp = iter == 0 ? 1.0 : st->Kp;
-    const int i = blockIdx.x * 256 + tid;
-    double a = 0, b = 0;
-    if (i < kn) {
-        const double s0 = kl.s_rho0[i], s = kl.s_rho[i];
-        if (!((unsigned int)kl.m_num[i] < mnm || s0 <= 0 || s > s_rho_min)) {
-            const double r = kl.rho[i], r0 = kl.rho0[i];
-            const double den = s * s + Kp * Kp * s0 * s0;
-            a = r * r / den;
-            b = r0 * r0 / den;
-        }
-    }
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+#define MU_T 512
+#define MU_C 8
+#define MU_KJ 4   // keylines per thread whose rescaling operands stay in registers (kn <= MU_KJ*MU_C*MU_T = 16384)
+
+struct MapUpdArgs {
+    int do_reg, do_ekf, do_rescale, re_escale;
+    double reg_thresh;
+    const double *vel;       // EKF: translation of the frame (device)
+    double zf, q_abs, loc_unc;
+    double s_rho_min;        // rescaling
+    unsigned int mnm;
+    const int *enable;       // stage-level API: run only if *enable (nullptr = run)
+    FrameState *fs;          // pipeline: gate = match count (post-match glue folded in), tail = pose integration
+    int match_threshold;
+    const MapState *ost;
+    const LMState *lm;
+    rb_nav *nav;
+    const FrameArgs *fa;
+};
+
+__device__ __forceinline__ void mu_block_sum2(double &a, double &b, double (*sw)[2], int tid) {
+    const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         a += __shfl_xor_sync(0xffffffffu, a, o);
         b += __shfl_xor_sync(0xffffffffu, b, o);
     }
     if (lane == 0) {
-        sa[wid] = a;
-        sb[wid] = b;
+        sw[wid][0] = a;
+        sw[wid][1] = b;
     }
     __syncthreads();
-    if (tid == 0) {
-        double x = 0, y = 0;
-        for (int k = 0; k < 8; k++) {
-            x += sa[k];
-            y += sb[k];
-        }
-        part[2 * blockIdx.x] = x;
-        part[2 * blockIdx.x + 1] = y;
-        __threadfence();
-        last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    double x = 0, y = 0;
+#pragma unroll
+    for (int k = 0; k < MU_T / 32; k++) {
+        x += sw[k][0];
+        y += sw[k][1];
     }
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    const int nb = gridDim.x;   // <= 256
-    pa[tid] = tid < nb ? __ldcg(part + 2 * tid) : 0.0;
-    pb[tid] = tid < nb ? __ldcg(part + 2 * tid + 1) : 0.0;
-    __syncthreads();
-    if (tid == 0) {
-        double rTr = 0, rTr0 = 0;
-        for (int k = 0; k < nb; k++) {
-            rTr += pa[k];
-            rTr0 += pb[k];
-        }
-        if (kn <= 0) {
-            st->Kp = 1;   // "if(kn<=0) return 1;"
-        } else {
-            st->Kp = rTr0 > 0 ? sqrt(rTr / rTr0) : 1;
-            st->RKp = 1 / rTr0;
-        }
-        *ticket = 0;
-    }
-}
-__global__ void __launch_bounds__(256) k_rescale_apply(KLSoA kl, const MapState *st, const int *enable) {
-    if (enable && !*enable) return;
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= st->kn) return;
-    const double Kp = st->Kp;
-    kl.rho[i] = kl.rho[i] / Kp;
-    kl.s_rho[i] = kl.s_rho[i] / Kp;
+    a = x;
+    b = y;
+    __syncthreads();   // sw may be reused
 }
 
-// The same five fixed-point iterations in ONE launch: block b keeps its keylines' operands in registers; after every
-// iteration the blocks exchange their two partial sums through self-validating 8-byte slots (every block polls every
-// block: an all-gather, so each block gets the new Kp without a second hop) and reduce them in a fixed order.  The
-// optional tail (block 0) is the per-frame pipeline's pose integration / nav record, folded in to save its launch.
-// Needs all blocks that own keylines co-resident, like k_minimizer_persist; bounded spins.
-__global__ void __launch_bounds__(256) k_rescale_persist(KLSoA kl, MapState *st, unsigned long long *ll2, MinCtl *ctl,
-                                                         double s_rho_min, unsigned int mnm, int re_escale,
-                                                         const int *enable, FrameState *fs, const MapState *ost,
-                                                         const LMState *lm, rb_nav *nav, const FrameArgs *fa) {
-    __shared__ double sa[8], sb[8], ga[8], gb[8];
-    __shared__ int s_abort;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const bool en = !enable || *enable;
+__global__ void __cluster_dims__(MU_C, 1, 1) __launch_bounds__(MU_T) k_map_update(KLSoA kl, MapState *st,
+                                                                                  double *__restrict__ reg_r,
+                                                                                  double *__restrict__ reg_s,
+                                                                                  unsigned char *__restrict__ reg_set,
+                                                                                  MapUpdArgs a) {
+    pdl_wait();
+    pdl_launch();
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ double sw[MU_T / 32][2];
+    __shared__ double slots[2][MU_C][2];   // [iteration parity][rank][sum]
+    const int tid = threadIdx.x, rank = (int)cluster.block_rank();
     const int kn = st->kn;
-    const int n_act = (en && kn > 0) ? (kn + 255) / 256 : 1;
-    if ((int)blockIdx.x >= n_act) return;
+    bool en;
+    if (a.fs) {   // per-frame pipeline: "after directed_matching" gate (rebvo_second_t.cpp:410-423)
+        en = a.fs->do_match && st->nmatch >= a.match_threshold;
+        cluster.sync();   // every CTA has read the gate inputs before CTA 0 rewrites FrameState
+        if (rank == 0 && tid == 0) d_frame_post_match(a.fs, st, a.match_threshold);
+    } else {
+        en = !a.enable || *a.enable;
+    }
+    const int i0 = rank * MU_T + tid, stride = MU_C * MU_T;
     if (en) {
-        const unsigned int seq0 = __ldcg(&ctl->gen2);
-        if (tid == 0) s_abort = 0;
-        const int i = blockIdx.x * 256 + tid;
-        bool valid = false;
-        double rho = 0, s = 0, s0 = 0, r2 = 0, r02 = 0, s2 = 0;
-        if (i < kn) {
-            s0 = kl.s_rho0[i];
-            s = kl.s_rho[i];
-            rho = kl.rho[i];
-            if (!((unsigned int)kl.m_num[i] < mnm || s0 <= 0 || s > s_rho_min)) {
-                valid = true;
-                const double r0 = kl.rho0[i];
-                r2 = rho * rho;
-                r02 = r0 * r0;
-                s2 = s * s;
+        // ---- Regularize_1_iter, first half: needs every neighbour's (rho, s_rho) before anybody writes --------
+        if (a.do_reg) {
+            int cnt = 0;
+            for (int i = i0; i < kn; i += stride) cnt += d_reg_a(kl, i, reg_r, reg_s, reg_set, a.reg_thresh) ? 1 : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            if ((tid & 31) == 0 && cnt) atomicAdd(&st->reg_num, cnt);
+            cluster.sync();
+        }
+        // ---- write-back half + EKF: both only touch the thread's own keyline ------------------------------
+        if (a.do_reg || a.do_ekf) {
+            for (int i = i0; i < kn; i += stride) {
+                double rho, s_rho;
+                if (a.do_reg && reg_set[i]) {
+                    rho = reg_r[i];
+                    s_rho = reg_s[i];
+                    kl.rho[i] = rho;
+                    kl.s_rho[i] = s_rho;
+                } else {
+                    rho = kl.rho[i];
+                    s_rho = kl.s_rho[i];
+                }
+                if (a.do_ekf && kl.m_id[i] >= 0) d_ekf(kl, i, rho, s_rho, a.vel, a.zf, a.q_abs, a.loc_unc);
             }
         }
-        double Kp = 1.0, RKp = 0;
-        __syncthreads();
-        for (int iter = 0; iter < 5; iter++) {
-            const unsigned int seq = seq0 + 1u + (unsigned int)iter;
-            double a = 0, b = 0;
-            if (valid) {
-                const double den = s2 + Kp * Kp * s0 * s0;
-                a = r2 / den;
-                b = r02 / den;
-            }
+        // ---- EstimateReScalingOpt: 5 fixed-point iterations on Kp -----------------------------------------
+        if (a.do_rescale) {
+            bool valid[MU_KJ];
+            double r2[MU_KJ], r02[MU_KJ], s2[MU_KJ], s0v[MU_KJ];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                a += __shfl_xor_sync(0xffffffffu, a, o);
-                b += __shfl_xor_sync(0xffffffffu, b, o);
-            }
-            if (lane == 0) {
-                sa[wid] = a;
-                sb[wid] = b;
-            }
-            __syncthreads();
-            if (tid < 4) {
-                double x = 0;
-                const double *src = (tid < 2) ? sa : sb;
-                for (int k = 0; k < 8; k++) x += src[k];
-                const unsigned int w = (tid & 1) ? (unsigned int)__double2hiint(x) : (unsigned int)__double2loint(x);
-                st_volatile_u64(ll2 + (size_t)tid * 256 + blockIdx.x, ((unsigned long long)seq << 32) | w);
-            }
-            double pa = 0, pb = 0;
-            if (tid < n_act) {
-                const unsigned long long *src = ll2 + tid;
-                const long long t0 = clock64();
-                for (;;) {
-                    const unsigned long long w0 = ld_volatile_u64(src), w1 = ld_volatile_u64(src + 256);
-                    const unsigned long long w2 = ld_volatile_u64(src + 512), w3 = ld_volatile_u64(src + 768);
-                    if ((unsigned int)(w0 >> 32) == seq && (unsigned int)(w1 >> 32) == seq &&
-                        (unsigned int)(w2 >> 32) == seq && (unsigned int)(w3 >> 32) == seq) {
-                        pa = __hiloint2double((int)(unsigned int)w1, (int)(unsigned int)w0);
-                        pb = __hiloint2double((int)(unsigned int)w3, (int)(unsigned int)w2);
-                        break;
-                    }
-                    if (clock64() - t0 > MIN_SPIN_LIMIT) {
-                        s_abort = 1;
-                        break;
+            for (int j = 0; j < MU_KJ; j++) {
+                const int i = i0 + j * stride;
+                valid[j] = false;
+                r2[j] = r02[j] = s2[j] = s0v[j] = 0;
+                if (i < kn) {
+                    const double s0 = kl.s_rho0[i], s = kl.s_rho[i];
+                    if (!((unsigned int)kl.m_num[i] < a.mnm || s0 <= 0 || s > a.s_rho_min)) {
+                        const double r = kl.rho[i], r0 = kl.rho0[i];
+                        valid[j] = true;
+                        r2[j] = r * r;
+                        r02[j] = r0 * r0;
+                        s2[j] = s * s;
+                        s0v[j] = s0;
                     }
                 }
             }
+            double Kp = 1.0, RKp = 0;
+            for (int iter = 0; iter < 5; iter++) {
+                double sa = 0, sb = 0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                pa += __shfl_xor_sync(0xffffffffu, pa, o);
-                pb += __shfl_xor_sync(0xffffffffu, pb, o);
-            }
-            if (lane == 0) {
-                ga[wid] = pa;
-                gb[wid] = pb;
-            }
-            __syncthreads();
-            double rTr = 0, rTr0 = 0;
+                for (int j = 0; j < MU_KJ; j++)
+                    if (valid[j]) {
+                        const double den = s2[j] + Kp * Kp * s0v[j] * s0v[j];
+                        sa += r2[j] / den;
+                        sb += r02[j] / den;
+                    }
+                for (int i = i0 + MU_KJ * stride; i < kn; i += stride) {   // maps beyond the register window
+                    const double s0 = kl.s_rho0[i], s = kl.s_rho[i];
+                    if (!((unsigned int)kl.m_num[i] < a.mnm || s0 <= 0 || s > a.s_rho_min)) {
+                        const double r = kl.rho[i], r0 = kl.rho0[i];
+                        const double den = s * s + Kp * Kp * s0 * s0;
+                        sa += r * r / den;
+                        sb += r0 * r0 / den;
+                    }
+                }
+                mu_block_sum2(sa, sb, sw, tid);
+                if (tid < MU_C) {   // this CTA's pair into every CTA's table
+                    double *dst = cluster.map_shared_rank(&slots[iter & 1][rank][0], tid);
+                    dst[0] = sa;
+                    dst[1] = sb;
+                }
+                cluster.sync();
+                double rTr = 0, rTr0 = 0;
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                rTr += ga[k];
-                rTr0 += gb[k];
+                for (int k = 0; k < MU_C; k++) {
+                    rTr += slots[iter & 1][k][0];
+                    rTr0 += slots[iter & 1][k][1];
+                }
+                if (kn > 0) {   // "if(kn<=0) return 1;"
+                    Kp = rTr0 > 0 ? sqrt(rTr / rTr0) : 1;
+                    RKp = 1 / rTr0;
+                }
             }
-            if (kn > 0) {
-                Kp = rTr0 > 0 ? sqrt(rTr / rTr0) : 1;
-                RKp = 1 / rTr0;
+            if (a.re_escale)
+                for (int i = i0; i < kn; i += stride) {
+                    kl.rho[i] = kl.rho[i] / Kp;
+                    kl.s_rho[i] = kl.s_rho[i] / Kp;
+                }
+            if (rank == 0 && tid == 0) {
+                st->Kp = Kp;
+                if (kn > 0) st->RKp = RKp;
             }
-            if (s_abort) break;
-        }
-        if (s_abort) Kp = __longlong_as_double(0x7FF8000000000000ll);
-        if (re_escale && i < kn) {
-            kl.rho[i] = rho / Kp;
-            kl.s_rho[i] = s / Kp;
-        }
-        if (blockIdx.x == 0 && tid == 0) {
-            st->Kp = Kp;              // "if(kn<=0) return 1;" leaves RKp alone
-            if (kn > 0) st->RKp = RKp;
-            ctl->gen2 = seq0 + 8u;
-            if (s_abort) ctl->abort = 1;
         }
     }
-    if (fs && blockIdx.x == 0 && tid == 0) d_frame_finish(fs, st, ost, lm->score, nav, fa);
+    cluster.sync();   // no CTA may exit while a peer can still store into its shared memory
+    if (a.fs && a.nav && rank == 0 && tid == 0) d_frame_finish(a.fs, st, a.ost, a.lm->score, a.nav, a.fa);
 }
 
-int rb_rescale_enqueue(rb_ctx *c, rb_map *m, double s_rho_min, unsigned int match_num_min, int re_escale,
-                       const int *enable_dev, FrameState *fs, const MapState *ost, rb_nav *nav, const FrameArgs *fa,
-                       bool *finish_folded) {
-    const int nb = m->ts_host.nblk;
-    if (finish_folded) *finish_folded = false;
-    if (c->min_persist && nb <= c->min_resident && nb <= 256) {
-        k_rescale_persist<<<nb, 256, 0, c->stream>>>(m->kl, m->st, m->ts_host.ll2, m->ts_host.ctl, s_rho_min,
-                                                     match_num_min, re_escale, enable_dev, fs, ost, &m->ts->lm, nav, fa);
-        RB_LAUNCH_CHECK();
-        if (finish_folded) *finish_folded = fs != nullptr;
-        return RB_OK;
-    }
-    for (int iter = 0; iter < 5; iter++) {
-        k_rescale_iter<<<nb, 256, 0, c->stream>>>(m->kl, m->st, m->ts_host.partials, c->ticket + 3, s_rho_min,
-                                                  match_num_min, iter, enable_dev);
-        RB_LAUNCH_CHECK();
-    }
-    if (re_escale) {
-        k_rescale_apply<<<nb, 256, 0, c->stream>>>(m->kl, m->st, enable_dev);
-        RB_LAUNCH_CHECK();
-    }
+static int launch_map_update(rb_ctx *c, rb_map *m, const MapUpdArgs &a) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(MU_C);
+    cfg.blockDim = dim3(MU_T);
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = c->pdl ? 1 : 0;
+    TrackState &t = m->ts_host;
+    c->launches++;
+    RB_CUDA(cudaLaunchKernelEx(&cfg, k_map_update, m->kl, m->st, t.reg_r, t.reg_s, t.reg_set, a));
     return RB_OK;
+}
+
+// the pipeline's whole map update (gate, smoothing, EKF, rescaling, pose integration / nav record)
+int rb_map_update_enqueue(rb_ctx *c, rb_map *m, double reg_thresh, const double *vel_dev, double q_abs, double loc_unc,
+                          double s_rho_min, unsigned int match_num_min, int re_escale, FrameState *fs,
+                          int match_threshold, const MapState *ost, rb_nav *nav, const FrameArgs *fa) {
+    MapUpdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.do_reg = a.do_ekf = a.do_rescale = 1;
+    a.re_escale = re_escale;
+    a.reg_thresh = reg_thresh;
+    a.vel = vel_dev;
+    a.zf = c->zfm;
+    a.q_abs = q_abs;
+    a.loc_unc = loc_unc;
+    a.s_rho_min = s_rho_min;
+    a.mnm = match_num_min;
+    a.fs = fs;
+    a.match_threshold = match_threshold;
+    a.ost = ost;
+    a.lm = &m->ts->lm;
+    a.nav = nav;
+    a.fa = fa;
+    return launch_map_update(c, m, a);
+}
+
+// EstimateReScalingOpt alone (stage-level API): the same kernel with only its last phase, hence the same bits
+int rb_rescale_enqueue(rb_ctx *c, rb_map *m, double s_rho_min, unsigned int match_num_min, int re_escale,
+                       const int *enable_dev) {
+    MapUpdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.do_rescale = 1;
+    a.re_escale = re_escale;
+    a.s_rho_min = s_rho_min;
+    a.mnm = match_num_min;
+    a.enable = enable_dev;
+    return launch_map_update(c, m, a);
 }

@@ -59,12 +59,13 @@ int rb_directed_matching_enqueue(rb_ctx *c, rb_map *neu, rb_map *old, const DMat
                                  double min_thr_mod, double min_thr_ang, double max_radius,
                                  double loc_uncertainty, const int *enable_dev);
 int rb_regularize_enqueue(rb_ctx *c, rb_map *m, double thresh, const int *enable_dev);
-int rb_regularize_a_enqueue(rb_ctx *c, rb_map *m, double thresh, FrameState *fs, int match_threshold);
-int rb_regb_ekf_enqueue(rb_ctx *c, rb_map *m, const double *vel_dev, double q_abs, double loc_unc,
-                        const int *enable_dev);
+struct rb_nav;
+int rb_map_update_enqueue(rb_ctx *c, rb_map *m, double reg_thresh, const double *vel_dev, double q_abs,
+                          double loc_unc, double s_rho_min, unsigned int match_num_min, int re_escale,
+                          FrameState *fs, int match_threshold, const MapState *ost, rb_nav *nav,
+                          const FrameArgs *fa);
 int rb_ekf_enqueue(rb_ctx *c, rb_map *m, const double *vel_dev, double q_abs, double loc_unc,
                    const int *enable_dev);
 int rb_rescale_enqueue(rb_ctx *c, rb_map *m, double s_rho_min, unsigned int match_num_min, int re_escale,
-                       const int *enable_dev, FrameState *fs = nullptr, const MapState *ost = nullptr,
-                       rb_nav *nav = nullptr, const FrameArgs *fa = nullptr, bool *finish_folded = nullptr);
+                       const int *enable_dev);
 int rb_read_map_state(rb_map *m, MapState *host);
