@@ -302,7 +302,6 @@ static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, const FrameArg
     }
     // :354  FordwardMatch ; :369 rotate_keylines(R0)
     if ((r = rb_forward_match_enqueue(c, old, neu, pl->overlap))) return r;
-    RB_TRACE(c->stream, 10);
     if ((r = rb_rotate_enqueue(c, old, pl->fs->R0))) return r;
     RB_TRACE(c->stream, 11);
     prof_mark(pl, ST_FWD_ROT);
@@ -312,8 +311,12 @@ static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, const FrameArg
         return r;
     RB_TRACE(c->stream, 4);
     prof_mark(pl, ST_DMATCH);
-    // :410-423 match-count gate, :452-487 Regularize_1_iter / UpdateInverseDepthKalman / EstimateReScalingOpt and
-    // :545-585 pose integration + NavData: one cluster kernel (tracker.cu, k_map_update)
+    // :410-423 match-count gate + :452-470 Regularize_1_iter / UpdateInverseDepthKalman on wide grids, then
+    // :480-487 EstimateReScalingOpt and :545-585 pose integration + NavData in one cluster kernel (k_map_update)
+    if ((r = rb_regularize_ekf_enqueue(c, neu, p.RegularizeThresh, pl->fs, p.MatchThreshold, pl->fs->V,
+                                       p.ReshapeQAbsolute, p.LocationUncertainty, &pl->fs->do_map)))
+        return r;
+    RB_TRACE(c->stream, 9);
     if ((r = rb_map_update_enqueue(c, neu, p.RegularizeThresh, pl->fs->V, p.ReshapeQAbsolute, p.LocationUncertainty,
                                    RB_RHO_MAX, 1, p.DoReScaling > 0 ? 1 : 0, pl->fs, p.MatchThreshold, old->st,
                                    nav_slot, fa)))

@@ -1404,15 +1404,36 @@ __global__ void __launch_bounds__(256) k_fm_init(unsigned long long *best, int *
     best[i] = 0ull;
     idx[i] = -1;
 }
+__device__ __forceinline__ void d_fm_pass1(const KLSoA &old, int i, int nkn, unsigned long long *best) {
+    const int f = old.m_id_f[i];
+    if (f < 0 || f >= nkn) return;
+    atomicMax(&best[f], dbl_key(old.rho[i]));
+}
+__device__ __forceinline__ void d_fm_pass2(const KLSoA &old, int i, int nkn, const unsigned long long *best,
+                                           int *idx) {
+    const int f = old.m_id_f[i];
+    if (f < 0 || f >= nkn) return;
+    if (dbl_key(old.rho[i]) == __ldcg(&best[f])) atomicMax(&idx[f], i);
+}
+__device__ __forceinline__ bool d_fm_apply(const KLSoA &old, const KLSoA &neu, int f, const int *idx) {
+    const int i = __ldcg(&idx[f]);
+    if (i < 0) return false;
+    neu.rho[f] = old.rho[i];
+    neu.s_rho[f] = old.s_rho[i];
+    neu.m_num[f] = old.m_num[i] + 1;
+    neu.m_id[f] = i;
+    neu.p_m_0[f] = old.p_m[i];
+    neu.m_m0[f] = old.m_m[i];
+    neu.n_m0[f] = (double)old.n_m[i];
+    return true;
+}
 __global__ void __launch_bounds__(256) k_fm_pass1(KLSoA old, const MapState *ost, const MapState *nst,
                                                   unsigned long long *best) {
     pdl_wait();
     pdl_launch();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ost->kn) return;
-    const int f = old.m_id_f[i];
-    if (f < 0 || f >= nst->kn) return;
-    atomicMax(&best[f], dbl_key(old.rho[i]));
+    d_fm_pass1(old, i, nst->kn, best);
 }
 __global__ void __launch_bounds__(256) k_fm_pass2(KLSoA old, const MapState *ost, const MapState *nst,
                                                   const unsigned long long *best, int *idx) {
@@ -1420,26 +1441,14 @@ __global__ void __launch_bounds__(256) k_fm_pass2(KLSoA old, const MapState *ost
     pdl_launch();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ost->kn) return;
-    const int f = old.m_id_f[i];
-    if (f < 0 || f >= nst->kn) return;
-    if (dbl_key(old.rho[i]) == best[f]) atomicMax(&idx[f], i);
+    d_fm_pass2(old, i, nst->kn, best, idx);
 }
 __global__ void __launch_bounds__(256) k_fm_apply(KLSoA old, KLSoA neu, MapState *nst, const int *idx) {
     pdl_wait();
     pdl_launch();
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = f < nst->kn;
-    int i = valid ? idx[f] : -1;
-    if (i >= 0) {
-        neu.rho[f] = old.rho[i];
-        neu.s_rho[f] = old.s_rho[i];
-        neu.m_num[f] = old.m_num[i] + 1;
-        neu.m_id[f] = i;
-        neu.p_m_0[f] = old.p_m[i];
-        neu.m_m0[f] = old.m_m[i];
-        neu.n_m0[f] = (double)old.n_m[i];
-    }
-    const unsigned int bal = __ballot_sync(0xffffffffu, i >= 0);
+    const bool hit = f < nst->kn ? d_fm_apply(old, neu, f, idx) : false;
+    const unsigned int bal = __ballot_sync(0xffffffffu, hit);
     if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&nst->fwd_match, __popc(bal));
 }
 __global__ void k_set_int(int *p, int v) { *p = v; }
@@ -1461,21 +1470,17 @@ int rb_forward_match_enqueue(rb_ctx *c, rb_map *old, rb_map *neu, bool scratch_r
         int r = rb_forward_match_init_enqueue(c, neu);
         if (r) return r;
     }
-    RB_KLAUNCH(k_fm_pass1, nb, 256, 0, old->kl, old->st, neu->st, t.fm_best);
-    RB_KLAUNCH(k_fm_pass2, nb, 256, 0, old->kl, old->st, neu->st, t.fm_best, t.fm_idx);
-    RB_KLAUNCH(k_fm_apply, nb, 256, 0, old->kl, neu->kl, neu->st, t.fm_idx);
+    RB_KLAUNCH(k_fm_pass1, nb, 256, 0, old->kl, (const MapState *)old->st, (const MapState *)neu->st, t.fm_best);
+    RB_KLAUNCH(k_fm_pass2, nb, 256, 0, old->kl, (const MapState *)old->st, (const MapState *)neu->st,
+               (const unsigned long long *)t.fm_best, t.fm_idx);
+    RB_KLAUNCH(k_fm_apply, nb, 256, 0, old->kl, neu->kl, neu->st, (const int *)t.fm_idx);
     return RB_OK;
 }
 
 // =====================================================================================================
 // rotate_keylines (edge_tracker.cpp:42-76)
 // =====================================================================================================
-__global__ void __launch_bounds__(256) k_rotate(KLSoA kl, const MapState *st, const double *__restrict__ Rp,
-                                                double zf) {
-    pdl_wait();
-    pdl_launch();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= st->kn) return;
+__device__ __forceinline__ void d_rotate(const KLSoA &kl, int i, const double *__restrict__ Rp, double zf) {
     double R[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) R[k] = Rp[k];
@@ -1502,9 +1507,17 @@ __global__ void __launch_bounds__(256) k_rotate(KLSoA kl, const MapState *st, co
     p.y = mr.y;
     kl.pack[2 * i] = p;
 }
+__global__ void __launch_bounds__(256) k_rotate(KLSoA kl, const MapState *st, const double *__restrict__ Rp,
+                                                double zf) {
+    pdl_wait();
+    pdl_launch();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st->kn) return;
+    d_rotate(kl, i, Rp, zf);
+}
 
 int rb_rotate_enqueue(rb_ctx *c, rb_map *m, const double *R_dev) {
-    RB_KLAUNCH(k_rotate, rb_div_up(c->kcap, 256), 256, 0, m->kl, m->st, R_dev, c->zfm);
+    RB_KLAUNCH(k_rotate, rb_div_up(c->kcap, 256), 256, 0, m->kl, (const MapState *)m->st, R_dev, c->zfm);
     return RB_OK;
 }
 
@@ -1752,6 +1765,57 @@ int rb_ekf_enqueue(rb_ctx *c, rb_map *m, const double *vel_dev, double q_abs, do
     return RB_OK;
 }
 
+// pipeline variants (wide grids: these two stages are FP64-heavy per keyline and want every SM):
+// first half of Regularize_1_iter with the "after directed_matching" gate folded in (block 0 publishes it) ...
+__global__ void __launch_bounds__(256) k_regularize_a_gate(KLSoA kl, MapState *st, double *__restrict__ r,
+                                                           double *__restrict__ s, unsigned char *__restrict__ set,
+                                                           double thresh, FrameState *fs, int match_threshold) {
+    pdl_wait();
+    pdl_launch();
+    const bool en = fs->do_match && st->nmatch >= match_threshold;
+    if (blockIdx.x == 0 && threadIdx.x == 0) d_frame_post_match(fs, st, match_threshold);
+    if (!en) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool did = i < st->kn ? d_reg_a(kl, i, r, s, set, thresh) : false;
+    const unsigned int bal = __ballot_sync(0xffffffffu, did);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&st->reg_num, __popc(bal));
+}
+// ... and its write-back half + UpdateInverseDepthKalman in one pass: both only touch the thread's own keyline, so
+// the EKF takes the regularised (rho, s_rho) straight from registers
+__global__ void __launch_bounds__(256) k_regb_ekf(KLSoA kl, const MapState *st, const double *__restrict__ r,
+                                                  const double *__restrict__ s,
+                                                  const unsigned char *__restrict__ set,
+                                                  const double *__restrict__ velp, double zf, double q_abs,
+                                                  double loc_unc, const int *enable) {
+    pdl_wait();
+    pdl_launch();
+    if (enable && !*enable) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st->kn) return;
+    double rho, s_rho;
+    if (set[i]) {
+        rho = r[i];
+        s_rho = s[i];
+        kl.rho[i] = rho;
+        kl.s_rho[i] = s_rho;
+    } else {
+        rho = kl.rho[i];
+        s_rho = kl.s_rho[i];
+    }
+    if (kl.m_id[i] < 0) return;
+    d_ekf(kl, i, rho, s_rho, velp, zf, q_abs, loc_unc);
+}
+int rb_regularize_ekf_enqueue(rb_ctx *c, rb_map *m, double thresh, FrameState *fs, int match_threshold,
+                              const double *vel_dev, double q_abs, double loc_unc, const int *do_map_dev) {
+    TrackState &t = m->ts_host;
+    const int nb = rb_div_up(c->kcap, 256);
+    RB_KLAUNCH(k_regularize_a_gate, nb, 256, 0, m->kl, m->st, t.reg_r, t.reg_s, t.reg_set, thresh, fs, match_threshold);
+    RB_KLAUNCH(k_regb_ekf, nb, 256, 0, m->kl, (const MapState *)m->st, (const double *)t.reg_r, (const double *)t.reg_s,
+               (const unsigned char *)t.reg_set, vel_dev, c->zfm, q_abs, loc_unc, do_map_dev);
+    return RB_OK;
+}
+
+
 
 // =====================================================================================================
 // Map update of a frame in ONE thread-block cluster: Regularize_1_iter (edge_tracker.cpp:87-148),
@@ -1774,7 +1838,7 @@ namespace cg = cooperative_groups;
 #define MU_KJ 4   // keylines per thread whose rescaling operands stay in registers (kn <= MU_KJ*MU_C*MU_T = 16384)
 
 struct MapUpdArgs {
-    int do_reg, do_ekf, do_rescale, re_escale;
+    int do_reg, do_ekf, do_rescale, re_escale, gate_post_match;
     double reg_thresh;
     const double *vel;       // EKF: translation of the frame (device)
     double zf, q_abs, loc_unc;
@@ -1825,7 +1889,7 @@ __global__ void __cluster_dims__(MU_C, 1, 1) __launch_bounds__(MU_T) k_map_updat
     const int tid = threadIdx.x, rank = (int)cluster.block_rank();
     const int kn = st->kn;
     bool en;
-    if (a.fs) {   // per-frame pipeline: "after directed_matching" gate (rebvo_second_t.cpp:410-423)
+    if (a.fs && a.gate_post_match) {   // "after directed_matching" gate (rebvo_second_t.cpp:410-423) folded in
         en = a.fs->do_match && st->nmatch >= a.match_threshold;
         cluster.sync();   // every CTA has read the gate inputs before CTA 0 rewrites FrameState
         if (rank == 0 && tid == 0) d_frame_post_match(a.fs, st, a.match_threshold);
@@ -1885,10 +1949,11 @@ __global__ void __cluster_dims__(MU_C, 1, 1) __launch_bounds__(MU_T) k_map_updat
                 double sa = 0, sb = 0;
 #pragma unroll
                 for (int j = 0; j < MU_KJ; j++)
-                    if (valid[j]) {
+                    if (valid[j]) {   // r*r/den and r0*r0/den through one reciprocal (div_with_rcp == IEEE division)
                         const double den = s2[j] + Kp * Kp * s0v[j] * s0v[j];
-                        sa += r2[j] / den;
-                        sb += r02[j] / den;
+                        const double iden = 1 / den;
+                        sa += div_with_rcp(r2[j], den, iden);
+                        sb += div_with_rcp(r02[j], den, iden);
                     }
                 for (int i = i0 + MU_KJ * stride; i < kn; i += stride) {   // maps beyond the register window
                     const double s0 = kl.s_rho0[i], s = kl.s_rho[i];
@@ -1955,7 +2020,8 @@ int rb_map_update_enqueue(rb_ctx *c, rb_map *m, double reg_thresh, const double 
                           int match_threshold, const MapState *ost, rb_nav *nav, const FrameArgs *fa) {
     MapUpdArgs a;
     memset(&a, 0, sizeof(a));
-    a.do_reg = a.do_ekf = a.do_rescale = 1;
+    a.do_reg = a.do_ekf = 0;   // the pipeline runs those two on wide grids (rb_regularize_ekf_enqueue)
+    a.do_rescale = 1;
     a.re_escale = re_escale;
     a.reg_thresh = reg_thresh;
     a.vel = vel_dev;
@@ -1965,6 +2031,8 @@ int rb_map_update_enqueue(rb_ctx *c, rb_map *m, double reg_thresh, const double 
     a.s_rho_min = s_rho_min;
     a.mnm = match_num_min;
     a.fs = fs;
+    a.enable = &fs->do_map;   // published by k_regularize_a_gate
+    a.gate_post_match = 0;
     a.match_threshold = match_threshold;
     a.ost = ost;
     a.lm = &m->ts->lm;

@@ -60,6 +60,8 @@ int rb_directed_matching_enqueue(rb_ctx *c, rb_map *neu, rb_map *old, const DMat
                                  double loc_uncertainty, const int *enable_dev);
 int rb_regularize_enqueue(rb_ctx *c, rb_map *m, double thresh, const int *enable_dev);
 struct rb_nav;
+int rb_regularize_ekf_enqueue(rb_ctx *c, rb_map *m, double thresh, FrameState *fs, int match_threshold,
+                              const double *vel_dev, double q_abs, double loc_unc, const int *do_map_dev);
 int rb_map_update_enqueue(rb_ctx *c, rb_map *m, double reg_thresh, const double *vel_dev, double q_abs,
                           double loc_unc, double s_rho_min, unsigned int match_num_min, int re_escale,
                           FrameState *fs, int match_threshold, const MapState *ost, rb_nav *nav,
