@@ -99,6 +99,11 @@ class ClockSampler:
             self.p.terminate()
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+# (profiles/r1_summary.md section 3, 64-frame batch = the default bench batch)
+TRAFFIC = {"k_rowscan_ring<avg>": 3.19e8}   # 307-331 MB over the two launches of a 64-frame batch
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -225,6 +230,18 @@ def bench_ours(args):
     t_e2e_ms = pl2.event_elapsed(0, 1)
     nav_e2e = np.concatenate(navs2)
     pl2.close()
+    # ---------------- where the step goes: in-situ stage profile (eager launches, one stream, CUDA events) ---------
+    stage_us = None
+    if rank == 0:
+        os.environ["REBVO_B200_STAGE_PROF"] = "1"
+        try:
+            pl3 = capi.Pipeline(params, max_batch=B, device=dev)
+            for s in range(3):
+                pl3.push_dev(devbuf[s * B].data_ptr(), ts[s * B:(s + 1) * B])
+            stage_us, _ = pl3.stage_profile()
+            pl3.close()
+        finally:
+            del os.environ["REBVO_B200_STAGE_PROF"]
     sampler.stop()
     clocks = sampler.summary(c0, c1)
     same = bool(np.array_equal(nav_dev["Pos"], nav_e2e["Pos"]))
@@ -237,11 +254,23 @@ def bench_ours(args):
     value = multi.aggregate_fps(K * B, world, t_max)
     e2e = multi.aggregate_fps(K * B, world, t_e2e_max)
     peak, peak_src = peaks()
+    # launches of each scale-space pass in one step (rb_dog_build_batch: gray, one plain row pass and one column pass over
+    # B images, then per box stage an averaged row pass + a column pass over 2B images, then the blur/DoG pass); the
+    # timed column pass is the 2B-image one, the B-image one counts half
+    per_step = {"k_rgb2gray": 1, rs + "<plain>": 1, rs + "<avg>": 2, "k_colscan": 2.5, "k_blur_dog": 1}
+    dog_ms = sum(passes[k]["ms_per_launch"] * n for k, n in per_step.items())
     dom = rs + "<avg>"
     roof = {"bound": "hbm", "kernel": dom, "achieved": passes[dom]["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": passes[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+            "frac": passes[dom]["gbs"] / peak, "traffic": TRAFFIC.get(dom), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": passes[dom]["bytes_per_launch"],
-            "ms_per_launch": passes[dom]["ms_per_launch"], "all_passes": passes}
+            "ms_per_launch": passes[dom]["ms_per_launch"], "all_passes": passes,
+            "note": "roofline of the kernel that moves the most bytes (the batched scale space carries >95% of a step's "
+                    "HBM traffic). By TIME the step is dominated by k_minimizer_persist, a latency-bound kernel (12 "
+                    "dependent grid-wide reductions per frame over ~1.6 MB of keyline data): see time_dominant and "
+                    "DESIGN.md section 4.",
+            "scale_space_share_of_step": dog_ms / (t_max / K) if t_max > 0 else None,
+            "time_dominant": {"kernel": "k_minimizer_persist", "bound": "latency (L2 round trips between dependent "
+                              "evaluations)", "stage_us_per_frame_eager": stage_us}}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:

@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(64) k_colscan(const float4 *__restrict__ in, f
 }
 
 // Last box of both filters + sspace::build_dog (sspace.cpp:63-70): img0, dog = img1 - img0
+#define BLUR_RY 8
 __global__ void __launch_bounds__(256) k_blur_dog(const float *__restrict__ I, float *__restrict__ img0,
                                                   float *__restrict__ dog, float *__restrict__ img1_opt,
                                                   int w, int h, int B, int d0, int d1,
@@ -170,16 +171,30 @@ __global__ void __launch_bounds__(256) k_blur_dog(const float *__restrict__ I, f
     else if (threadIdx.x < 2 * BOX_TAB_N) st1[threadIdx.x - BOX_TAB_N] = tab1[threadIdx.x - BOX_TAB_N];
     __syncthreads();
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
+    const int y0 = blockIdx.y * BLUR_RY;
     const int b = blockIdx.z;
     if (x >= w) return;
     const size_t N = (size_t)w * h;
-    const float v0 = box_avg(I + (size_t)b * N, x, y, w, h, d0, d0 / 2, st0);
-    const float v1 = box_avg(I + (size_t)(B + b) * N, x, y, w, h, d1, d1 / 2, st1);
-    const size_t o = (size_t)b * N + (size_t)y * w + x;
-    img0[o] = v0;
-    dog[o] = v1 - v0;
-    if (img1_opt) img1_opt[(size_t)y * w + x] = v1;
+    const float *I0 = I + (size_t)b * N, *I1 = I + (size_t)(B + b) * N;
+    // BLUR_RY rows per thread, unrolled: 8 x BLUR_RY independent taps in flight per thread (one row per thread left
+    // the pass latency-bound: 92k tiny blocks, each paying the table load and a barrier for 8 loads per thread)
+    float v0[BLUR_RY], v1[BLUR_RY];
+#pragma unroll
+    for (int r = 0; r < BLUR_RY; r++) {
+        const int y = min(y0 + r, h - 1);
+        v0[r] = box_avg(I0, x, y, w, h, d0, d0 / 2, st0);
+        v1[r] = box_avg(I1, x, y, w, h, d1, d1 / 2, st1);
+    }
+#pragma unroll
+    for (int r = 0; r < BLUR_RY; r++) {
+        const int y = y0 + r;
+        if (y < h) {
+            const size_t o = (size_t)b * N + (size_t)y * w + x;
+            img0[o] = v0[r];
+            dog[o] = v1[r] - v0[r];
+            if (img1_opt) img1_opt[(size_t)y * w + x] = v1[r];
+        }
+    }
 }
 
 // sspace::calc_gradient (sspace.cpp:75-85), materialised only for the debug accessor; borders = 0
@@ -421,7 +436,7 @@ static int rowscan(rb_ctx *c, int stage, const float *in, float *out, int nimg, 
 }
 
 static int blur_dog(rb_ctx *c, DogWS *ws, int nimg, float *img1_opt, int out_slot = 0) {
-    dim3 grid(rb_div_up(c->w, 256), c->h, nimg);
+    dim3 grid(rb_div_up(c->w, 256), rb_div_up(c->h, BLUR_RY), nimg);
     const size_t off = (size_t)out_slot * c->N;
     k_blur_dog<<<grid, 256, 0, c->stream>>>(ws->I, ws->img0 + off, ws->dog + off, img1_opt, c->w, c->h, nimg,
                                             c->plan.d[0][2],
