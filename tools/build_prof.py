@@ -1,0 +1,14 @@
+"""Build the profiling variant of the library (-DRB_TVR_PROF: clock64 stamps in the minimiser, %globaltimer marker kernels
+in the pipeline) into tools/_prof/ (git-ignored).  Used by minimiser_stamps.py and trace_run.py on a GPU box."""
+import os, subprocess, sys
+sys.path.insert(0, '/root/repo')
+from rebvo_b200 import build as B
+out = '/root/repo/tools/_prof'
+os.makedirs(out, exist_ok=True)
+objs = []
+for s in B.SOURCES:
+    o = os.path.join(out, s.replace('.cu', '.o'))
+    subprocess.check_call([B.NVCC] + B.FLAGS + ['-DRB_TVR_PROF', '-c', os.path.join(B.CSRC, s), '-o', o])
+    objs.append(o)
+subprocess.check_call([B.NVCC, '-shared', '-o', os.path.join(out, 'librebvo_b200_dbg.so')] + objs + ['-lcudart'])
+print('ok')

@@ -1,0 +1,24 @@
+import os, sys, ctypes as C
+import numpy as np
+sys.path.insert(0, '/root/repo')
+os.environ["REBVO_B200_NO_GRAPH"] = "1"
+from rebvo_b200 import capi, synth
+capi.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_prof', 'librebvo_b200_dbg.so')
+cam = synth.EUROC
+seq = synth.Sequence(w=cam["w"], h=cam["h"], seed=7, zf=cam["zfx"])
+ts, fr = seq.frames(8)
+pl = capi.Pipeline(capi.default_params(cam), max_batch=8)
+nav = pl.push(fr, ts)
+print('kn', nav['kn'], 'pos', nav['Pos'][-1])
+dbg = np.zeros(256 * 16, np.int64)
+L = capi.lib()
+print('fetch rc', L.rb_debug_fetch(dbg.ctypes.data_as(C.c_void_p)))
+d = dbg.reshape(256, 16)
+print('n_act', int(d[255, 15]))
+names = ['exp', 'body', 'tail+ll', 'gather', 'carries', 'reduce', 'lm_step', 'epilogue']
+for b in (0, 1, 30, 58):
+    row = d[b]
+    print('block', b, ' '.join('%s=%d' % (names[k], row[k + 1] - row[k]) for k in range(0, 8) if row[k + 1] and row[k] and row[k + 1] > row[k]))
+print('flag wait max per block (cycles):', [int(d[b][10]) for b in (0,1,30,58)], 'own flag wait', [int(d[b][11]) for b in (0,1,30,58)], 'payload done rel stamp3', [int(d[b][12]-d[b][3]) for b in (0,1,30,58)])
+print('stamp3 skew across blocks', int(max(d[b][3] for b in range(65)) - min(d[b][3] for b in range(65))), 'stamp0 skew', int(max(d[b][0] for b in range(65)) - min(d[b][0] for b in range(65))))
+print('master last eval total', d[0][7] - d[0][0])
