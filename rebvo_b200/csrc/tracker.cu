@@ -1003,15 +1003,15 @@ struct MinSetup {
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
     unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int *p) {
     unsigned int v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
