@@ -226,7 +226,7 @@ static inline cudaError_t rb_klaunch(bool pdl, void (*kernel)(KArgs...), dim3 gr
 // dog.cu
 int rb_dogws_alloc(rb_ctx *c, DogWS *ws, int B);
 void rb_dogws_free(DogWS *ws);
-int rb_dog_gray(rb_ctx *c, DogWS *ws, int nimg);                 // rgb -> gray
+int rb_dog_gray(rb_ctx *c, DogWS *ws, int nimg, const void *const *src_pp = nullptr);   // rgb -> gray
 int rb_dog_build_batch(rb_ctx *c, DogWS *ws, int nimg);          // gray -> img0, dog
 int rb_dog_aux_planes(rb_ctx *c, DogWS *ws, int img);            // Img(1), dx, dy into ws->aux
 int rb_dog_make_tables(rb_ctx *c);

@@ -49,10 +49,14 @@ __device__ __forceinline__ float box_avg(const float *__restrict__ I, int x, int
 }
 
 // Image<float>::ConvertRGB2BW (image.h:197-203): b+g+r as float, 4 pixels per thread
-__global__ void __launch_bounds__(256) k_rgb2gray(const uint32_t *__restrict__ rgb,
+// src_pp (optional): the RGB source is read through a device-resident pointer, so that one captured graph serves
+// whichever staging region / caller buffer a push uses (rb_pipeline)
+__global__ void __launch_bounds__(256) k_rgb2gray(const uint32_t *__restrict__ rgb_fixed,
+                                                  const uint32_t *const *__restrict__ src_pp,
                                                   float4 *__restrict__ gray, size_t n4) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
+    const uint32_t *__restrict__ rgb = src_pp ? *src_pp : rgb_fixed;
     uint32_t a = rgb[3 * i], b = rgb[3 * i + 1], c = rgb[3 * i + 2];
     // bytes: a = p0.0 p0.1 p0.2 p1.0 | b = p1.1 p1.2 p2.0 p2.1 | c = p2.2 p3.0 p3.1 p3.2
     float4 o;
@@ -240,9 +244,10 @@ void rb_dogws_free(DogWS *ws) {
     memset(ws, 0, sizeof(*ws));
 }
 
-int rb_dog_gray(rb_ctx *c, DogWS *ws, int nimg) {
+int rb_dog_gray(rb_ctx *c, DogWS *ws, int nimg, const void *const *src_pp) {
     const size_t n4 = (size_t)nimg * c->N / 4;
     k_rgb2gray<<<(unsigned)((n4 + 255) / 256), 256, 0, c->stream>>>((const uint32_t *)ws->rgb,
+                                                                   (const uint32_t *const *)src_pp,
                                                                    (float4 *)ws->gray, n4);
     RB_LAUNCH_CHECK();
     return RB_OK;

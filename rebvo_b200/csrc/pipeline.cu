@@ -51,6 +51,13 @@ struct rb_pipeline {
     cudaStream_t det_stream;
     cudaEvent_t ev_dog, *ev_det, *ev_trk;
     bool overlap;
+    // host-input pushes are cut into a short head and the rest: the H2D copy of the rest (copy stream) runs beside the
+    // kernels of the head.  The gray kernel reads its RGB source through rgb_src_dev, so one graph serves every region.
+    cudaStream_t copy_stream;
+    cudaEvent_t *ev_copy;
+    const void **rgb_src_dev;     // device: pointer to the RGB24 frames of the sub-batch being processed
+    const void **rgb_src_pin;     // pinned: one pointer per sub-batch of the current push
+    int sub;                      // head sub-batch of a host-input push (env REBVO_B200_SUB, default 8 frames)
     DetChain *chain;      // device
     FrameState *fs;       // device
     rb_nav *nav_dev;
@@ -200,6 +207,16 @@ extern "C" int rb_pipeline_create(rb_pipeline **out, int device, const rb_params
         memset(pl->ev_det, 0, sizeof(cudaEvent_t) * max_batch);
         memset(pl->ev_trk, 0, sizeof(cudaEvent_t) * max_batch);
         RB_CUDA(cudaStreamCreateWithFlags(&pl->det_stream, cudaStreamNonBlocking));
+        RB_CUDA(cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking));
+        const char *sb = getenv("REBVO_B200_SUB");
+        pl->sub = sb ? atoi(sb) : 8;
+        if (pl->sub < 1) pl->sub = max_batch;
+        pl->ev_copy = new (std::nothrow) cudaEvent_t[max_batch];
+        if (!pl->ev_copy) return RB_ERR_ARG;
+        memset(pl->ev_copy, 0, sizeof(cudaEvent_t) * max_batch);
+        for (int i = 0; i < max_batch; i++) RB_CUDA(cudaEventCreateWithFlags(&pl->ev_copy[i], cudaEventDisableTiming));
+        RB_CUDA(cudaMalloc(&pl->rgb_src_dev, sizeof(void *)));
+        RB_CUDA(cudaMallocHost(&pl->rgb_src_pin, sizeof(void *) * max_batch));
         RB_CUDA(cudaEventCreateWithFlags(&pl->ev_dog, cudaEventDisableTiming));
         for (int i = 0; i < max_batch; i++) {
             RB_CUDA(cudaEventCreateWithFlags(&pl->ev_det[i], cudaEventDisableTiming));
@@ -229,6 +246,15 @@ extern "C" void rb_pipeline_destroy(rb_pipeline *pl) {
     delete[] pl->ev_det;
     delete[] pl->ev_trk;
     if (pl->det_stream) cudaStreamDestroy(pl->det_stream);
+    if (pl->copy_stream) {
+        cudaStreamSynchronize(pl->copy_stream);
+        cudaStreamDestroy(pl->copy_stream);
+    }
+    for (int i = 0; i < pl->max_batch; i++)
+        if (pl->ev_copy && pl->ev_copy[i]) cudaEventDestroy(pl->ev_copy[i]);
+    delete[] pl->ev_copy;
+    cudaFree(pl->rgb_src_dev);
+    if (pl->rgb_src_pin) cudaFreeHost(pl->rgb_src_pin);
     rb_dogws_free(&pl->ws);
     cudaFree(pl->chain);
     cudaFree(pl->fs);
@@ -334,7 +360,7 @@ static int enqueue_batch(rb_pipeline *pl, int n, long long first_frame, bool wit
     const rb_params &p = pl->p;
     int r;
     prof_mark(pl, ST_H2D);
-    if ((r = rb_dog_gray(c, &pl->ws, n))) return r;
+    if ((r = rb_dog_gray(c, &pl->ws, n, pl->rgb_src_dev))) return r;
     prof_mark(pl, ST_GRAY);
     if (with_events) RB_CUDA(cudaEventRecord(pl->ev[1], c->stream));
     if ((r = rb_dog_build_batch(c, &pl->ws, n))) return r;
@@ -406,51 +432,74 @@ static int push_impl(rb_pipeline *pl, const uint8_t *rgb, bool on_device, const 
     pl->pn = 0;
     prof_mark(pl, ST_NAV);   // origin of this push
     RB_CUDA(cudaEventRecord(pl->ev[0], c->stream));
-    RB_CUDA(cudaMemcpyAsync(pl->fa_dev, pl->fa_pin, sizeof(FrameArgs) * n, cudaMemcpyHostToDevice, c->stream));
-    RB_CUDA(cudaMemcpyAsync(pl->ws.rgb, rgb, (size_t)n * 3 * c->N,
-                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
-    const bool graph_ok = pl->use_graph && first > 0;
-    if (!graph_ok) {
-        if ((r = enqueue_batch(pl, n, first, true))) return r;
-    } else {
-        const int key = (int)(first % RB_NMAPS) * (pl->max_batch + 1) + n;
-        // capture the batch once per ring phase; replays only differ through fa_dev / ws.rgb contents.  All phases of
-        // this batch size are instantiated together, so that no later push pays for a capture.
-        const bool build = !pl->gexec[key];
-        for (int ph = 0; ph < RB_NMAPS && build; ph++) {
-            const int k = ph * (pl->max_batch + 1) + n;
-            if (pl->gexec[k]) continue;
-            cudaGraph_t g = nullptr;
-            const int64_t l0 = c->launches;
-            RB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-            r = enqueue_batch(pl, n, ph == 0 ? RB_NMAPS : ph, false);   // any first frame > 0 of that phase
-            cudaError_t e = cudaStreamEndCapture(c->stream, &g);
-            if (r) {
-                if (g) cudaGraphDestroy(g);
-                return r;
-            }
-            if (e != cudaSuccess) {
-                snprintf(c->err, sizeof(c->err), "graph capture: %s", cudaGetErrorString(e));
-                return RB_ERR_CUDA;
-            }
-            pl->glaunches[k] = (int)(c->launches - l0);
-            c->launches = l0;
-            e = cudaGraphInstantiate(&pl->gexec[k], g, 0);
-            cudaGraphDestroy(g);
-            if (e != cudaSuccess) {
-                pl->gexec[k] = nullptr;
-                snprintf(c->err, sizeof(c->err), "graph instantiate: %s", cudaGetErrorString(e));
-                return RB_ERR_CUDA;
-            }
+    // sub-batches: device input = one (the caller's buffer is read in place).  Host input = a short head (pl->sub
+    // frames) and the rest: only the head's H2D copy is exposed, the rest of the frames are copied on the copy stream into
+    // their own staging region while the head computes (a frame costs ~8x more to track than to copy), and the scale
+    // space of the rest still runs as one large batch.
+    const int head = (on_device || pl->prof_on || n < 3 * pl->sub) ? n : pl->sub;
+    const int nsub = head < n ? 2 : 1;
+    const size_t fbytes = (size_t)3 * c->N;
+    for (int j = 0; j < nsub; j++) {
+        const int off = j == 0 ? 0 : head, nj = j == 0 ? head : n - head;
+        if (on_device) {
+            pl->rgb_src_pin[j] = rgb;
+        } else {
+            pl->rgb_src_pin[j] = pl->ws.rgb + (size_t)off * fbytes;
+            cudaStream_t cs = nsub > 1 ? pl->copy_stream : c->stream;
+            RB_CUDA(cudaMemcpyAsync(pl->ws.rgb + (size_t)off * fbytes, rgb + (size_t)off * fbytes, (size_t)nj * fbytes,
+                                    cudaMemcpyHostToDevice, cs));
+            if (nsub > 1) RB_CUDA(cudaEventRecord(pl->ev_copy[j], cs));
         }
-        RB_CUDA(cudaEventRecord(pl->ev[1], c->stream));
-        RB_CUDA(cudaGraphLaunch(pl->gexec[key], c->stream));
-        RB_CUDA(cudaEventRecord(pl->ev[2], c->stream));
-        c->launches += pl->glaunches[key];
+    }
+    for (int j = 0; j < nsub; j++) {
+        const int off = j == 0 ? 0 : head, nj = j == 0 ? head : n - head;
+        const long long first_j = first + (long long)off;
+        if (!on_device && nsub > 1) RB_CUDA(cudaStreamWaitEvent(c->stream, pl->ev_copy[j], 0));
+        RB_CUDA(cudaMemcpyAsync(pl->fa_dev, pl->fa_pin + off, sizeof(FrameArgs) * nj, cudaMemcpyHostToDevice, c->stream));
+        RB_CUDA(cudaMemcpyAsync(pl->rgb_src_dev, pl->rgb_src_pin + j, sizeof(void *), cudaMemcpyHostToDevice, c->stream));
+        const bool graph_ok = pl->use_graph && first_j > 0;
+        if (!graph_ok) {
+            if ((r = enqueue_batch(pl, nj, first_j, j == 0))) return r;
+        } else {
+            const int key = (int)(first_j % RB_NMAPS) * (pl->max_batch + 1) + nj;
+            // capture the batch once per ring phase; replays only differ through fa_dev / rgb_src_dev contents.  All
+            // phases of this batch size are instantiated together, so that no later push pays for a capture.
+            const bool build = !pl->gexec[key];
+            for (int ph = 0; ph < RB_NMAPS && build; ph++) {
+                const int k = ph * (pl->max_batch + 1) + nj;
+                if (pl->gexec[k]) continue;
+                cudaGraph_t g = nullptr;
+                const int64_t l0 = c->launches;
+                RB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                r = enqueue_batch(pl, nj, ph == 0 ? RB_NMAPS : ph, false);   // any first frame > 0 of that phase
+                cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+                if (r) {
+                    if (g) cudaGraphDestroy(g);
+                    return r;
+                }
+                if (e != cudaSuccess) {
+                    snprintf(c->err, sizeof(c->err), "graph capture: %s", cudaGetErrorString(e));
+                    return RB_ERR_CUDA;
+                }
+                pl->glaunches[k] = (int)(c->launches - l0);
+                c->launches = l0;
+                e = cudaGraphInstantiate(&pl->gexec[k], g, 0);
+                cudaGraphDestroy(g);
+                if (e != cudaSuccess) {
+                    pl->gexec[k] = nullptr;
+                    snprintf(c->err, sizeof(c->err), "graph instantiate: %s", cudaGetErrorString(e));
+                    return RB_ERR_CUDA;
+                }
+            }
+            if (j == 0) RB_CUDA(cudaEventRecord(pl->ev[1], c->stream));
+            RB_CUDA(cudaGraphLaunch(pl->gexec[key], c->stream));
+            if (j == 0) RB_CUDA(cudaEventRecord(pl->ev[2], c->stream));
+            c->launches += pl->glaunches[key];
+        }
+        RB_CUDA(cudaMemcpyAsync(pl->nav_pin + off, pl->nav_dev, sizeof(rb_nav) * nj, cudaMemcpyDeviceToHost, c->stream));
     }
     pl->t_prev = ts[n - 1];
     pl->n_pushed += n;
-    RB_CUDA(cudaMemcpyAsync(pl->nav_pin, pl->nav_dev, sizeof(rb_nav) * n, cudaMemcpyDeviceToHost, c->stream));
     prof_mark(pl, ST_NAV);
     RB_CUDA(cudaEventRecord(pl->ev[3], c->stream));
     RB_CUDA(cudaStreamSynchronize(c->stream));

@@ -79,12 +79,33 @@ def test_trajectory_vs_reference(built, stream, ref_run):
         pass
 
 
-def test_batch_size_invariance(built, stream):
+def test_batch_size_invariance(built, stream, monkeypatch):
     a, _ = _gpu_run(stream, 20)
     b, _ = _gpu_run(stream, 7)
     c, _ = _gpu_run(stream, 1)
+    # host-input pushes of >= 3 x REBVO_B200_SUB frames are cut into a head and the rest (copy/compute overlap)
+    monkeypatch.setenv("REBVO_B200_SUB", "5")
+    d, _ = _gpu_run(stream, 20)
     for f in ("Pos", "Pose", "kn", "matches", "Kp"):
-        assert np.array_equal(a[f], b[f]) and np.array_equal(a[f], c[f]), f
+        assert np.array_equal(a[f], b[f]) and np.array_equal(a[f], c[f]) and np.array_equal(a[f], d[f]), f
+
+
+def test_device_input_equals_host_input(built, stream):
+    """rb_pipeline_push_dev reads the caller's device buffer in place; same bits as the host-input path."""
+    import torch
+    from rebvo_b200 import capi, synth
+    ts, fr = stream
+    a, _ = _gpu_run(stream, 20)
+    pl = capi.Pipeline(capi.default_params(synth.EUROC), max_batch=20)
+    navs = []
+    for s in range(0, NF, 20):
+        dev = torch.from_numpy(np.ascontiguousarray(fr[s:s + 20])).cuda()
+        navs.append(pl.push_dev(dev.data_ptr(), ts[s:s + 20]))
+        del dev
+    pl.close()
+    b = np.concatenate(navs)
+    for f in ("Pos", "Pose", "kn", "matches", "Kp"):
+        assert np.array_equal(a[f], b[f]), f
 
 
 def test_graph_replay_equals_eager_launches(built, stream, monkeypatch):
