@@ -343,12 +343,12 @@ static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, const FrameArg
                                        p.ReshapeQAbsolute, p.LocationUncertainty, &pl->fs->do_map)))
         return r;
     RB_TRACE(c->stream, 9);
+    prof_mark(pl, ST_REG_EKF);
     if ((r = rb_map_update_enqueue(c, neu, p.RegularizeThresh, pl->fs->V, p.ReshapeQAbsolute, p.LocationUncertainty,
                                    RB_RHO_MAX, 1, p.DoReScaling > 0 ? 1 : 0, pl->fs, p.MatchThreshold, old->st,
                                    nav_slot, fa)))
         return r;
-    prof_mark(pl, ST_REG_EKF);
-    prof_mark(pl, ST_RESCALE);
+    prof_mark(pl, ST_RESCALE);   // rescaling + pose integration / nav record (folded)
     RB_TRACE(c->stream, 5);
     prof_mark(pl, ST_FINISH);
     return RB_OK;
