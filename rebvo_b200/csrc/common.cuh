@@ -129,7 +129,6 @@ struct LMState {
 
 struct TrackState {
     LMState lm;
-    int *blk_first;       // per block: offset of the first matched keyline (blockDim if none)
     int *blk_has;
     double *blk_last_fi;  // per block: residual of its last matched keyline
     double *partials;     // per block x 28 reduction partials
@@ -137,7 +136,6 @@ struct TrackState {
     int nblk;
     struct MinCtl *ctl;   // request slots / sequence base of the persistent minimiser kernel
     unsigned long long *ll;   // its per-block partial-sum slots
-    unsigned long long *ll2;  // same for the persistent rescaling kernel
     // scratch for FordwardMatch / Regularize_1_iter
     unsigned long long *fm_best;
     int *fm_idx;

@@ -48,7 +48,6 @@ int rb_track_state_alloc(rb_ctx *c, rb_map *m) {
     const int nblk = rb_div_up(c->kcap, TVR_T);
     const size_t K = c->kcap + 32;
     host.nblk = nblk;
-    RB_CUDA(cudaMalloc(&host.blk_first, sizeof(int) * nblk));
     RB_CUDA(cudaMalloc(&host.blk_has, sizeof(int) * nblk));
     RB_CUDA(cudaMalloc(&host.blk_last_fi, sizeof(double) * nblk));
     RB_CUDA(cudaMalloc(&host.partials, sizeof(double) * 28 * TVR_T));
@@ -56,8 +55,6 @@ int rb_track_state_alloc(rb_ctx *c, rb_map *m) {
     RB_CUDA(cudaMemsetAsync(host.carry, 0, sizeof(double) * 3 * TVR_T, c->stream));
     RB_CUDA(cudaMalloc(&host.ctl, sizeof(MinCtl)));
     RB_CUDA(cudaMemsetAsync(host.ctl, 0, sizeof(MinCtl), c->stream));
-    RB_CUDA(cudaMalloc(&host.ll2, sizeof(unsigned long long) * 4 * TVR_T));
-    RB_CUDA(cudaMemsetAsync(host.ll2, 0, sizeof(unsigned long long) * 4 * TVR_T, c->stream));
     RB_CUDA(cudaMalloc(&host.ll, sizeof(unsigned long long) * 64 * TVR_T));
     RB_CUDA(cudaMemsetAsync(host.ll, 0, sizeof(unsigned long long) * 64 * TVR_T, c->stream));
     RB_CUDA(cudaMalloc(&host.fm_best, sizeof(unsigned long long) * K));
@@ -74,14 +71,12 @@ int rb_track_state_alloc(rb_ctx *c, rb_map *m) {
 
 void rb_track_state_free(rb_map *m) {
     TrackState &h = m->ts_host;
-    cudaFree(h.blk_first);
     cudaFree(h.blk_has);
     cudaFree(h.blk_last_fi);
     cudaFree(h.partials);
     cudaFree(h.carry);
     cudaFree(h.ctl);
     cudaFree(h.ll);
-    cudaFree(h.ll2);
     cudaFree(h.fm_best);
     cudaFree(h.fm_idx);
     cudaFree(h.reg_r);

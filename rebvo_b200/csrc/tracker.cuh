@@ -19,7 +19,6 @@ enum LMStep {
 struct MinCtl {
     unsigned long long slot[40];   // {hi: sequence number, lo: payload word}; all zero between minimisations
     unsigned int gen;              // base of the sequence numbers of the next minimisation
-    unsigned int gen2;             // same for the persistent rescaling kernel
     int abort;                     // sticky: a spin timed out
 };
 
