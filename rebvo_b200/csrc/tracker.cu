@@ -18,11 +18,18 @@
 #ifdef RB_TVR_PROF
 __device__ long long g_tvr_prof[256 * 16];
 #define TVR_STAMP(k) do { if (threadIdx.x == 0) g_tvr_prof[blockIdx.x * 16 + (k)] = clock64(); } while (0)
+__device__ __forceinline__ long long tvr_gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TVR_GSTAMP(k) do { if (threadIdx.x == 0) g_tvr_prof[blockIdx.x * 16 + (k)] = tvr_gtime(); } while (0)
 extern "C" int rb_debug_fetch(long long *out) {
     return (int)cudaMemcpyFromSymbol(out, g_tvr_prof, sizeof(long long) * 256 * 16);
 }
 #else
 #define TVR_STAMP(k) do { } while (0)
+#define TVR_GSTAMP(k) do { } while (0)
 #endif
 
 struct CamC {
@@ -1093,6 +1100,7 @@ __global__ void __launch_bounds__(TVR_T, 2) k_minimizer_persist(KLSoA old, const
             if (tid < MIN_REQ_WORDS && n_act > 1) {
                 st_volatile_u64(&ctl->slot[tid], ((unsigned long long)seq << 32) | s_req[tid]);
             }
+            TVR_GSTAMP(12);   // request published
         } else if (tid < MIN_REQ_WORDS + 2) {
             // words 34, 35: this block's stale-fi carry of the previous evaluation, published with the request
             const unsigned long long *src = tid < MIN_REQ_WORDS
@@ -1113,6 +1121,7 @@ __global__ void __launch_bounds__(TVR_T, 2) k_minimizer_persist(KLSoA old, const
         __syncthreads();
         if (s_abort) break;
         TVR_STAMP(1);
+        if (!master) TVR_GSTAMP(12);   // request observed
         if (!master && e > 0 && tid == 0)
             s_carry[prev_out] = __hiloint2double((int)s_req[MIN_REQ_WORDS + 1], (int)s_req[MIN_REQ_WORDS]);
         const int res_in = (int)s_req[32], res_out = (int)s_req[33];
@@ -1167,6 +1176,7 @@ __global__ void __launch_bounds__(TVR_T, 2) k_minimizer_persist(KLSoA old, const
             st_volatile_u64(tp.ll + (size_t)tid * TVR_T + blockIdx.x, ((unsigned long long)seq << 32) | w);
         }
         TVR_STAMP(3);
+        TVR_GSTAMP(13);   // partial sums stored
         if (!master) continue;
         // ---- master: gather (thread b polls block b's slots), carries, grid sums, LM step ------------------
         double pv[28];
@@ -1207,6 +1217,7 @@ __global__ void __launch_bounds__(TVR_T, 2) k_minimizer_persist(KLSoA old, const
             } while (!ok);
         }
         TVR_STAMP(4);
+        TVR_GSTAMP(14);   // all partial sums gathered (master)
         {
             const double cy = tvr_carries(has, lastv, tp.carry + res_out * TVR_T, n_act, s_blast, s_wmask, tid, lane, wid);
             if (tid < n_act && tid > 0) {   // travels with the next request (same sequence number), no fence needed

@@ -19,6 +19,9 @@ names = ['exp', 'body', 'tail+ll', 'gather', 'carries', 'reduce', 'lm_step', 'ep
 for b in (0, 1, 30, 58):
     row = d[b]
     print('block', b, ' '.join('%s=%d' % (names[k], row[k + 1] - row[k]) for k in range(0, 8) if row[k + 1] and row[k] and row[k + 1] > row[k]))
-print('flag wait max per block (cycles):', [int(d[b][10]) for b in (0,1,30,58)], 'own flag wait', [int(d[b][11]) for b in (0,1,30,58)], 'payload done rel stamp3', [int(d[b][12]-d[b][3]) for b in (0,1,30,58)])
-print('stamp3 skew across blocks', int(max(d[b][3] for b in range(65)) - min(d[b][3] for b in range(65))), 'stamp0 skew', int(max(d[b][0] for b in range(65)) - min(d[b][0] for b in range(65))))
+na = int(d[255, 15])
+pub = int(d[0][12]); obs = np.array([int(d[b][12]) for b in range(1, na)]); sto = np.array([int(d[b][13]) for b in range(na)]); gath = int(d[0][14])
+print('globaltimer ns: request published -> observed by workers: min %d mean %d max %d' % ((obs - pub).min(), (obs - pub).mean(), (obs - pub).max()))
+print('worker observed -> sums stored: mean %d ; last store -> master gathered %d ; first store -> gathered %d' % ((sto[1:] - obs).mean(), gath - sto.max(), gath - sto.min()))
+print('master publish -> gathered (one evaluation minus LM/exp): %d ns' % (gath - pub))
 print('master last eval total', d[0][7] - d[0][0])
