@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(64) k_colscan(const float4 *__restrict__ in, f
 }
 
 // Last box of both filters + sspace::build_dog (sspace.cpp:63-70): img0, dog = img1 - img0
-#define BLUR_RY 8
+#define BLUR_RY 4
 __global__ void __launch_bounds__(256) k_blur_dog(const float *__restrict__ I, float *__restrict__ img0,
                                                   float *__restrict__ dog, float *__restrict__ img1_opt,
                                                   int w, int h, int B, int d0, int d1,
