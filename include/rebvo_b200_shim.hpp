@@ -291,6 +291,43 @@ class edge_tracker : public edge_finder {
         return n;
     }
     int NumMatches() { return nmatch; }
+    // IMU mode (config 3).  edge_tracker.cpp:1207-1301: linearised 6-DoF estimate over the forward matches of this map
+    bool ExtRotVel(const TooN::Vector<3> &vel, TooN::Matrix<6, 6> &Wx, TooN::Matrix<6, 6> &Rx, TooN::Vector<6> &X,
+                   const double &LocUncert, double HubReweigth) {
+        double v[3] = {vel[0], vel[1], vel[2]}, wx[36], rx[36], x[6];
+        int ok = 0;
+        dev->check(rb_ext_rot_vel(map, v, wx, rx, x, LocUncert, HubReweigth, &ok));
+        for (int i = 0; i < 6; i++) {
+            X[i] = x[i];
+            for (int j = 0; j < 6; j++) {
+                Wx(i, j) = wx[i * 6 + j];
+                Rx(i, j) = rx[i * 6 + j];
+            }
+        }
+        return ok != 0;
+    }
+    // edge_tracker.cpp:1308-1338: gyroscope-prior correction of the roto-translation estimate (host algebra)
+    static void BiasCorrect(TooN::Vector<6> &X, TooN::Matrix<6, 6> &Wx, TooN::Vector<3> &Gb, TooN::Matrix<3, 3> &Wb,
+                            const TooN::Matrix<3, 3> &Rg, const TooN::Matrix<3, 3> &Rb) {
+        double x[6], wx[36], gb[3], wb[9], rg[9], rb[9];
+        for (int i = 0; i < 6; i++) {
+            x[i] = X[i];
+            for (int j = 0; j < 6; j++) wx[i * 6 + j] = Wx(i, j);
+        }
+        for (int i = 0; i < 3; i++) gb[i] = Gb[i];
+        m3(Wb, wb);
+        m3(Rg, rg);
+        m3(Rb, rb);
+        rb_bias_correct(x, wx, gb, wb, rg, rb);
+        for (int i = 0; i < 6; i++) {
+            X[i] = x[i];
+            for (int j = 0; j < 6; j++) Wx(i, j) = wx[i * 6 + j];
+        }
+        for (int i = 0; i < 3; i++) {
+            Gb[i] = gb[i];
+            for (int j = 0; j < 3; j++) Wb(i, j) = wb[i * 3 + j];
+        }
+    }
     friend class global_tracker;
 };
 
@@ -333,6 +370,22 @@ class global_tracker {
         for (int i = 0; i < 6; i++)
             for (int j = 0; j < 6; j++) W_X(i, j) = (T)WX[i * 6 + j];
         klist.invalidate_host();  // m_id_f of the old map was rewritten
+        return score;
+    }
+    // IMU mode (config 3).  global_tracker.cpp:1036-1093: translation-only Levenberg-Marquardt (the reference
+    // instantiates float and double; both forward to the float64 kernels)
+    template <class T>
+    double Minimizer_V(TooN::Vector<3> &Vel, TooN::Matrix<3, 3> &RVel, edge_tracker &klist, T match_thresh, int iter_max,
+                       T s_rho_min, uint MatchNumThresh, double reweigth_distance, float min_mod) {
+        if (!klist_f || klist.KNum() <= 0) return 0;
+        double V[3] = {Vel[0], Vel[1], Vel[2]}, RV[9], score = 0;
+        klist.dev->check(rb_minimizer_v(klist_f->map, klist.map, V, RV, (double)match_thresh, iter_max, (double)s_rho_min,
+                                        MatchNumThresh, reweigth_distance, min_mod, &score));
+        for (int i = 0; i < 3; i++) {
+            Vel[i] = V[i];
+            for (int j = 0; j < 3; j++) RVel(i, j) = RV[i * 3 + j];
+        }
+        klist.invalidate_host();
         return score;
     }
 };

@@ -135,3 +135,21 @@ def test_bias_correct_against_reference(built):
         R.ref_bias_correct(_p(b[0]), _p(b[1]), _p(b[2]), _p(b[3]), _p(Rg), _p(Rb))
         for x, y in zip(a, b):
             assert np.allclose(x, y, rtol=1e-9, atol=1e-12 * max(1.0, np.abs(y).max()))
+
+
+def test_shim_imu_mirrors_compile():
+    """The IMU-mode mirrors of the C++ shim (Minimizer_V, ExtRotVel, BiasCorrect) are header-only templates that the
+    replay driver does not instantiate: compile them against the reference's own TooN / cam_model headers."""
+    import shutil
+    import subprocess
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = "/root/reference"
+    out = os.path.join(repo, "oracle", "_ref")
+    if not os.path.isdir(ref) or not os.path.isdir(os.path.join(out, "toon")) or shutil.which("g++") is None:
+        pytest.skip("reference headers not available here")
+    cmd = ["g++", "-std=c++11", "-O0", "-w", "-fsyntax-only", "-include", os.path.join(out, "shim", "fix_gcc13.h"),
+           "-I" + os.path.join(out, "shim"), "-I" + os.path.join(repo, "include"), "-I" + os.path.join(ref, "include"),
+           "-I" + os.path.join(out, "toon"), os.path.join(repo, "tests", "shim_syntax.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+
