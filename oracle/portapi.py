@@ -18,7 +18,8 @@ def lib():
         L.orc_map_create.restype = C.c_void_p
         L.orc_map_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_double,
                                      C.c_double]
-        for f in ("orc_quantile", "orc_minimizer_rv", "orc_try_vel_rot", "orc_rescale"):
+        for f in ("orc_quantile", "orc_minimizer_rv", "orc_try_vel_rot", "orc_rescale", "orc_try_vel",
+                  "orc_minimizer_v"):
             getattr(L, f).restype = C.c_double
         L.orc_reestimate.restype = C.c_float
         _lib = L
@@ -115,6 +116,30 @@ class PortMap:
                                    _p(res_out), _p(JtJ), _p(JtF))
         return s, JtJ, JtF, res_out
 
+    # ---- IMU-mode rows (same signatures as oracle/refapi.py) ----------------------------------------------
+    def try_vel(self, old, V, match_thresh, s_rho_min, match_num_thresh, residuals, rw_dist, min_mod):
+        V = np.array(V, np.float64)
+        res = np.ascontiguousarray(residuals[:old.knum()], np.float64).copy()
+        JtJ, JtF = np.zeros((3, 3)), np.zeros(3)
+        s = self.L.orc_try_vel(self.h_, old.h_, _p(V), C.c_double(match_thresh), C.c_double(s_rho_min),
+                               C.c_uint(match_num_thresh), _p(res), C.c_double(rw_dist), C.c_float(min_mod), _p(JtJ),
+                               _p(JtF))
+        return s, JtJ, JtF, res
+
+    def minimizer_v(self, old, V, match_thresh, iter_max, s_rho_min, match_num_thresh, rw_dist, min_mod):
+        V = np.array(V, np.float64)
+        RV = np.zeros((3, 3))
+        F = self.L.orc_minimizer_v(self.h_, old.h_, _p(V), _p(RV), C.c_double(match_thresh), iter_max,
+                                   C.c_double(s_rho_min), C.c_uint(match_num_thresh), C.c_double(rw_dist),
+                                   C.c_float(min_mod))
+        return dict(F=F, V=V, RVel=RV)
+
+    def ext_rot_vel(self, V, loc_unc, hub):
+        V = np.array(V, np.float64)
+        Wx, Rx, X = np.zeros((6, 6)), np.zeros((6, 6)), np.zeros(6)
+        ok = self.L.orc_ext_rot_vel(self.h_, _p(V), _p(Wx), _p(Rx), _p(X), C.c_double(loc_unc), C.c_double(hub))
+        return bool(ok), Wx, Rx, X
+
     def minimizer_rv(self, old, V, W, match_thresh, iter_max, init_type, reweight, max_s_rho, match_num_thresh,
                      init_iter):
         V, W = np.array(V, np.float64), np.array(W, np.float64)
@@ -157,3 +182,12 @@ def so3_exp(w):
     R = np.zeros((3, 3))
     lib().orc_so3_exp(_p(w), _p(R))
     return R
+
+
+def bias_correct(X, Wx, Gb, Wb, Rg, Rb):
+    """edge_tracker::BiasCorrect restated (in/out arrays like the reference)."""
+    a = [np.ascontiguousarray(np.array(v, np.float64)) for v in (X, Wx, Gb, Wb)]
+    Rg, Rb = np.ascontiguousarray(Rg, np.float64), np.ascontiguousarray(Rb, np.float64)
+    lib().orc_bias_correct(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(Rg), _p(Rb))
+    return a
+

@@ -7,7 +7,9 @@
 // that build (tests/golden/make_golden.py).  Float32 stages, keyline records, masks and fields must match
 // the reference bit for bit; the pairwise-tree sums of TryVelRot are restated in the reference's order, so
 // JtJ / JtF / score match bitwise as well; only the 6x6 SVD solve differs (LAPACK dgesvd_ there, Gaussian
-// elimination here) and is compared to 1e-9.
+// elimination here) and is compared to 1e-9.  The IMU-mode rows (TryVel, Minimizer_V, ExtRotVel, BiasCorrect) are restated
+// at the end of the file: TryVel is sequential double arithmetic and matches bitwise, the 3x3 solves follow
+// util::Matrix3x3Inv over TooN's Gaussian-elimination determinant (1e-12), ExtRotVel's SVD is again an elimination solve.
 //
 // Third-party arithmetic restated from its published algorithm: TooN 2.2 (vendored in the reference as
 // TooN-2.2.zip): SO3::exp (so3.h:254-285), Cholesky<6> (Cholesky.h), dot products accumulate from zero.
@@ -1138,4 +1140,312 @@ double orc_rescale(void *p, double *RKp, double s_rho_min, unsigned mnm, int re_
 }
 void orc_so3_exp(const double *w, double *R) { so3_exp(w, R); }
 void orc_set_frame_count(void *p, unsigned fc) { ((OMap *)p)->frame_count = fc; }
+
+// =====================================================================================================
+// IMU-mode rows (configuration 3)
+// =====================================================================================================
+// TooN::determinant of a 3x3 = determinant_gaussian_elimination (TooN/determinant.h:91-146): partial pivoting, the
+// running product of the pivots, early exit on zero
+static double det3_gauss(const double *Ain) {
+    double A[3][3];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) A[i][j] = Ain[i * 3 + j];
+    double det = 1;
+    for (int i = 0; i < 3; i++) {
+        int argmax = i;
+        double maxval = fabs(A[i][i]);
+        for (int ii = i + 1; ii < 3; ii++) {
+            const double v = fabs(A[ii][i]);
+            if (v > maxval) {
+                maxval = v;
+                argmax = ii;
+            }
+        }
+        const double pivot = A[argmax][i];
+        if (argmax != i) {
+            det *= -1;
+            for (int j = i; j < 3; j++) {
+                const double t = A[i][j];
+                A[i][j] = A[argmax][j];
+                A[argmax][j] = t;
+            }
+        }
+        det *= A[i][i];
+        if (det == 0) return 0;
+        for (int u = i + 1; u < 3; u++) {
+            const double factor = A[u][i] / pivot;
+            for (int j = i + 1; j < 3; j++) A[u][j] = A[u][j] - factor * A[i][j];
+        }
+    }
+    return det;
+}
+// util::Matrix3x3Inv (include/UtilLib/toon_util.h:32-41): cofactors / TooN::determinant
+static void mat3_inv(const double *A, double *B) {
+    double t[9];
+    t[0] = A[8] * A[4] - A[7] * A[5];
+    t[1] = -(A[8] * A[1] - A[7] * A[2]);
+    t[2] = A[5] * A[1] - A[4] * A[2];
+    t[3] = -(A[8] * A[3] - A[6] * A[5]);
+    t[4] = A[8] * A[0] - A[6] * A[2];
+    t[5] = -(A[5] * A[0] - A[3] * A[2]);
+    t[6] = A[7] * A[3] - A[6] * A[4];
+    t[7] = -(A[7] * A[0] - A[6] * A[1]);
+    t[8] = A[4] * A[0] - A[3] * A[1];
+    const double det = det3_gauss(A);
+    for (int i = 0; i < 9; i++) B[i] = t[i] / det;
+}
+// TooN fixed-size products: every element is a dot product accumulated from zero in index order
+static void mat3_mul(const double *A, const double *B, double *C) {
+    double t[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double r = 0;
+            for (int k = 0; k < 3; k++) r += A[i * 3 + k] * B[k * 3 + j];
+            t[i * 3 + j] = r;
+        }
+    for (int i = 0; i < 9; i++) C[i] = t[i];
+}
+static void mat3_vec(const double *A, const double *v, double *o) {
+    double t[3];
+    for (int i = 0; i < 3; i++) {
+        double r = 0;
+        for (int k = 0; k < 3; k++) r += A[i * 3 + k] * v[k];
+        t[i] = r;
+    }
+    for (int i = 0; i < 3; i++) o[i] = t[i];
+}
+
+// global_tracker::TryVel<double> (global_tracker.cpp:829-934) with Calc_f_J (:174-220) and Test_f_k
+// (global_tracker.h:89-104).  pn = the map whose field is searched, po = the keylines being projected; residuals is read
+// and updated in place (K0 doubles).  Sequential sums in the reference's order.
+double orc_try_vel(void *pn, void *po, const double *Vel, double match_thresh, double s_rho_min,
+                   unsigned match_num_thresh, double *residuals, double reweigth_distance, float min_mod, double *JtJ,
+                   double *JtF) {
+    OMap *mn = (OMap *)pn, *mo = (OMap *)po;
+    const double max_r = mn->max_r, zfm = mn->zfm;
+    double score = 0, f;
+    for (int i = 0; i < 9; i++) JtJ[i] = 0;
+    for (int i = 0; i < 3; i++) JtF[i] = 0;
+    double fi = 0;
+    const unsigned mnt = match_num_thresh < mn->frame_count ? match_num_thresh : mn->frame_count;
+    for (int ikl = 0; ikl < mo->kn; ikl++) {
+        OKeyLine &kl = mo->kl[ikl];
+        kl.m_id_f = -1;
+        if (min_mod > 0 && kl.n_m < min_mod) continue;
+        if (kl.s_rho > s_rho_min || (unsigned)kl.m_num < mnt) continue;
+        double weight = 1;
+        if (residuals[ikl] > reweigth_distance) weight = reweigth_distance / residuals[ikl];
+        const double z_p = 1.0 / kl.rho + Vel[2];
+        if (z_p <= 0) {
+            f = (1 / (kl.s_rho)) * max_r * weight;
+            score += f * f;
+            continue;
+        }
+        const double rho_p = 1.0 / z_p;
+        const double pjx = rho_p * (Vel[0] * zfm - Vel[2] * kl.p_m[0]) + kl.p_m[0];
+        const double pjy = rho_p * (Vel[1] * zfm - Vel[2] * kl.p_m[1]) + kl.p_m[1];
+        const double pix = pjx + mn->ppx, piy = pjy + mn->ppy;   // cam_mod.Hom2Img
+        const int x = (int)(pix + 0.5), y = (int)(piy + 0.5);    // util::round2int_positive
+        if (x < 1 || y < 1 || x >= mn->w - 1 || y >= mn->h - 1) {
+            f = (1 / (kl.s_rho)) * max_r * weight;
+            score += f * f;
+            continue;
+        }
+        double df_dx, df_dy;
+        {   // Calc_f_J<double>(y*w+x, df_dx, df_dy, kl, p_pji, max_r, match_thresh, mnum, fi)
+            const int fidx = y * mn->w + x;
+            bool hit = false;
+            if (mn->fikl[fidx] >= 0) {
+                const OKeyLine &fk = mn->kl[mn->fikl[fidx]];
+                const double p_n2 = (kl.n_m * kl.n_m);                              // float product -> double
+                const double p_esc = kl.m_m[0] * fk.m_m[0] + kl.m_m[1] * fk.m_m[1];  // float arithmetic -> double
+                if (!(fabs(p_esc - p_n2) > match_thresh * p_n2)) {
+                    const double dx = pix - fk.c_p[0], dy = piy - fk.c_p[1];
+                    fi = (dx * fk.u_m[0] + dy * fk.u_m[1]);
+                    df_dx = fk.u_m[0] / kl.s_rho;
+                    df_dy = fk.u_m[1] / kl.s_rho;
+                    kl.m_id_f = mn->fikl[fidx];
+                    f = fi / kl.s_rho;
+                    hit = true;
+                }
+            }
+            if (!hit) {
+                df_dx = 0;
+                df_dy = 0;
+                f = max_r / kl.s_rho;
+            }
+        }
+        f *= weight;
+        score += f * f;
+        const double jx = rho_p * zfm * df_dx * weight;
+        const double jy = rho_p * zfm * df_dy * weight;
+        const double jz = -rho_p * (pjx * df_dx + pjy * df_dy) * weight;
+        JtJ[0] += jx * jx;
+        JtJ[4] += jy * jy;
+        JtJ[8] += jz * jz;
+        JtJ[1] += jx * jy;
+        JtJ[2] += jx * jz;
+        JtJ[5] += jy * jz;
+        JtF[0] += jx * f;
+        JtF[1] += jy * f;
+        JtF[2] += jz * f;
+        residuals[ikl] = fabs(fi);
+    }
+    JtJ[3] = JtJ[1];
+    JtJ[6] = JtJ[2];
+    JtJ[7] = JtJ[5];
+    return score;
+}
+
+// global_tracker::Minimizer_V<double> (global_tracker.cpp:1036-1093)
+double orc_minimizer_v(void *pn, void *po, double *Vel, double *RVel, double match_thresh, int iter_max, double s_rho_min,
+                       unsigned match_num_thresh, double reweigth_distance, float min_mod) {
+    OMap *mo = (OMap *)po;
+    double JtJ[9], ApI[9], JtJnew[9], JtF[3], JtFnew[3], h[3], Vnew[3], inv[9];
+    std::vector<double> residuals(mo->kn > 0 ? mo->kn : 1, 0.0);
+    double F = orc_try_vel(pn, po, Vel, match_thresh, s_rho_min, match_num_thresh, residuals.data(), reweigth_distance,
+                           min_mod, JtJ, JtF),
+           Fnew;
+    double v = 2, tau = 1e-3;
+    double mx = JtJ[0];
+    for (int i = 1; i < 9; i++)
+        if (JtJ[i] > mx) mx = JtJ[i];
+    double u = tau * mx;
+    for (int lm_iter = 0; lm_iter < iter_max; lm_iter++) {
+        for (int i = 0; i < 9; i++) ApI[i] = JtJ[i];
+        for (int i = 0; i < 3; i++) ApI[i * 4] = JtJ[i * 4] + u;
+        mat3_inv(ApI, inv);
+        const double ng[3] = {-JtF[0], -JtF[1], -JtF[2]};
+        mat3_vec(inv, ng, h);
+        for (int i = 0; i < 3; i++) Vnew[i] = Vel[i] + h[i];
+        Fnew = orc_try_vel(pn, po, Vnew, match_thresh, s_rho_min, match_num_thresh, residuals.data(), reweigth_distance,
+                           min_mod, JtJnew, JtFnew);
+        double den = 0;
+        for (int i = 0; i < 3; i++) den += (0.5 * h[i]) * (u * h[i] - JtF[i]);
+        const double gain = (F - Fnew) / den;
+        if (gain > 0) {
+            F = Fnew;
+            for (int i = 0; i < 3; i++) Vel[i] = Vnew[i];
+            for (int i = 0; i < 9; i++) JtJ[i] = JtJnew[i];
+            for (int i = 0; i < 3; i++) JtF[i] = JtFnew[i];
+            const double g = 1 - ((2 * gain - 1) * (2 * gain - 1) * (2 * gain - 1));
+            u *= (0.33 > g ? 0.33 : g);
+            v = 2;
+        } else {
+            u *= v;
+            v *= 2;
+        }
+    }
+    mat3_inv(JtJ, RVel);
+    return F;
+}
+
+// edge_tracker::ExtRotVel(vel, Wx, Rx, X, LocUncert, HubReweigth) (edge_tracker.cpp:1207-1301).  The float / double mix of
+// every expression follows the reference's declarations.  SVD<>::backsub / get_pinv are replaced by an elimination solve
+// (the 6x6 system is well conditioned on tracked maps): X and Rx are compared to 1e-9, Wx = Phi^T Phi exactly.
+int orc_ext_rot_vel(void *p, const double *vel, double *Wx, double *Rx, double *X, double LocUncert, double HubReweigth) {
+    OMap *m = (OMap *)p;
+    const double zf = m->zfm;
+    int n = 0;
+    for (int i = 0; i < m->kn; i++)
+        if (m->kl[i].m_id >= 0) n++;
+    std::vector<double> Phi((size_t)n * 6 + 6, 0.0), Y(n > 0 ? n : 1, 0.0);
+    int j = 0;
+    for (int i = 0; i < m->kn; i++) {
+        const OKeyLine &k = m->kl[i];
+        if (k.m_id < 0) continue;
+        const float u_x = k.u_m[0], u_y = k.u_m[1];
+        const double rho_t = 1 / (1 / k.rho + vel[2]);
+        const float qt_x = k.p_m_0[0] + rho_t * (vel[0] * zf - vel[2] * k.p_m_0[0]);
+        const float qt_y = k.p_m_0[1] + rho_t * (vel[1] * zf - vel[2] * k.p_m_0[1]);
+        const double s_rho = k.s_rho;
+        const float q_x = k.p_m[0], q_y = k.p_m[1];
+        double *row = &Phi[(size_t)j * 6];
+        row[0] = u_x * rho_t * zf;
+        row[1] = u_y * rho_t * zf;
+        row[2] = u_x * (-rho_t * q_x) + u_y * (-rho_t * q_y);
+        row[3] = -u_x * q_x * q_y / zf - u_y * (zf + q_y * q_y / zf);
+        row[4] = +u_y * q_x * q_y / zf + u_x * (zf + q_x * q_x / zf);
+        row[5] = -u_x * q_y + u_y * q_x;
+        Y[j] = u_x * (k.p_m[0] - qt_x) + u_y * (k.p_m[1] - qt_y);
+        const float dqvel = u_x * (vel[0] * zf - vel[2] * k.p_m_0[0]) + u_y * (vel[1] * zf - vel[2] * k.p_m_0[1]);
+        const float s_y = sqrt(s_rho * s_rho * dqvel * dqvel + LocUncert * LocUncert);
+        double weigth = 1;
+        if (fabs(Y[j]) > HubReweigth) weigth = fabs(Y[j]) / HubReweigth;
+        for (int c = 0; c < 6; c++) row[c] /= s_y * weigth;
+        Y[j] /= s_y * weigth;
+        j++;
+    }
+    double JtJ[36], JtF[6];
+    for (int a = 0; a < 6; a++) {   // Phi.T()*Phi, Phi.T()*Y: dot products over the rows, from zero, in row order
+        for (int b = 0; b < 6; b++) {
+            double r = 0;
+            for (int q = 0; q < n; q++) r += Phi[(size_t)q * 6 + a] * Phi[(size_t)q * 6 + b];
+            JtJ[a * 6 + b] = r;
+        }
+        double r = 0;
+        for (int q = 0; q < n; q++) r += Phi[(size_t)q * 6 + a] * Y[q];
+        JtF[a] = r;
+    }
+    solve6(JtJ, JtF, X);
+    for (int c = 0; c < 6; c++) {
+        double e[6] = {0, 0, 0, 0, 0, 0}, col[6];
+        e[c] = 1;
+        solve6(JtJ, e, col);
+        for (int r = 0; r < 6; r++) Rx[r * 6 + c] = col[r];
+    }
+    for (int i = 0; i < 36; i++) Wx[i] = JtJ[i];
+    for (int i = 0; i < 36; i++)
+        if (Rx[i] != Rx[i]) return 0;
+    for (int i = 0; i < 6; i++)
+        if (X[i] != X[i]) return 0;
+    return 1;
+}
+
+// edge_tracker::BiasCorrect (edge_tracker.cpp:1308-1338); all arguments in/out like the reference
+void orc_bias_correct(double *X, double *Wx, double *Gb, double *Wb, const double *Rg, const double *Rb) {
+    double Wg[9], t3[9], iWgWb[9];
+    mat3_inv(Rg, Wg);
+    mat3_inv(Wb, t3);
+    for (int i = 0; i < 9; i++) t3[i] = t3[i] + Rb[i];
+    mat3_inv(t3, Wb);   // Wb = Matrix3x3Inv(Matrix3x3Inv(Wb) + Rb)
+    double Wxb[36];
+    for (int i = 0; i < 36; i++) Wxb[i] = Wx[i];
+    for (int i = 0; i < 9; i++) t3[i] = Wg[i] + Wb[i];
+    mat3_inv(t3, iWgWb);
+    double A[9], B[9];
+    mat3_mul(iWgWb, Wg, A);                       // iWgWb*Wg
+    for (int i = 0; i < 9; i++) A[i] = ((i % 4 == 0) ? 1.0 : 0.0) - A[i];   // Identity - iWgWb*Wg
+    mat3_mul(Wg, A, B);                           // Wg*(Identity - iWgWb*Wg)
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) Wxb[(3 + r) * 6 + 3 + c] += B[r * 3 + c];
+    double X1[6];
+    for (int r = 0; r < 6; r++) {                 // X1 = Wx*X
+        double acc = 0;
+        for (int c = 0; c < 6; c++) acc += Wx[r * 6 + c] * X[c];
+        X1[r] = acc;
+    }
+    double v3[3];
+    mat3_mul(Wg, iWgWb, A);                       // Wg*iWgWb*Wb*Gb, left to right
+    mat3_mul(A, Wb, B);
+    mat3_vec(B, Gb, v3);
+    for (int r = 0; r < 3; r++) X1[3 + r] += v3[r];
+    Chol ch;
+    chol_compute(Wxb, &ch);
+    double inv[36];
+    chol_inverse(&ch, inv);
+    for (int r = 0; r < 6; r++) {                 // X = Cholesky<6>(Wxb).get_inverse()*X1
+        double acc = 0;
+        for (int c = 0; c < 6; c++) acc += inv[r * 6 + c] * X1[c];
+        X[r] = acc;
+    }
+    double a3[3], b3[3];
+    mat3_vec(Wg, X + 3, a3);                      // Gb = iWgWb*(Wg*X.slice<3,3>() + Wb*Gb)
+    mat3_vec(Wb, Gb, b3);
+    for (int r = 0; r < 3; r++) a3[r] = a3[r] + b3[r];
+    mat3_vec(iWgWb, a3, Gb);
+    for (int i = 0; i < 9; i++) Wb[i] = Wg[i] + Wb[i];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) Wx[(3 + r) * 6 + 3 + c] += Wg[r * 3 + c];
+}
 }  // extern "C"

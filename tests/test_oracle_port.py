@@ -8,7 +8,9 @@ import os
 import numpy as np
 import pytest
 
-from flow import SMALL, compare, run_flow, small_frames
+import ctypes as C
+
+from flow import DOG_THRESH, PLANE_FIT, POS_NEG, SMALL, compare, run_flow, small_frames
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "flow_small.npz")
 TOL = ("min_V", "min_W", "min_RVel", "min_RW0", "min_W_X", "min_scalars")
@@ -98,3 +100,82 @@ def test_box_plan_known_answers():
         d, s = m.box_plan()
         assert d[0].tolist() == want[0] and d[1].tolist() == want[1]
         assert abs(s[0] - want[2]) < 1e-6 and abs(s[1] - want[3]) < 1e-6
+
+
+def test_port_imu_rows_match_reference():
+    """SURVEY.md 8(a) rows K6 / K13 (IMU mode): TryVel, Minimizer_V<double>, ExtRotVel, BiasCorrect restated in the port
+    against the unmodified reference on a seeded frame pair.  TryVel is sequential double arithmetic in the reference's
+    order: bit-identical, including the in-place residual buffer and the forward-match ids."""
+    from oracle import portapi, refapi
+    from rebvo_b200 import synth
+    if not refapi.available():
+        pytest.skip("oracle/_ref not built")
+    cam = dict(w=320, h=240, zfx=260.0, zfy=258.0, ppx=161.0, ppy=118.5)
+    cfg = dict(SMALL, cam=cam, kl_max=9000, kl_ref=5000, track_points=4000, radius=20, sigma0=3.56359)
+    f0, f1 = synth.frame_pair(seed=31, w=320, h=240, nrect=90, shift=(0.5, -0.3))
+    mk = lambda cls: [cls(cam["w"], cam["h"], cam["ppx"], cam["ppy"], cam["zfx"], cam["zfy"], cfg["sigma0"],
+                          cfg["ksigma"]) for _ in range(2)]
+    refs, ports = mk(refapi.RefMap), mk(portapi.PortMap)
+    t, l = 0.012, 0
+    for r, fr in zip(refs, (f0, f1)):
+        r.rgb2bw(fr)
+        r.build()
+        _, t, l = r.detect(PLANE_FIT, POS_NEG, DOG_THRESH, cfg["kl_max"], t, l, cfg["kl_ref"], cfg["gain"], cfg["tmax"],
+                           cfg["tmin"])
+    old_r, new_r = refs
+    _, rt_new = new_r.reestimate(cfg["track_points"], 100)
+    _, rt_old = old_r.reestimate(cfg["track_points"], 100)
+    rng = np.random.default_rng(5)
+    kl = old_r.keylines()
+    assert len(kl) > 1500
+    kl["rho"] = rng.uniform(0.7, 1.5, len(kl))
+    kl["s_rho"] = rng.uniform(0.05, 0.5, len(kl))
+    kl["m_num"] = rng.integers(0, 6, len(kl))
+    old_r.set_keylines(kl)
+    old_p, new_p = ports
+    for pm, rm in ((old_p, old_r), (new_p, new_r)):
+        pm.set_keylines(rm.keylines())
+        pm.set_mask(rm.mask())
+    new_r.build_field(cfg["radius"], rt_new)
+    new_p.build_field(cfg["radius"], rt_new)
+    q = old_r.quantile(1e-3, 20.0, 0.9, 100)
+    res = np.zeros(old_r.knum())
+    for V in (np.zeros(3), np.array([0.003, -0.002, 0.004]), np.array([-0.005, 0.001, -0.6])):
+        s_r, J_r, F_r, res_r = new_r.try_vel(old_r, V, cfg["match_thresh"], q, 0, res, 2.0, rt_old)
+        s_p, J_p, F_p, res_p = new_p.try_vel(old_p, V, cfg["match_thresh"], q, 0, res, 2.0, rt_old)
+        assert s_r == s_p and np.array_equal(J_r, J_p) and np.array_equal(F_r, F_p)
+        assert np.array_equal(res_r, res_p)
+        assert np.array_equal(old_r.keylines()["m_id_f"], old_p.keylines()["m_id_f"])
+        assert (old_r.keylines()["m_id_f"] >= 0).sum() > 50
+        res = res_r
+    m_r = new_r.minimizer_v(old_r, np.zeros(3), cfg["match_thresh"], 5, q, 0, 2.0, rt_old)
+    m_p = new_p.minimizer_v(old_p, np.zeros(3), cfg["match_thresh"], 5, q, 0, 2.0, rt_old)
+    assert np.allclose(m_r["V"], m_p["V"], rtol=1e-12, atol=1e-15) and np.isclose(m_r["F"], m_p["F"], rtol=1e-12)
+    assert np.allclose(m_r["RVel"], m_p["RVel"], rtol=1e-10)
+    assert np.array_equal(old_r.keylines()["m_id_f"], old_p.keylines()["m_id_f"])
+    # ExtRotVel on the forward matches (the port's elimination solve stands in for SVD<>)
+    assert old_r.forward_match(new_r) == old_p.forward_match(new_p) > 50
+    ok_r, Wx_r, Rx_r, X_r = new_r.ext_rot_vel(m_r["V"], 1.0, 2.0)
+    ok_p, Wx_p, Rx_p, X_p = new_p.ext_rot_vel(m_r["V"], 1.0, 2.0)
+    assert ok_r and ok_p
+    assert np.allclose(Wx_r, Wx_p, rtol=1e-12, atol=1e-12 * np.abs(Wx_r).max())
+    assert np.allclose(X_r, X_p, rtol=1e-7, atol=1e-9 * np.abs(X_r).max())
+    assert np.allclose(Rx_r, Rx_p, rtol=1e-7, atol=1e-9 * np.abs(Rx_r).max())
+    # BiasCorrect
+    R = refapi.lib()
+    _p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for _ in range(5):
+        J = rng.normal(size=(30, 6))
+        Wx = J.T @ J + np.eye(6)
+        X = rng.normal(size=6) * 1e-2
+        Gb = rng.normal(size=3) * 1e-3
+        A = rng.normal(size=(3, 3))
+        Wb = A @ A.T + np.eye(3) * 10
+        Rg = np.ascontiguousarray(np.eye(3) * 1e-4 + 1e-6 * (A @ A.T))
+        Rb = np.ascontiguousarray(np.eye(3) * 1e-8)
+        b = [np.ascontiguousarray(v.copy()) for v in (X, Wx, Gb, Wb)]
+        R.ref_bias_correct(_p(b[0]), _p(b[1]), _p(b[2]), _p(b[3]), _p(Rg), _p(Rb))
+        a = portapi.bias_correct(X, Wx, Gb, Wb, Rg, Rb)
+        for x, y in zip(a, b):
+            assert np.allclose(x, y, rtol=1e-11, atol=1e-14 * max(1.0, np.abs(y).max()))
+
