@@ -308,7 +308,42 @@ RB_HD void solve_sym6_like_svd(const double *ApI, const double *rhs, double *h) 
     }
 }
 
-// util::Matrix3x3Inv (include/UtilLib/toon_util.h:32-41)
+// TooN::determinant of a 3x3 (TooN/determinant.h:91-146, determinant_gaussian_elimination): partial pivoting, running
+// product of the pivots -- not the cofactor expansion, and the last bits differ
+RB_HD double det3_toon(const double *Ain) {
+    double A[3][3];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) A[i][j] = Ain[i * 3 + j];
+    double det = 1;
+    for (int i = 0; i < 3; i++) {
+        int argmax = i;
+        double maxval = fabs(A[i][i]);
+        for (int ii = i + 1; ii < 3; ii++) {
+            const double v = fabs(A[ii][i]);
+            if (v > maxval) {
+                maxval = v;
+                argmax = ii;
+            }
+        }
+        const double pivot = A[argmax][i];
+        if (argmax != i) {
+            det *= -1;
+            for (int j = i; j < 3; j++) {
+                const double t = A[i][j];
+                A[i][j] = A[argmax][j];
+                A[argmax][j] = t;
+            }
+        }
+        det *= A[i][i];
+        if (det == 0) return 0;
+        for (int u = i + 1; u < 3; u++) {
+            const double factor = A[u][i] / pivot;
+            for (int j = i + 1; j < 3; j++) A[u][j] = A[u][j] - factor * A[i][j];
+        }
+    }
+    return det;
+}
+// util::Matrix3x3Inv (include/UtilLib/toon_util.h:32-41): cofactors / TooN::determinant
 RB_HD void mat3_inv(const double *A, double *B) {
     double t[9];
     t[0] = A[8] * A[4] - A[7] * A[5];
@@ -320,7 +355,6 @@ RB_HD void mat3_inv(const double *A, double *B) {
     t[6] = A[7] * A[3] - A[6] * A[4];
     t[7] = -(A[7] * A[0] - A[6] * A[1]);
     t[8] = A[4] * A[0] - A[3] * A[1];
-    const double det = A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) +
-                       A[2] * (A[3] * A[7] - A[4] * A[6]);
+    const double det = det3_toon(A);
     for (int i = 0; i < 9; i++) B[i] = t[i] / det;
 }
