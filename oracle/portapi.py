@@ -191,3 +191,13 @@ def bias_correct(X, Wx, Gb, Wb, Rg, Rb):
     lib().orc_bias_correct(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(Rg), _p(Rb))
     return a
 
+
+def undistort_rgb(cam, kc, rgb):
+    """image_undistort(cam).undistort<true>(out, in) restated, one RGB24 frame."""
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    out = np.zeros_like(rgb)
+    kc = np.ascontiguousarray(kc, np.float64)
+    lib().orc_undistort_rgb(cam["w"], cam["h"], C.c_float(cam["ppx"]), C.c_float(cam["ppy"]), C.c_float(cam["zfx"]),
+                            C.c_float(cam["zfy"]), _p(kc), _p(rgb), _p(out))
+    return out
+

@@ -1448,4 +1448,66 @@ void orc_bias_correct(double *X, double *Wx, double *Gb, double *Wb, const doubl
     for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++) Wx[(3 + r) * 6 + 3 + c] += Wg[r * 3 + c];
 }
+
+// =====================================================================================================
+// image_undistort: constructor map (src/VideoLib/image_undistort.cpp:29-94) with
+// cam_model::distortHom2Hom (include/UtilLib/cam_model.h:77-88), then undistort<true> on RGB24 through
+// biInterp (include/VideoLib/image_undistort.h:63-78).  kc = {Kc2, Kc4, Kc6, P1, P2}.
+// =====================================================================================================
+static bool und_inx_valid(float fx, float fy, int w, int h) {
+    // Image::isInxValid takes `const uint&`: the float argument converts to unsigned (x86-64 cvttss2si to 64 bit, low
+    // half kept), so negative coordinates become huge and fail the bound
+    const unsigned x = (unsigned)(long long)fx, y = (unsigned)(long long)fy;
+    return x < (unsigned)w && y < (unsigned)h;
+}
+void orc_undistort_rgb(int w, int h, float ppx, float ppy, float zfx, float zfy, const double *kc,
+                       const unsigned char *in, unsigned char *out) {
+    const double zfm = (double)((zfx + zfy) / 2);   // cam_model: zfm((focal_dist.x+focal_dist.y)/2) in float
+    const double Kc2 = kc[0], Kc4 = kc[1], Kc6 = kc[2], P1 = kc[3], P2 = kc[4];
+    const float i_mult = (float)(1 << 16);
+    for (int x = 0; x < w; x++)
+        for (int y = 0; y < h; y++) {
+            float qx = (float)x - ppx, qy = (float)y - ppy;   // cam.Img2Hom(Point2D<float>(x,y))
+            {
+                const double xp = qx / zfm, yp = qy / zfm;
+                const double r2 = xp * xp + yp * yp;
+                const double xpp = xp * (1 + r2 * (Kc2 + r2 * (Kc4 + r2 * Kc6))) + 2 * P1 * xp * yp + P2 * (r2 + 2 * xp * xp);
+                const double ypp = yp * (1 + r2 * (Kc2 + r2 * (Kc4 + r2 * Kc6))) + P1 * (r2 + 2 * yp * yp) + 2 * P2 * xp * yp;
+                qx = xpp * zfx;
+                qy = ypp * zfy;
+            }
+            const float idx = qx + ppx, idy = qy + ppy;       // cam.Hom2Img(qd)
+            const float p00x = floor(idx), p00y = floor(idy), p11x = floor(idx) + 1, p11y = floor(idy) + 1;
+            const float tx[4] = {p00x, p11x, p00x, p11x}, ty[4] = {p00y, p00y, p11y, p11y};
+            const float tw[4] = {(p11x - idx) * (p11y - idy), (idx - p00x) * (p11y - idy), (p11x - idx) * (idy - p00y),
+                                 (idx - p00x) * (idy - p00y)};
+            int num = 0, inx[4], iw[4];
+            float wgt[4];
+            for (int k = 0; k < 4; k++)
+                if (und_inx_valid(tx[k], ty[k], w, h)) {
+                    wgt[num] = tw[k];
+                    inx[num] = index_rc(tx[k], ty[k], w, h);
+                    num++;
+                }
+            if (num > 0) {
+                float sum_w = 0;
+                for (int i = 0; i < num; i++) sum_w += wgt[i];
+                for (int i = 0; i < num; i++) {
+                    wgt[i] /= sum_w;
+                    iw[i] = wgt[i] * i_mult;
+                }
+            }
+            int r = 0, g = 0, b = 0;                          // biInterp(Image<RGB24Pixel>&, inx)
+            for (int i = 0; i < num; i++) {
+                const unsigned char *p = in + 3 * (size_t)inx[i];
+                r += iw[i] * p[0];
+                g += iw[i] * p[1];
+                b += iw[i] * p[2];
+            }
+            unsigned char *o = out + 3 * ((size_t)y * w + x);   // umap(x,y) -> out[inx]
+            o[0] = (unsigned char)(r >> 16);
+            o[1] = (unsigned char)(g >> 16);
+            o[2] = (unsigned char)(b >> 16);
+        }
+}
 }  // extern "C"

@@ -179,3 +179,20 @@ def test_port_imu_rows_match_reference():
         for x, y in zip(a, b):
             assert np.allclose(x, y, rtol=1e-11, atol=1e-14 * max(1.0, np.abs(y).max()))
 
+
+def test_port_undistort_matches_reference():
+    """image_undistort map + integer bilinear interpolation, bit for bit, with EuRoC-like and
+    exaggerated distortion coefficients (taps that leave the image drop out of the weights)."""
+    from oracle import portapi, refapi
+    if not refapi.available():
+        pytest.skip("oracle/_ref not built")
+    cam = dict(w=320, h=240, zfx=260.0, zfy=258.0, ppx=161.0, ppy=118.5)
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, (cam["h"], cam["w"], 3), dtype=np.uint8)
+    for kc in ([-0.28340811, 0.07395907, 0.0, 0.00019359, 1.76187114e-05], [-0.6, 0.3, -0.05, 0.01, -0.02],
+               [0.0, 0.0, 0.0, 0.0, 0.0]):
+        a = refapi.undistort_rgb(cam, kc, img)
+        b = portapi.undistort_rgb(cam, kc, img)
+        assert np.array_equal(a, b), "differs in %d bytes" % int((a != b).sum())
+    assert not np.array_equal(refapi.undistort_rgb(cam, [-0.6, 0.3, -0.05, 0.01, -0.02], img), img)
+
