@@ -240,6 +240,14 @@ def undistort_rgb(cam, kc, rgb):
     return out
 
 
+def bias_correct(X, Wx, Gb, Wb, Rg, Rb):
+    """edge_tracker::BiasCorrect of the reference (in/out arrays)."""
+    a = [np.ascontiguousarray(np.array(v, np.float64)) for v in (X, Wx, Gb, Wb)]
+    Rg, Rb = np.ascontiguousarray(Rg, np.float64), np.ascontiguousarray(Rb, np.float64)
+    lib().ref_bias_correct(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(Rg), _p(Rb))
+    return a
+
+
 def so3_exp(w):
     w = np.ascontiguousarray(w, np.float64)
     R = np.zeros((3, 3))

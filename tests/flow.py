@@ -132,3 +132,53 @@ def compare(ref, got, tol_keys=(), rtol=1e-9, loose=()):
             if not same:
                 fails.append("%s differs in %d elements" % (k, int((a != b).sum())))
     return fails
+
+
+def run_imu_rows(Map, api, cfg, f0, f1, keylines=None):
+    """IMU-mode rows + undistort (8(f) rank 1) on the same frame pair.  `api` is the module
+    that owns Map (oracle.refapi / oracle.portapi): it provides undistort_rgb and bias_correct.  keylines: optional
+    (old, new, masks, retuned) taken from the golden file so that a map class without a detector pass can be fed."""
+    cam = cfg["cam"]
+    old, new = [Map(cam["w"], cam["h"], cam["ppx"], cam["ppy"], cam["zfx"], cam["zfy"], cfg["sigma0"], cfg["ksigma"])
+                for _ in range(2)]
+    out = {}
+    if keylines is None:
+        t, l, rt = cfg["thresh"], 0, []
+        for m, fr in ((old, f0), (new, f1)):
+            m.rgb2bw(fr)
+            m.build()
+            _, t, l = m.detect(PLANE_FIT, POS_NEG, DOG_THRESH, cfg["kl_max"], t, l, cfg["kl_ref"], cfg["gain"],
+                               cfg["tmax"], cfg["tmin"])
+            rt.append(m.reestimate(cfg["track_points"], 100)[1])
+        old.set_keylines(seed_depth(old.keylines()))
+    else:
+        k_old, k_new, m_old, m_new, rt = keylines
+        old.set_keylines(k_old)
+        old.set_mask(m_old)
+        new.set_keylines(k_new)
+        new.set_mask(m_new)
+    out["imu_old_kl"], out["imu_new_kl"] = old.keylines(), new.keylines()
+    out["imu_old_mask"], out["imu_new_mask"] = old.mask(), new.mask()
+    out["imu_retuned"] = np.array(rt, np.float32)
+    new.build_field(cfg["radius"], float(rt[1]))
+    q = old.quantile(1e-3, 20.0, 0.9, 100)
+    res = np.zeros(old.knum())
+    for vi, V in enumerate((np.zeros(3), np.array([0.004, -0.003, 0.005]), np.array([-0.006, 0.002, -0.55]))):
+        s, J, F, res = new.try_vel(old, V, cfg["match_thresh"], q, 0, res, cfg["reweight"], float(rt[0]))
+        out["tv%d_score" % vi], out["tv%d_JtJ" % vi], out["tv%d_JtF" % vi] = np.array([s]), J, F
+        out["tv%d_res" % vi], out["tv%d_m_id_f" % vi] = res.copy(), old.keylines()["m_id_f"].copy()
+    mv = new.minimizer_v(old, np.zeros(3), cfg["match_thresh"], 5, q, 0, cfg["reweight"], float(rt[0]))
+    out["mv_V"], out["mv_RVel"], out["mv_F"] = np.array(mv["V"]), np.array(mv["RVel"]), np.array([mv["F"]])
+    out["mv_m_id_f"] = old.keylines()["m_id_f"].copy()
+    out["er_nfwd"] = np.array([old.forward_match(new)])
+    ok, Wx, Rx, X = new.ext_rot_vel(out["mv_V"], cfg["loc_unc"], cfg["reweight"])
+    out["er_ok"], out["er_Wx"], out["er_Rx"], out["er_X"] = np.array([int(ok)]), Wx, Rx, X
+    rng = np.random.default_rng(4)
+    Jm = rng.normal(size=(30, 6))
+    A = rng.normal(size=(3, 3))
+    bc = api.bias_correct(rng.normal(size=6) * 1e-2, Jm.T @ Jm + np.eye(6), rng.normal(size=3) * 1e-3,
+                          A @ A.T + np.eye(3) * 10, np.eye(3) * 1e-4 + 1e-6 * (A @ A.T), np.eye(3) * 1e-8)
+    out["bc_X"], out["bc_Wx"], out["bc_Gb"], out["bc_Wb"] = bc
+    out["und"] = api.undistort_rgb(cam, [-0.28340811, 0.07395907, 0.0, 0.00019359, 1.76187114e-05], f0)
+    return out
+

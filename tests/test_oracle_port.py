@@ -10,7 +10,7 @@ import pytest
 
 import ctypes as C
 
-from flow import DOG_THRESH, PLANE_FIT, POS_NEG, SMALL, compare, run_flow, small_frames
+from flow import DOG_THRESH, PLANE_FIT, POS_NEG, SMALL, compare, run_flow, run_imu_rows, small_frames
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "flow_small.npz")
 TOL = ("min_V", "min_W", "min_RVel", "min_RW0", "min_W_X", "min_scalars")
@@ -195,4 +195,54 @@ def test_port_undistort_matches_reference():
         b = portapi.undistort_rgb(cam, kc, img)
         assert np.array_equal(a, b), "differs in %d bytes" % int((a != b).sum())
     assert not np.array_equal(refapi.undistort_rgb(cam, [-0.6, 0.3, -0.05, 0.01, -0.02], img), img)
+
+
+GOLD_IMU = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "imu_small.npz")
+# bit-exact unless listed: the port's 3x3 / 6x6 solves are restatements of TooN's (1e-12) or stand-ins for SVD<> (1e-7)
+IMU_TOL = {"mv_V": 1e-11, "mv_RVel": 1e-9, "mv_F": 1e-11, "er_Rx": 1e-7, "er_X": 1e-7, "er_Wx": 1e-12, "bc_X": 1e-11,
+           "bc_Wx": 1e-11, "bc_Gb": 1e-11, "bc_Wb": 1e-11}
+
+
+def _check_imu(out, gold):
+    fails = []
+    for k in gold:
+        a, b = gold[k], out[k]
+        if k in IMU_TOL:
+            if not np.allclose(a, b, rtol=IMU_TOL[k], atol=IMU_TOL[k] * max(1e-300, float(np.abs(a).max()))):
+                fails.append("%s: max abs diff %.3e" % (k, float(np.abs(a - b).max())))
+        elif a.dtype.names:
+            for f in a.dtype.names:
+                if not np.array_equal(a[f], b[f]):
+                    fails.append("%s.%s differs" % (k, f))
+        elif not np.array_equal(a, b):
+            fails.append("%s differs in %d entries" % (k, int((a != b).sum())))
+    return fails
+
+
+def test_port_imu_rows_match_golden():
+    """The IMU-mode rows and the undistortion of the port against vectors generated from the unmodified reference
+    (tests/golden/make_golden.py): runs everywhere, with or without oracle/_ref."""
+    from oracle import portapi
+    z = np.load(GOLD_IMU)
+    gold = {k: z[k] for k in z.files}
+    f0, f1 = small_frames()
+    kls = (gold["imu_old_kl"], gold["imu_new_kl"], gold["imu_old_mask"], gold["imu_new_mask"], gold["imu_retuned"])
+    out = run_imu_rows(portapi.PortMap, portapi, SMALL, f0, f1, keylines=kls)
+    fails = _check_imu(out, gold)
+    assert not fails, "\n".join(fails)
+    assert int(gold["er_nfwd"][0]) > 500 and int(gold["er_ok"][0]) == 1
+
+
+def test_reference_imu_rows_match_golden():
+    from oracle import refapi
+    if not refapi.available():
+        pytest.skip("oracle/_ref not built")
+    z = np.load(GOLD_IMU)
+    gold = {k: z[k] for k in z.files}
+    f0, f1 = small_frames()
+    out = run_imu_rows(refapi.RefMap, refapi, SMALL, f0, f1)
+    for k in gold:
+        a, b = gold[k], out[k]
+        same = all(np.array_equal(a[f], b[f]) for f in a.dtype.names) if a.dtype.names else np.array_equal(a, b)
+        assert same, k
 
