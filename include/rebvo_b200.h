@@ -120,6 +120,10 @@ int64_t rb_ctx_launch_count(const rb_ctx *c);
 /* ---- edge map (ring slot) ---------------------------------------------------------------------- */
 int rb_map_create(rb_ctx *c, rb_map **out);
 void rb_map_destroy(rb_map *m);
+/* edge_finder(const edge_finder&) + global_tracker(const global_tracker&) (edge_finder.cpp:42-52,
+ * global_tracker.cpp:42-47; used by keyframe, keyframe.cpp:28-35): a new map holding a device-side copy of the
+ * keylines, id mask, match field (+ radius) and FrameCount of src */
+int rb_map_clone(const rb_map *src, rb_map **out);
 
 /* Image<float>::ConvertRGB2BW (image.h:197-203) after the H2D copy of the RGB24 frame */
 int rb_map_upload_rgb(rb_map *m, const uint8_t *rgb);

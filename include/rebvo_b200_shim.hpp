@@ -175,7 +175,13 @@ class edge_finder {
                                            "as REBVO::construct does (rebvo.cpp:299-300)");
         if (dev->ok()) dev->check(rb_map_create(dev->ctx, &map));
     }
-    edge_finder(const edge_finder &) = delete;  // keyframes (out of scope) deep-copy maps
+    // edge_finder.cpp:42-52 (keyframes deep-copy an edge map, keyframe.cpp:28-35): device-side clone of keylines, mask
+    // and, because the match field lives in the same ring-slot object here, of global_tracker's field as well
+    edge_finder(const edge_finder &o)
+        : cam_mod(o.cam_mod), dev(o.dev), host_valid(false), kn(o.kn), reTunedThresh(o.reTunedThresh) {
+        if (o.map && dev && dev->ok()) dev->check(rb_map_clone(o.map, &map));
+    }
+    edge_finder &operator=(const edge_finder &) = delete;
     ~edge_finder() {
         if (map) rb_map_destroy(map);
     }

@@ -57,7 +57,7 @@ KEYLINE = np.dtype({
 
 # every symbol include/rebvo_b200.h declares
 SYMBOLS = ["rb_ctx_create", "rb_ctx_destroy", "rb_last_error", "rb_ctx_sync", "rb_ctx_box_plan",
-           "rb_ctx_launch_count", "rb_map_create", "rb_map_destroy", "rb_map_upload_rgb", "rb_map_upload_gray",
+           "rb_ctx_launch_count", "rb_map_create", "rb_map_destroy", "rb_map_clone", "rb_map_upload_rgb", "rb_map_upload_gray",
            "rb_map_dog_build", "rb_map_get_plane", "rb_map_detect", "rb_map_detect_ss", "rb_map_reestimate_thresh", "rb_map_knum",
            "rb_map_sync_host_keylines", "rb_map_load_keylines", "rb_map_get_mask", "rb_map_quantile",
            "rb_map_build_field", "rb_map_get_field", "rb_try_vel_rot", "rb_minimizer_rv", "rb_forward_match",
@@ -196,6 +196,13 @@ class Map:
         if self.h_ and self.owned:
             self.L.rb_map_destroy(self.h_)
         self.h_ = None
+
+    def clone(self):
+        h = C.c_void_p()
+        self.ctx.check(self.L.rb_map_clone(self.h_, C.byref(h)))
+        m = Map(self.ctx, h)
+        m.owned = True
+        return m
 
     def upload_rgb(self, rgb):
         rgb = np.ascontiguousarray(rgb, np.uint8)

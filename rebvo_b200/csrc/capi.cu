@@ -308,6 +308,48 @@ extern "C" int rb_map_create(rb_ctx *c, rb_map **out) {
     return rb_map_alloc(c, out, true);
 }
 
+// edge_finder(const edge_finder&) + global_tracker(const global_tracker&) (edge_finder.cpp:42-52,
+// global_tracker.cpp:42-47): a new ring-slot-like object holding a copy of the keylines, the id mask, the match field
+// (+ its search radius) and FrameCount.  Device-to-device copies on the context's stream; scale-space planes and the
+// minimiser scratch are not part of the reference's copy either.
+extern "C" int rb_map_clone(const rb_map *src, rb_map **out) {
+    if (!src || !out) return RB_ERR_ARG;
+    rb_ctx *c = src->c;
+    int r = rb_map_alloc(c, out, false);
+    if (r) return r;
+    rb_map *m = *out;
+    const size_t N = c->N, K = c->kcap + 32;
+    const KLSoA &a = src->kl;
+    KLSoA &b = m->kl;
+#define CP(dst, srcp, bytes) RB_CUDA(cudaMemcpyAsync(dst, srcp, bytes, cudaMemcpyDeviceToDevice, c->stream))
+    CP(m->mask, src->mask, sizeof(int) * N);
+    CP(m->field, src->field, sizeof(unsigned long long) * N);
+    CP(b.p_inx, a.p_inx, sizeof(int) * K);
+    CP(b.m_m, a.m_m, sizeof(float2) * K);
+    CP(b.u_m, a.u_m, sizeof(float2) * K);
+    CP(b.c_p, a.c_p, sizeof(float2) * K);
+    CP(b.p_m, a.p_m, sizeof(float2) * K);
+    CP(b.p_m_0, a.p_m_0, sizeof(float2) * K);
+    CP(b.m_m0, a.m_m0, sizeof(float2) * K);
+    CP(b.n_m, a.n_m, sizeof(float) * K);
+    CP(b.rho, a.rho, sizeof(double) * K);
+    CP(b.s_rho, a.s_rho, sizeof(double) * K);
+    CP(b.rho0, a.rho0, sizeof(double) * K);
+    CP(b.s_rho0, a.s_rho0, sizeof(double) * K);
+    CP(b.n_m0, a.n_m0, sizeof(double) * K);
+    CP(b.m_id, a.m_id, sizeof(int) * K);
+    CP(b.m_id_f, a.m_id_f, sizeof(int) * K);
+    CP(b.m_num, a.m_num, sizeof(int) * K);
+    CP(b.p_id, a.p_id, sizeof(int) * K);
+    CP(b.n_id, a.n_id, sizeof(int) * K);
+    CP(b.pack, a.pack, sizeof(float4) * 2 * K);
+    CP(m->st, src->st, sizeof(MapState));
+#undef CP
+    m->field_radius = src->field_radius;
+    RB_CUDA(cudaStreamSynchronize(c->stream));
+    return RB_OK;
+}
+
 extern "C" void rb_map_destroy(rb_map *m) {
     if (!m) return;
     rb_ctx *c = m->c;

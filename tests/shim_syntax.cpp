@@ -1,4 +1,4 @@
-// compile-only: instantiate the IMU-mode mirrors of the shim
+// compile-only: instantiate the IMU-mode mirrors and the copy constructors of the shim
 #include <rebvo_b200_shim.hpp>
 using namespace rebvo;
 void instantiate(global_tracker &gt, edge_tracker &a) {
@@ -11,4 +11,10 @@ void instantiate(global_tracker &gt, edge_tracker &a) {
     gt.Minimizer_V<float>(V, R, a, 0.5f, 5, 1.0f, 2u, 1.0, 0.f);
     a.ExtRotVel(V, Wx, Rx, X, 1.0, 1.0);
     edge_tracker::BiasCorrect(X, Wx, Gb, Wb, R, R);
+    // keyframe.cpp:28-35: deep copies of the edge map and its tracker
+    edge_tracker *copy = new edge_tracker(a);
+    global_tracker *gcopy = new global_tracker(gt);
+    gcopy->SetEdgeTracker(copy);
+    delete gcopy;
+    delete copy;
 }
