@@ -195,8 +195,7 @@ __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.laun
 template <typename... KArgs, typename... Args>
 static inline cudaError_t rb_klaunch(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                      cudaStream_t stream, Args... args) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;

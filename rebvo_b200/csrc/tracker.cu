@@ -2004,8 +2004,7 @@ __global__ void __cluster_dims__(MU_C, 1, 1) __launch_bounds__(MU_T) k_map_updat
 }
 
 static int launch_map_update(rb_ctx *c, rb_map *m, const MapUpdArgs &a) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(MU_C);
     cfg.blockDim = dim3(MU_T);
     cfg.stream = c->stream;
