@@ -163,7 +163,9 @@ def run_imu_rows(Map, api, cfg, f0, f1, keylines=None):
     new.build_field(cfg["radius"], float(rt[1]))
     q = old.quantile(1e-3, 20.0, 0.9, 100)
     res = np.zeros(old.knum())
-    for vi, V in enumerate((np.zeros(3), np.array([0.004, -0.003, 0.005]), np.array([-0.006, 0.002, -0.55]))):
+    # the last velocity drives 1/rho + Vz negative for the nearer keylines (TryVel's z_p <= 0 branch)
+    for vi, V in enumerate((np.zeros(3), np.array([0.004, -0.003, 0.005]), np.array([-0.006, 0.002, -0.55]),
+                            np.array([0.001, 0.0, -0.7]))):
         s, J, F, res = new.try_vel(old, V, cfg["match_thresh"], q, 0, res, cfg["reweight"], float(rt[0]))
         out["tv%d_score" % vi], out["tv%d_JtJ" % vi], out["tv%d_JtF" % vi] = np.array([s]), J, F
         out["tv%d_res" % vi], out["tv%d_m_id_f" % vi] = res.copy(), old.keylines()["m_id_f"].copy()

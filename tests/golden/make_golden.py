@@ -25,5 +25,5 @@ if __name__ == "__main__":
     print("kn:", out["f0_kn_tresh"], out["f1_kn_tresh"], "dm:", out["dm_count"], "min V:", out["min_V"])
     imu = run_imu_rows(refapi.RefMap, refapi, SMALL, f0, f1)
     np.savez_compressed(os.path.join(HERE, "imu_small.npz"), **imu)
-    print("wrote imu_small.npz: TryVel scores", [float(imu["tv%d_score" % i][0]) for i in range(3)], "Minimizer_V",
+    print("wrote imu_small.npz: TryVel scores", [float(imu["tv%d_score" % i][0]) for i in range(4)], "Minimizer_V",
           imu["mv_V"], "forward matches", imu["er_nfwd"], "ExtRotVel X", imu["er_X"])
