@@ -168,6 +168,8 @@ extern "C" int rb_ctx_create(rb_ctx **out, int device, const rb_camera *cam, dou
         c->pdl = !(pd && atoi(pd) == 0);
         const char *mp = getenv("REBVO_B200_MIN_PERSIST");
         c->min_persist = !(mp && atoi(mp) == 0);
+        const char *mc = getenv("REBVO_B200_MIN_CLUSTER");
+        c->min_cluster = !(mc && atoi(mc) == 0);
         const char *rs = getenv("REBVO_B200_ROWSCAN");
         c->rowscan_mode = rs ? atoi(rs) : 2;   // cp.async ring measured 1.85x faster than register prefetch
     }
@@ -194,6 +196,7 @@ extern "C" int rb_ctx_create(rb_ctx **out, int device, const rb_camera *cam, dou
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     c->min_resident = rb_minimizer_resident_blocks(c->sm_count);
+    rb_minimizer_cluster_setup(c);
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->nseg = c->h * rb_div_up(c->w, 32);
     CK(cudaMalloc(&c->seg_cnt, sizeof(int) * c->nseg));

@@ -94,6 +94,10 @@ struct rb_ctx {
     bool pdl;            // programmatic dependent launch of the per-frame chain (env REBVO_B200_PDL=0 disables)
     bool min_persist;    // whole Minimizer_RV in one persistent launch (env REBVO_B200_MIN_PERSIST=0 disables)
     int min_resident;    // blocks of that kernel the device keeps resident at once
+    bool min_cluster;    // Minimizer_RV in one 16-CTA cluster (min_cluster.cuh); env REBVO_B200_MIN_CLUSTER=0 disables
+    int min_cluster_kpc; // keylines per CTA its shared memory is sized for (0: not available on this device / capacity)
+    size_t min_cluster_dyn;
+    int min_cluster_xchg; // 1: st.async + mbarrier exchange, 0: DSMEM stores + barrier.cluster (env REBVO_B200_MIN_XCHG)
     int rowscan_mode;    // env REBVO_B200_ROWSCAN: 1 = register-prefetch kernel, 2 = cp.async shared-memory ring
 };
 // layout of rb_ctx::dev_small / pinned (byte offsets)

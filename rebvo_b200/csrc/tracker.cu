@@ -384,7 +384,7 @@ __device__ void lm_finalize(LMState &s, MapState *fst) {   // :793-816; RVel / R
         s.rel_error_score = 1e20;
     }
     s.score = s.F;
-    fst->frame_count = fst->frame_count + 1;   // FrameCount++
+    if (fst) fst->frame_count = fst->frame_count + 1;   // FrameCount++ (one CTA of the cluster kernel does it)
 }
 
 __device__ __noinline__ void lm_step(LMState &s, int step, MapState *fst) {
@@ -653,7 +653,7 @@ __device__ __forceinline__ void tvr_body(const KlOp &o, bool has_rin, double r_p
         if (x < 1 || y < 1 || x >= cam.w - 1 || y >= cam.h - 1) {               // :376
             f = max_r;
             if (RW) f *= weight;
-            rout[i] = max_r;
+            if (rout) rout[i] = max_r;   // (the cluster kernel keeps the residual buffers in shared memory: rout == nullptr)
             wrote = true;
             r_w = max_r;
         } else {
@@ -689,7 +689,7 @@ __device__ __forceinline__ void tvr_body(const KlOp &o, bool has_rin, double r_p
             }
         }
     }
-    m_id_f[i] = mid_f;
+    if (m_id_f) m_id_f[i] = mid_f;   // only the last evaluation of a minimisation is visible afterwards
     // Jacobians (:419-449) and the 1/q_rho scaling (:452-463)
     const double qvel = (cam.zfm * dfx * sV[0] + cam.zfm * dfy * sV[1]) + (qx * dfx + qy * dfy) * sV[2];
     double q_rho = sqrt(o.s_rho * qvel * o.s_rho * qvel + 1);
@@ -1269,6 +1269,8 @@ __global__ void __launch_bounds__(TVR_T, 2) k_minimizer_persist(KLSoA old, const
 #endif
 }
 
+#include "min_cluster.cuh"
+
 static TrackPtrs track_ptrs(const rb_map *fmap) {
     TrackPtrs tp;
     tp.lm = &fmap->ts->lm;
@@ -1295,6 +1297,70 @@ static int launch_eval_step(rb_ctx *c, rb_map *fmap, rb_map *old, int step) {
     if (step >= STEP_MAIN_FIRST) return launch_eval<true, true>(c, fmap, old, step);
     if (step == STEP_INIT_LAST_ZERO || step == STEP_INIT_LAST_PRIOR) return launch_eval<false, false>(c, fmap, old, step);
     return launch_eval<false, true>(c, fmap, old, step);
+}
+
+// per-device set-up of the cluster minimiser (rb_ctx_create, after cudaSetDevice): opt-ins + how many keylines per CTA
+// fit.  Leaves c->min_cluster_kpc = 0 when the device cannot run it (the one-launch-per-evaluation path serves then).
+int rb_minimizer_cluster_setup(rb_ctx *c) {
+    c->min_cluster_kpc = 0;
+    const char *xe = getenv("REBVO_B200_MIN_XCHG");
+    c->min_cluster_xchg = xe ? atoi(xe) : 1;
+    int dev_max = 0;
+    if (cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device) != cudaSuccess) return RB_OK;
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, k_minimizer_cluster<1>) != cudaSuccess) {
+        cudaGetLastError();
+        return RB_OK;
+    }
+    int kpc = (c->kcap + MC_C - 1) / MC_C;
+    kpc = (kpc + 31) & ~31;
+    const size_t dyn = (size_t)kpc * MC_BYTES_PER_KL + 64;
+    if (kpc > MC_T * MC_MAXJ || dyn + fa.sharedSizeBytes > (size_t)dev_max) return RB_OK;
+    bool ok = true;
+    ok = ok && cudaFuncSetAttribute(k_minimizer_cluster<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_minimizer_cluster<0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_minimizer_cluster<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_minimizer_cluster<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) == cudaSuccess;
+    if (ok) {   // can the device place one such cluster at all?
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(MC_C);
+        cfg.blockDim = dim3(MC_T);
+        cfg.dynamicSmemBytes = dyn;
+        int ncl = 0;
+        ok = cudaOccupancyMaxActiveClusters(&ncl, k_minimizer_cluster<1>, &cfg) == cudaSuccess && ncl >= 1;
+    }
+    if (!ok) {
+        cudaGetLastError();
+        return RB_OK;
+    }
+    c->min_cluster_kpc = kpc;
+    c->min_cluster_dyn = dyn;
+    return RB_OK;
+}
+
+static int launch_minimizer_cluster(rb_ctx *c, rb_map *fmap, rb_map *old, const McPlan &plan, const MinSetup &su,
+                                    FrameState *post_fs) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(MC_C);
+    cfg.blockDim = dim3(MC_T);
+    cfg.dynamicSmemBytes = c->min_cluster_dyn;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = c->pdl ? 1 : 0;
+    c->launches++;
+    auto kern = c->min_cluster_xchg ? k_minimizer_cluster<1> : k_minimizer_cluster<0>;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, old->kl, (const MapState *)old->st,
+                                             (const unsigned long long *)fmap->field, (const float4 *)fmap->kl.pack,
+                                             fmap->st, &fmap->ts->lm, &fmap->ts_host.ctl->abort, make_cam(c), plan, su,
+                                             post_fs, c->min_cluster_kpc);
+    if (e != cudaSuccess) {
+        snprintf(c->err, sizeof(c->err), "Minimizer_RV cluster launch: %s", cudaGetErrorString(e));
+        return RB_ERR_CUDA;
+    }
+    return RB_OK;
 }
 
 // how many 256-thread blocks of the persistent kernel the device keeps resident at once
@@ -1327,6 +1393,34 @@ int rb_minimizer_enqueue(rb_ctx *c, rb_map *fmap, rb_map *old, const double *VW_
     steps[ns++] = STEP_MAIN_FIRST;
     for (int j = 0; j < m; j++) steps[ns++] = j == m - 1 ? STEP_MAIN_LAST : STEP_MAIN_ITER;
     int r;
+    if (c->min_persist && c->min_cluster && c->min_cluster_kpc > 0 && ns <= MIN_MAX_EVALS) {
+        // rounds of the cluster kernel: the two init tries of type 2 share their rounds
+        McPlan plan;
+        memset(&plan, 0, sizeof(plan));
+        plan.merge_round = -1;
+        int k = 0;
+        if (a->init_type != 0 && a->init_type != 1) {
+            for (int i = 0; i <= n; i++, k++) {
+                plan.sa[k] = i == 0 ? STEP_INIT_FIRST_ZERO : i == n ? STEP_INIT_LAST_ZERO : STEP_INIT_ITER_ZERO;
+                plan.sb[k] = i == 0 ? STEP_INIT_FIRST_PRIOR : i == n ? STEP_INIT_LAST_PRIOR : STEP_INIT_ITER_PRIOR;
+            }
+            plan.merge_round = k - 1;
+        }
+        plan.sb[k++] = STEP_MAIN_FIRST;
+        for (int j = 0; j < m; j++) plan.sb[k++] = j == m - 1 ? STEP_MAIN_LAST : STEP_MAIN_ITER;
+        plan.n = k;
+        MinSetup su;
+        su.a = *a;
+        su.max_r = (double)fmap->field_radius;
+        su.max_s_rho = max_s_rho;
+        su.VW = VW_dev;
+        su.frame_count = frame_count;
+        su.s_rho_from_state = s_rho_from_state ? 1 : 0;
+        su.fc_from_state = fc_from_state ? 1 : 0;
+        if ((r = launch_minimizer_cluster(c, fmap, old, plan, su, post_fs))) return r;
+        if (post_folded) *post_folded = post_fs != nullptr;
+        return RB_OK;
+    }
     if (c->min_persist && ns <= MIN_MAX_EVALS && nblk <= c->min_resident) {
         MinPlan plan;
         memset(&plan, 0, sizeof(plan));

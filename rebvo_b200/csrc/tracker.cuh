@@ -23,6 +23,7 @@ struct MinCtl {
 };
 
 int rb_minimizer_resident_blocks(int sm_count);
+int rb_minimizer_cluster_setup(rb_ctx *c);
 int rb_track_state_alloc(rb_ctx *c, rb_map *m);
 void rb_track_state_free(rb_map *m);
 

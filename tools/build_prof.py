@@ -1,9 +1,9 @@
 """Build the profiling variant of the library (-DRB_TVR_PROF: clock64 stamps in the minimiser, %globaltimer marker kernels
 in the pipeline) into tools/_prof/ (git-ignored).  Used by minimiser_stamps.py and trace_run.py on a GPU box."""
 import os, subprocess, sys
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rebvo_b200 import build as B
-out = '/root/repo/tools/_prof'
+out = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_prof')
 os.makedirs(out, exist_ok=True)
 objs = []
 for s in B.SOURCES:

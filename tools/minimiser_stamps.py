@@ -1,6 +1,6 @@
 import os, sys, ctypes as C
 import numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ["REBVO_B200_NO_GRAPH"] = "1"
 from rebvo_b200 import capi, synth
 capi.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_prof', 'librebvo_b200_dbg.so')
