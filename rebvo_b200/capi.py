@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librebvo_b200.so")
+LIB_PATH = os.environ.get("REBVO_B200_LIB") or os.path.join(HERE, "librebvo_b200.so")   # (override: A/B builds of tools/build_alt.py)
 
 
 class RbError(RuntimeError):

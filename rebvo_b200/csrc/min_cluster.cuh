@@ -20,19 +20,29 @@
 #pragma once
 
 #define MC_C 16                      // CTAs per cluster (non-portable size, one CTA per SM)
-#define MC_T 512
+#ifndef MC_T
+#define MC_T 384                     // 12 warps: measured best (512: the warp butterflies and barriers cost more than the extra warps hide)
+#endif
 #define MC_NW (MC_T / 32)
-#define MC_MAXJ 7                    // keylines per thread: kcap <= MC_C * MC_T * MC_MAXJ = 57344 >= KEYLINE_MAX
+#define MC_MAXJ (3584 / MC_T)         // keylines per thread: kcap <= MC_C * MC_T * MC_MAXJ = 57344 >= KEYLINE_MAX
 #define MC_NV (MC_MAXJ * MC_NW)      // "virtual warps" of a CTA (32 consecutive keylines each)
 #define MC_PW 30                     // doubles per pose and CTA in the exchange: 28 sums, has-a-match, last matched fi
-#define MC_XW 64
+#define MC_XW 60
+#ifndef MC_KPC_FAST
+#define MC_KPC_FAST 1280               // keylines per CTA kept in shared memory (16 x 1280 = 20480 per edge map); see McView
+#endif
 #define MC_SPIN_LIMIT (1ll << 29)    // ~0.27 s: a broken exchange aborts with NaN results instead of hanging the device
 #define MC_BYTES_PER_KL 57           // x0,y0,z0,s_rho, 3 residual buffers (double) + 1 flag byte
 
-#ifdef RB_TVR_PROF   // stamps: [CTA][round (15 = kernel level)][8]
-#define MC_STAMP(e, k) do { if (threadIdx.x == 0) g_tvr_prof[(blockIdx.x * 16 + (e)) * 8 + (k)] = clock64(); } while (0)
+#ifdef RB_TVR_PROF   // stamps: [CTA][round (15 = kernel level)][16]
+#define MC_STAMP(e, k) do { if (threadIdx.x == 0) g_tvr_prof[(blockIdx.x * 16 + (e)) * 16 + (k)] = clock64(); } while (0)
 #else
 #define MC_STAMP(e, k) do { } while (0)
+#endif
+#if defined(RB_TVR_PROF) && defined(MC_BODY_STAMPS)   // stage stamps of thread 0's first keyline of the last evaluation (CTA 0, round slot 14)
+#define MC_BSTAMP(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_tvr_prof[(14) * 16 + (k)] = clock64(); } while (0)
+#else
+#define MC_BSTAMP(k) do { } while (0)
 #endif
 
 struct McPlan {
@@ -44,8 +54,7 @@ struct McPlan {
 struct __align__(16) McSmem {
     double gather[2][MC_C][MC_XW];   // [round parity][source rank][value]
     double part[MC_NW][32];
-    double xout[MC_XW];
-    double tot[2][28];
+    double xout[64];
     double req[2][16];               // per pose: R[9] V[3] RotM[4]
     int req_res[2][2];               // per pose: res_in, res_out
     double wcarry[3][MC_NV];         // per residual buffer: the stale fi that leading misses of a virtual warp inherit
@@ -94,15 +103,177 @@ __device__ __forceinline__ bool mc_mbar_try_wait(unsigned long long *bar, unsign
     return ok != 0;
 }
 
-struct McView {          // this CTA's slice of the edge map in dynamic shared memory
+// This CTA's slice of the edge map.  The first S keylines of the slice live in dynamic shared memory (operands +
+// residual buffers); S is sized for the maps the detector's auto-gain actually produces (ReferencePoints ~ 15 k), not
+// for the capacity MaxPoints: the gathers through the field image only stay L1-resident between evaluations if the
+// unified L1/shared array is not all shared memory.  Keylines beyond S (rare) re-load their operands from the global
+// SoA and keep their residuals in the global residual buffers.
+struct McView {
     double *x0, *y0, *z0, *s_rho;
     double *res[3];
     unsigned char *flag;  // 1: m_num < min(MatchNumThresh, FrameCount)
+    double *gres[3];      // global Res0 / Res1 / Rest (overflow keylines)
+    int S;
     int base, cnt, J;     // first keyline, keylines of this CTA, iterations per thread (uniform over the cluster)
 };
 
+// Per-keyline part of TryVelRot (global_tracker.cpp:350-463) for U keylines of one thread at once.  Same operations
+// in the same order as tvr_body (tracker.cu), but written stage by stage over the U keylines with selects instead of
+// branches, so that their dependent chains (projection -> 1/z -> pixel -> field -> matched keyline -> residual ->
+// Jacobian -> 1/q_rho) interleave: one keyline alone is a ~1800-cycle latency chain, and a CTA here owns ~1000 of them.
+template <bool RW, bool PJ, int U>
+__device__ __forceinline__ void mc_body(const double (&x0)[U], const double (&y0)[U], const double (&z0)[U],
+                                        const double (&s_rho)[U], const float2 (&m)[U], const float (&n_m)[U],
+                                        const bool (&skip)[U], const bool (&act)[U], bool has_rin,
+                                        const double (&r_prev)[U], const double *sR, const double *sV, const double *sRM,
+                                        const TvrConst &tc, const CamC &cam, const unsigned long long *__restrict__ field,
+                                        const float4 *__restrict__ fpack, int *__restrict__ m_id_f, const int (&gi)[U],
+                                        double (&acc)[28], bool (&matched)[U], bool (&need)[U], double (&fi_own)[U],
+                                        bool (&wrote)[U]) {
+    MC_BSTAMP(0);
+    const double max_r = tc.max_r;
+    double px[U], py[U], pz[U], rho_p[U], qx[U], qy[U], pix[U], piy[U], weight[U];
+    bool inb[U], outside[U];
+    int pixel[U];
+    // SE3on3PMatrix (ne10wrapper.h:375-405) and ProyP3toI3PMatrix (:429-445)
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        double t = sR[0] * x0[u];
+        t = t + sR[1] * y0[u];
+        t = t + sR[2] * z0[u];
+        px[u] = sV[0] + t;
+        t = sR[3] * x0[u];
+        t = t + sR[4] * y0[u];
+        t = t + sR[5] * z0[u];
+        py[u] = sV[1] + t;
+        t = sR[6] * x0[u];
+        t = t + sR[7] * y0[u];
+        t = t + sR[8] * z0[u];
+        pz[u] = sV[2] + t;
+    }
+    MC_BSTAMP(1);
+#pragma unroll
+    for (int u = 0; u < U; u++) rho_p[u] = 1 / pz[u];
+    MC_BSTAMP(2);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const double pz_zf = cam.zfm * rho_p[u];
+        qx[u] = pz_zf * px[u];
+        qy[u] = pz_zf * py[u];
+        pix[u] = qx[u] + (double)cam.ppx;   // cam_mod.Hom2Img
+        piy[u] = qy[u] + (double)cam.ppy;
+        const int x = (int)(pix[u] + 0.5), y = (int)(piy[u] + 0.5);   // util::round2int_positive
+        weight[u] = 1;
+        if (RW && has_rin) {
+            const double r = fabs(r_prev[u]);
+            if (!skip[u] && r > tc.k_huber) weight[u] = tc.k_huber / r;   // :370-372
+        }
+        outside[u] = x < 1 || y < 1 || x >= cam.w - 1 || y >= cam.h - 1;   // :376
+        inb[u] = !skip[u] && !outside[u];
+        pixel[u] = inb[u] ? y * cam.w + x : 0;
+    }
+    MC_BSTAMP(3);
+    // field lookup, then the matched keyline's gather record
+    unsigned long long key[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) key[u] = inb[u] ? field[pixel[u]] : ~0ull;
+    float4 ga[U], gb[U];
+    int ikl[U];
+    bool cand[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        cand[u] = key[u] != ~0ull;
+        MC_BSTAMP(4);
+        ikl[u] = cand[u] ? (int)(0xFFFFFFFFu - (unsigned int)(key[u] & 0xFFFFFFFFull)) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        ga[u] = cand[u] ? fpack[2 * ikl[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+        gb[u] = cand[u] ? fpack[2 * ikl[u] + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    double f[U], dfx[U], dfy[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        if (ga[u].x != 12345.f) MC_BSTAMP(5);
+        const float mrx = (float)(sRM[0] * (double)m[u].x + sRM[1] * (double)m[u].y);   // :386-388
+        const float mry = (float)(sRM[2] * (double)m[u].x + sRM[3] * (double)m[u].y);
+        const double p_n2 = (double)(n_m[u] * n_m[u]);                                   // Test_f_k (global_tracker.h:89-104)
+        const double p_esc = (double)(mrx * ga[u].x + mry * ga[u].y);
+        const bool hit = cand[u] && !(fabs(p_esc - p_n2) > tc.match_thresh * p_n2);
+        const double dx = pix[u] - (double)ga[u].z, dy = piy[u] - (double)ga[u].w;      // Calc_f_J2 :254-262
+        const double fi = dx * (double)gb[u].x + dy * (double)gb[u].y;
+        matched[u] = hit;
+        need[u] = inb[u] && !hit;
+        wrote[u] = !skip[u] && outside[u];
+        fi_own[u] = hit ? fi : 0.0;
+        double fv = hit ? fi : max_r;
+        double gx = hit ? (double)gb[u].x : 0.0, gy = hit ? (double)gb[u].y : 0.0;
+        if (RW) {   // fm*=weigth; df_dPi*=weigth (:380,399-403); the weight of a skipped keyline is 1
+            fv = fv * weight[u];
+            gx = gx * weight[u];
+            gy = gy * weight[u];
+        }
+        f[u] = skip[u] ? 0.0 : fv;
+        dfx[u] = gx;
+        dfy[u] = gy;
+        if (m_id_f && act[u]) m_id_f[gi[u]] = hit ? ikl[u] : -1;
+    }
+    if (f[0] != 1e300) MC_BSTAMP(6);
+    // Jacobians (:419-449), the 1/q_rho scaling (:452-463), products
+    double q_rho[U], iq[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const double qvel = (cam.zfm * dfx[u] * sV[0] + cam.zfm * dfy[u] * sV[1]) + (qx[u] * dfx[u] + qy[u] * dfy[u]) * sV[2];
+        q_rho[u] = RW ? sqrt(s_rho[u] * qvel * s_rho[u] * qvel + 1) : s_rho[u];
+    }
+    if (q_rho[0] != 1e300) MC_BSTAMP(7);
+    if (PJ) {
+#pragma unroll
+        for (int u = 0; u < U; u++) iq[u] = 1 / q_rho[u];
+        if (iq[0] != 1e300) MC_BSTAMP(8);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            double t0 = cam.zfm * rho_p[u];
+            const double J0 = t0 * dfx[u], J1 = t0 * dfy[u];
+            t0 = rho_p[u] * qx[u];
+            double J2 = t0 * dfx[u];
+            t0 = rho_p[u] * qy[u];
+            J2 = J2 + t0 * dfy[u];
+            double J3 = J1 * pz[u];
+            J3 = J3 + J2 * py[u];
+            double J4 = J0 * pz[u];
+            J4 = J4 + J2 * px[u];
+            t0 = J0 * py[u];
+            double J5 = -1.0 * t0;
+            J5 = J5 + J1 * px[u];
+            const double J[6] = {div_with_rcp(J0, q_rho[u], iq[u]), div_with_rcp(J1, q_rho[u], iq[u]),
+                                 div_with_rcp(J2, q_rho[u], iq[u]), div_with_rcp(J3, q_rho[u], iq[u]),
+                                 div_with_rcp(J4, q_rho[u], iq[u]), div_with_rcp(J5, q_rho[u], iq[u])};
+            const double fs = div_with_rcp(f[u], q_rho[u], iq[u]);
+            int k = 0;
+#pragma unroll
+            for (int a = 0; a < 6; a++)
+#pragma unroll
+                for (int b = a; b < 6; b++, k++) acc[k] = fma(J[a], J[b], acc[k]);   // (sums are order-toleranced anyway)
+#pragma unroll
+            for (int a = 0; a < 6; a++) acc[21 + a] = fma(J[a], fs, acc[21 + a]);
+            acc[27] = fma(fs, fs, acc[27]);
+        }
+        if (acc[27] != 1e300) MC_BSTAMP(9);
+    } else {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const double fs = f[u] / q_rho[u];
+            acc[27] = fma(fs, fs, acc[27]);
+        }
+    }
+}
+
 // one TryVelRot evaluation of pose slot p over this CTA's keylines; leaves the CTA's 28 sums and stale-fi summary in
 // sm.xout[p * MC_PW ..]
+#ifndef MC_U
+#define MC_U 1                         // keylines of a thread evaluated side by side (2, 3 measured slower: register pressure)
+#endif
 template <bool RW, bool PJ>
 __device__ __forceinline__ void mc_eval_pose(McSmem &sm, const McView &v, int p, const KLSoA &old, const TvrConst &tc,
                                              const CamC &cam, const unsigned long long *__restrict__ field,
@@ -111,59 +282,86 @@ __device__ __forceinline__ void mc_eval_pose(McSmem &sm, const McView &v, int p,
     const double *sR = sm.req[p], *sV = sR + 9, *sRM = sR + 12;
     const int res_in = sm.req_res[p][0], res_out = sm.req_res[p][1];
     const bool has_rin = RW && res_in >= 0;
-    const double *rin = has_rin ? v.res[res_in] : nullptr;
-    double *rout = v.res[res_out];
+    const double *rin = v.res[has_rin ? res_in : 0], *grin = v.gres[has_rin ? res_in : 0];
+    double *rout = v.res[res_out], *grout = v.gres[res_out];
+    int *mid_out = write_mid ? old.m_id_f : nullptr;
     double acc[28];
 #pragma unroll
     for (int k = 0; k < 28; k++) acc[k] = 0;
-    for (int j = 0; j < v.J; j++) {
-        const int li = j * MC_T + tid, i = v.base + li;
-        const int vw = j * MC_NW + wid;
-        const bool active = li < v.cnt;
-        bool matched = false, need = false, wrote = false;
-        double fi_own = 0, r_w = 0;
-        if (active) {
-            KlOp o;
-            o.x0 = v.x0[li];
-            o.y0 = v.y0[li];
-            o.z0 = v.z0[li];
-            o.s_rho = v.s_rho[li];
-            o.m = __ldg(&old.m_m[i]);
-            o.n_m = __ldg(&old.n_m[i]);
-            o.m_num = v.flag[li] ? 0 : 0x7fffffff;   // the m_num part of the skip test (:356) does not change between evaluations
-            double r_prev = 0.0;
-            if (has_rin) {
-                r_prev = rin[li];
-                if ((unsigned long long)__double_as_longlong(r_prev) == RES_SENTINEL) r_prev = sm.wcarry[res_in][vw];
-            }
-            double pr[28];
-            tvr_body<RW, PJ>(o, has_rin, r_prev, sR, sV, sRM, tc, cam, field, fpack, nullptr, write_mid ? old.m_id_f : nullptr,
-                             i, pr, matched, need, fi_own, wrote, r_w);
-            if (PJ) {
+    MC_BSTAMP(10);
+    for (int j0 = 0; j0 < v.J; j0 += MC_U) {
+        if (j0 == MC_U) MC_BSTAMP(11);
+        double x0[MC_U], y0[MC_U], z0[MC_U], s_rho[MC_U], r_prev[MC_U], fi_own[MC_U];
+        float2 m[MC_U];
+        float n_m[MC_U];
+        bool skip[MC_U], act[MC_U], matched[MC_U], need[MC_U], wrote[MC_U];
+        int gi[MC_U], li[MC_U];
 #pragma unroll
-                for (int k = 0; k < 28; k++) acc[k] += pr[k];
-            } else {
-                acc[27] += pr[27];
+        for (int u = 0; u < MC_U; u++) {
+            li[u] = (j0 + u) * MC_T + tid;
+            gi[u] = v.base + li[u];
+            act[u] = li[u] < v.cnt;
+            // lanes without a keyline run on harmless operands and contribute exact zeros
+            x0[u] = y0[u] = 0.0;
+            z0[u] = s_rho[u] = 1.0;
+            m[u] = make_float2(0.f, 0.f);
+            n_m[u] = 0.f;
+            bool fl = false;
+            if (act[u]) {
+                if (li[u] < v.S) {
+                    x0[u] = v.x0[li[u]];
+                    y0[u] = v.y0[li[u]];
+                    z0[u] = v.z0[li[u]];
+                    s_rho[u] = v.s_rho[li[u]];
+                    fl = v.flag[li[u]] != 0;
+                } else {
+                    const KlOp o = load_klop(old, gi[u], cam);
+                    x0[u] = o.x0;
+                    y0[u] = o.y0;
+                    z0[u] = o.z0;
+                    s_rho[u] = o.s_rho;
+                    fl = (unsigned int)o.m_num < tc.mnt;
+                }
+                m[u] = __ldg(&old.m_m[gi[u]]);
+                n_m[u] = __ldg(&old.n_m[gi[u]]);
             }
+            skip[u] = !act[u] || s_rho[u] > tc.s_rho_min || fl;   // :356
+            double r = 0.0;
+            if (has_rin && act[u]) {
+                r = li[u] < v.S ? rin[li[u]] : grin[gi[u]];
+                if ((unsigned long long)__double_as_longlong(r) == RES_SENTINEL) r = sm.wcarry[res_in][(j0 + u) * MC_NW + wid];
+            }
+            r_prev[u] = r;
         }
+        mc_body<RW, PJ, MC_U>(x0, y0, z0, s_rho, m, n_m, skip, act, has_rin, r_prev, sR, sV, sRM, tc, cam, field, fpack,
+                              mid_out, gi, acc, matched, need, fi_own, wrote);
         // "DResidualNew[ikl]=fi" keeps the fi of the last matched keyline before ikl (:341,399-408): in-warp scan here,
         // earlier warps / CTAs through wcarry once the round's exchange is complete
-        const unsigned int bal = __ballot_sync(0xffffffffu, matched);
-        const unsigned int lower = bal & ((1u << lane) - 1u);
-        const double prev_fi = __shfl_sync(0xffffffffu, fi_own, lower ? 31 - __clz(lower) : 0);
-        const double wl = __shfl_sync(0xffffffffu, fi_own, bal ? 31 - __clz(bal) : 0);
-        if (lane == 0) {
-            sm.vw_has[p][vw] = bal != 0;
-            sm.vw_last[p][vw] = wl;
-        }
-        if (active) {
-            if (matched) rout[li] = fi_own;
-            else if (need) rout[li] = lower ? prev_fi : __longlong_as_double((long long)RES_SENTINEL);
-            else if (wrote) rout[li] = r_w;
+#pragma unroll
+        for (int u = 0; u < MC_U; u++) {
+            if (j0 + u >= v.J) break;
+            const int vw = (j0 + u) * MC_NW + wid;
+            const unsigned int bal = __ballot_sync(0xffffffffu, matched[u]);
+            const unsigned int lower = bal & ((1u << lane) - 1u);
+            const double prev_fi = __shfl_sync(0xffffffffu, fi_own[u], lower ? 31 - __clz(lower) : 0);
+            const double wl = __shfl_sync(0xffffffffu, fi_own[u], bal ? 31 - __clz(bal) : 0);
+            if (lane == 0) {
+                sm.vw_has[p][vw] = bal != 0;
+                sm.vw_last[p][vw] = wl;
+            }
+            if (act[u] && (matched[u] || need[u] || wrote[u])) {
+                const double rv = matched[u] ? fi_own[u]
+                                  : need[u]  ? (lower ? prev_fi : __longlong_as_double((long long)RES_SENTINEL))
+                                             : tc.max_r;
+                if (li[u] < v.S) rout[li[u]] = rv;
+                else grout[gi[u]] = rv;
+            }
         }
     }
+    MC_BSTAMP(12);
     // block sums in a fixed order
     __syncthreads();   // previous user of sm.part / sm.vw_* readers are done
+    MC_BSTAMP(13);
     if (PJ) {
         const double w = warp_transpose_sum28(acc, lane);
         sm.part[wid][lane] = w;
@@ -173,7 +371,9 @@ __device__ __forceinline__ void mc_eval_pose(McSmem &sm, const McView &v, int p,
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) sm.part[wid][27] = s;
     }
+    MC_BSTAMP(14);
     __syncthreads();
+    MC_BSTAMP(15);
     if (tid < 28) {
         double t = 0;
         if (PJ || tid == 27) {
@@ -252,11 +452,27 @@ __device__ __forceinline__ void mc_lm_merge(LMState &s, const LMState &z) {
     lm_after_prior_pass(s);
 }
 
+// next pose of a chain: R = exp(W), V, residual buffer ids (:309-311) / the z rotation RotM = exp((0,0,W.z)) (:313-314)
+__device__ __forceinline__ void mc_req_R(McSmem &sm, int p, const LMState &s) {
+    so3_exp(s.Xeval + 3, sm.req[p]);
+    for (int k = 0; k < 3; k++) sm.req[p][9 + k] = s.Xeval[k];
+    sm.req_res[p][0] = s.res_in;
+    sm.req_res[p][1] = s.res_out;
+}
+__device__ __forceinline__ void mc_req_RM(McSmem &sm, int p, const LMState &s) {
+    double wz[3] = {0, 0, s.Xeval[5]}, RMf[9];
+    so3_exp(wz, RMf);
+    sm.req[p][12] = RMf[0];
+    sm.req[p][13] = RMf[1];
+    sm.req[p][14] = RMf[3];
+    sm.req[p][15] = RMf[4];
+}
+
 template <int XCHG>   // 1: st.async + mbarrier complete_tx; 0: plain DSMEM stores + barrier.cluster
 __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
     k_minimizer_cluster(KLSoA old, const MapState *__restrict__ old_st, const unsigned long long *__restrict__ field,
                         const float4 *__restrict__ fpack, MapState *f_st, LMState *lm_out, int *abort_out, CamC cam,
-                        McPlan plan, MinSetup su, FrameState *post_fs, int kpc_cap) {
+                        McPlan plan, MinSetup su, FrameState *post_fs, int kpc_cap, ResPtrs gres) {
     MC_STAMP(15, 0);
     pdl_wait();
     pdl_launch();
@@ -277,9 +493,13 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
         v.res[1] = d + 5 * kpc_cap;
         v.res[2] = d + 6 * kpc_cap;
         v.flag = reinterpret_cast<unsigned char *>(d + 7 * kpc_cap);
+        v.S = kpc_cap;
+        v.gres[0] = gres.r[0];
+        v.gres[1] = gres.r[1];
+        v.gres[2] = gres.r[2];
         int kpc = (K0 + MC_C - 1) / MC_C;
         kpc = (kpc + 31) & ~31;               // whole virtual warps
-        if (kpc > kpc_cap) kpc = kpc_cap;     // (the host only launches this kernel when MC_C * kpc_cap >= capacity)
+        if (kpc > MC_T * MC_MAXJ) kpc = MC_T * MC_MAXJ;   // (the host only launches this kernel when the capacity fits)
         v.base = rank * kpc;
         v.cnt = K0 - v.base;
         v.cnt = v.cnt < 0 ? 0 : (v.cnt > kpc ? kpc : v.cnt);
@@ -296,13 +516,17 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
     }
     // ---- prologue: operands -> shared memory, LM state, barriers -----------------------------------------------
     for (int li = tid; li < v.cnt; li += MC_T) {
-        const KlOp o = load_klop(old, v.base + li, cam);
-        v.x0[li] = o.x0;
-        v.y0[li] = o.y0;
-        v.z0[li] = o.z0;
-        v.s_rho[li] = o.s_rho;
-        v.flag[li] = (unsigned int)o.m_num < tc.mnt ? 1 : 0;
-        v.res[0][li] = 0.0;   // for (auto &r : Residual) r = 0   (:625)
+        if (li < v.S) {
+            const KlOp o = load_klop(old, v.base + li, cam);
+            v.x0[li] = o.x0;
+            v.y0[li] = o.y0;
+            v.z0[li] = o.z0;
+            v.s_rho[li] = o.s_rho;
+            v.flag[li] = (unsigned int)o.m_num < tc.mnt ? 1 : 0;
+            v.res[0][li] = 0.0;   // for (auto &r : Residual) r = 0   (:625)
+        } else {
+            v.gres[0][v.base + li] = 0.0;
+        }
     }
     const bool fused = plan.merge_round >= 0;
     if (tid == 0) {
@@ -321,14 +545,22 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
             mc_mbar_init(&sm.mbar[1], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
+        mc_req_R(sm, 0, sm.lm);
+        mc_req_RM(sm, 0, sm.lm);
     } else if (tid == 32 && fused) {
         lm_begin(sm.lmz, old_st, f_st, su.VW, su.a, su.max_r, su.max_s_rho, su.s_rho_from_state, su.frame_count,
                  su.fc_from_state);   // X = 0, request {0, -1, Rest}
+        mc_req_R(sm, 1, sm.lmz);
+        mc_req_RM(sm, 1, sm.lmz);
     }
     __syncthreads();
     mc_cluster_sync();   // every CTA's barriers exist before anybody sends
     MC_STAMP(15, 2);
 
+    // Round e: all warps evaluate the round's pose(s); the CTA's sums go to every CTA; then three warps work side by side
+    // on the received data -- warp 0: totals, LM step, next pose of the main chain; warp 1: the same for the zero-init
+    // chain; warp 2: stale-fi carries -- while warps 3 / 4 compute the z rotations of the two next poses as soon as the
+    // LM steps are done (named barriers 1 / 2).  Two CTA-wide barriers per round.
     for (int e = 0; e < plan.n; e++) {
         const int sa = plan.sa[e], sb = plan.sb[e];
         const bool two = sa != STEP_NONE;
@@ -336,59 +568,23 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
         const bool PJ = !(sb == STEP_INIT_LAST_ZERO || sb == STEP_INIT_LAST_PRIOR);
         const int par = e & 1;
         const unsigned int nval = two ? 2 * MC_PW : MC_PW;
+        const bool last = e == plan.n - 1;
+        const bool merge = e == plan.merge_round;                 // this round ends the two init tries
+        const bool next_two = !last && plan.sa[e + 1] != STEP_NONE;
+        const int res_out_p[2] = {sm.req_res[0][1], sm.req_res[1][1]};   // (warp 0 / 1 rewrite req_res for the next round)
         MC_STAMP(e, 0);
-        // ---- poses of this round: R = exp(W), RotM = exp((0,0,W.z)) (:309-314), four exponentials on four warps ------
-        if (tid == 0) {
-            if (e > 0 && e - 1 == plan.merge_round) mc_lm_merge(sm.lm, sm.lmz);
-            so3_exp(sm.lm.Xeval + 3, sm.req[0]);
-            for (int k = 0; k < 3; k++) sm.req[0][9 + k] = sm.lm.Xeval[k];
-            sm.req_res[0][0] = sm.lm.res_in;
-            sm.req_res[0][1] = sm.lm.res_out;
-            if (e > 0 && e - 1 == plan.merge_round) {   // the z rotation depends on the merge as well
-                double wz[3] = {0, 0, sm.lm.Xeval[5]}, RMf[9];
-                so3_exp(wz, RMf);
-                sm.req[0][12] = RMf[0];
-                sm.req[0][13] = RMf[1];
-                sm.req[0][14] = RMf[3];
-                sm.req[0][15] = RMf[4];
-            }
-            if (XCHG) mc_mbar_expect_tx(&sm.mbar[par], nval * MC_C * 8u);
-        } else if (tid == 32) {
-            if (!(e > 0 && e - 1 == plan.merge_round)) {
-                double wz[3] = {0, 0, sm.lm.Xeval[5]}, RMf[9];
-                so3_exp(wz, RMf);
-                sm.req[0][12] = RMf[0];
-                sm.req[0][13] = RMf[1];
-                sm.req[0][14] = RMf[3];
-                sm.req[0][15] = RMf[4];
-            }
-        } else if (tid == 64 && two) {
-            so3_exp(sm.lmz.Xeval + 3, sm.req[1]);
-            for (int k = 0; k < 3; k++) sm.req[1][9 + k] = sm.lmz.Xeval[k];
-            sm.req_res[1][0] = sm.lmz.res_in;
-            sm.req_res[1][1] = sm.lmz.res_out;
-        } else if (tid == 96 && two) {
-            double wz[3] = {0, 0, sm.lmz.Xeval[5]}, RMf[9];
-            so3_exp(wz, RMf);
-            sm.req[1][12] = RMf[0];
-            sm.req[1][13] = RMf[1];
-            sm.req[1][14] = RMf[3];
-            sm.req[1][15] = RMf[4];
-        }
-        __syncthreads();
-        MC_STAMP(e, 1);
         // ---- keylines ---------------------------------------------------------------------------------------
-        const bool write_mid = e == plan.n - 1;
-        if (RW) mc_eval_pose<true, true>(sm, v, 0, old, tc, cam, field, fpack, write_mid, tid, lane, wid);
-        else if (PJ) mc_eval_pose<false, true>(sm, v, 0, old, tc, cam, field, fpack, write_mid, tid, lane, wid);
-        else mc_eval_pose<false, false>(sm, v, 0, old, tc, cam, field, fpack, write_mid, tid, lane, wid);
+        if (RW) mc_eval_pose<true, true>(sm, v, 0, old, tc, cam, field, fpack, last, tid, lane, wid);
+        else if (PJ) mc_eval_pose<false, true>(sm, v, 0, old, tc, cam, field, fpack, last, tid, lane, wid);
+        else mc_eval_pose<false, false>(sm, v, 0, old, tc, cam, field, fpack, last, tid, lane, wid);
         if (two) {
             if (PJ) mc_eval_pose<false, true>(sm, v, 1, old, tc, cam, field, fpack, false, tid, lane, wid);
             else mc_eval_pose<false, false>(sm, v, 1, old, tc, cam, field, fpack, false, tid, lane, wid);
         }
         __syncthreads();
-        MC_STAMP(e, 2);
+        MC_STAMP(e, 1);
         // ---- all-to-all of the CTAs' sums through distributed shared memory ------------------------------------
+        if (XCHG && tid == 0) mc_mbar_expect_tx(&sm.mbar[par], nval * MC_C * 8u);
         {
             const unsigned int np = nval / 2;
             for (unsigned int idx = tid; idx < np * MC_C; idx += MC_T) {
@@ -398,7 +594,11 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
                                          mc_mapa(mc_smem_u32(&sm.mbar[par]), dst));
                 else mc_st_remote_v2(mc_mapa(la, dst), sm.xout[2 * pair], sm.xout[2 * pair + 1]);
             }
-            if (XCHG) {
+        }
+        MC_STAMP(e, 2);
+        if (!XCHG) mc_cluster_sync();
+        if (wid < 3) {
+            if (XCHG) {   // only the warps that consume the data wait for it
                 const unsigned int ph = (unsigned int)(e >> 1) & 1u;
                 const long long t0 = clock64();
                 while (!mc_mbar_try_wait(&sm.mbar[par], ph)) {
@@ -407,53 +607,91 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
                         break;
                     }
                 }
-            } else {
-                mc_cluster_sync();
             }
-        }
-        MC_STAMP(e, 3);
-        // ---- totals in rank order; stale-fi carries of this CTA's virtual warps ---------------------------------
-        if (tid < 64) {
-            const int p = tid >> 5, k = tid & 31;
-            if (k < 28 && (p == 0 || two)) {
-                double t = sm.gather[par][0][p * MC_PW + k];
+            MC_STAMP(e, 3);
+            if (wid == 2) {   // stale-fi carries of this CTA's virtual warps
+                const int nvw = v.J * MC_NW;
+                for (int q = lane; q < (two ? 2 : 1) * nvw; q += 32) {
+                    const int p = q / nvw, vw = q - p * nvw;
+                    double cy = 0;
+                    bool found = false;
+                    for (int w2 = vw - 1; w2 >= 0 && !found; w2--)
+                        if (sm.vw_has[p][w2]) {
+                            cy = sm.vw_last[p][w2];
+                            found = true;
+                        }
+                    for (int r = rank - 1; r >= 0 && !found; r--)
+                        if (sm.gather[par][r][p * MC_PW + 28] != 0.0) {
+                            cy = sm.gather[par][r][p * MC_PW + 29];
+                            found = true;
+                        }
+                    sm.wcarry[res_out_p[p]][vw] = cy;
+                }
+            } else if (wid == 0 || two) {   // totals in rank order, then this chain's LM step and next pose
+                const int p = wid;
+                LMState &L = p == 0 ? sm.lm : sm.lmz;
+                if (lane < 28) {   // lane k: total k in rank order, filed straight into JtJn / JtFn (lm_ingest, sign fix-ups :484-490)
+                    double t = sm.gather[par][0][p * MC_PW + lane];
 #pragma unroll
-                for (int r = 1; r < MC_C; r++) t += sm.gather[par][r][p * MC_PW + k];
-                sm.tot[p][k] = t;
-            }
-        } else {
-            const int q = tid - 64, p = q / MC_NV, vw = q - p * MC_NV;
-            if (p < (two ? 2 : 1) && vw < v.J * MC_NW) {
-                double cy = 0;
-                bool found = false;
-                for (int w2 = vw - 1; w2 >= 0 && !found; w2--)
-                    if (sm.vw_has[p][w2]) {
-                        cy = sm.vw_last[p][w2];
-                        found = true;
+                    for (int r = 1; r < MC_C; r++) t += sm.gather[par][r][p * MC_PW + lane];
+                    if (lane == 27) {
+                        L.last_score = t;
+                    } else if (PJ) {
+                        if (lane < 21) {
+                            int a = 0, b = lane;
+                            while (b >= 6 - a) {
+                                b -= 6 - a;
+                                a++;
+                            }
+                            b += a;
+                            const bool neg = (a < 2 && (b == 2 || b == 3)) || ((a == 2 || a == 3) && b >= 4);
+                            t = neg ? -t : t;
+                            L.JtJn[a * 6 + b] = t;
+                            L.JtJn[b * 6 + a] = t;
+                        } else {
+                            const int a = lane - 21;
+                            L.JtFn[a] = (a == 2 || a == 3) ? -t : t;
+                        }
                     }
-                for (int r = rank - 1; r >= 0 && !found; r--)
-                    if (sm.gather[par][r][p * MC_PW + 28] != 0.0) {
-                        cy = sm.gather[par][r][p * MC_PW + 29];
-                        found = true;
+                }
+                __syncwarp();
+                MC_STAMP(e, 4);
+                if (lane == 0 && !sm.abort) {
+                    L.n_eval++;
+                    MC_STAMP(e, 5);
+                    if (p == 0) {
+                        mc_lm_step_main(sm.lm, sb, rank == 0 ? f_st : nullptr);
+                        MC_STAMP(e, 6);
+                    } else {
+                        mc_lm_step_zero(sm.lmz, sa);
                     }
-                sm.wcarry[sm.req_res[p][1]][vw] = cy;
+                }
+                __syncwarp();
+                if (merge) {   // (uniform) the main chain picks the better try once both LM steps are done
+                    asm volatile("bar.sync 3, 64;" ::: "memory");
+                    if (p == 0 && lane == 0 && !sm.abort) mc_lm_merge(sm.lm, sm.lmz);
+                    __syncwarp();
+                }
+                if (!last) {
+                    if (p == 0) {
+                        asm volatile("bar.sync 1, 64;" ::: "memory");      // releases warp 3
+                        if (lane == 0) mc_req_R(sm, 0, sm.lm);
+                    } else if (next_two) {
+                        asm volatile("bar.sync 2, 64;" ::: "memory");      // releases warp 4
+                        if (lane == 0) mc_req_R(sm, 1, sm.lmz);
+                    }
+                }
+                MC_STAMP(e, 7);
             }
+        } else if (wid == 3 && !last) {
+            asm volatile("bar.sync 1, 64;" ::: "memory");
+            if (lane == 0) mc_req_RM(sm, 0, sm.lm);
+        } else if (wid == 4 && next_two) {
+            asm volatile("bar.sync 2, 64;" ::: "memory");
+            if (lane == 0) mc_req_RM(sm, 1, sm.lmz);
         }
         __syncthreads();
         if (sm.abort) break;
-        MC_STAMP(e, 4);
-        // ---- LM steps (every CTA computes the same step on the same totals) ---------------------------------------
-        if (tid == 0) {
-            if (PJ) lm_ingest<true>(sm.lm, sm.tot[0]);
-            else lm_ingest<false>(sm.lm, sm.tot[0]);
-            mc_lm_step_main(sm.lm, sb, rank == 0 ? f_st : nullptr);
-        } else if (tid == 32 && two) {
-            if (PJ) lm_ingest<true>(sm.lmz, sm.tot[1]);
-            else lm_ingest<false>(sm.lmz, sm.tot[1]);
-            mc_lm_step_zero(sm.lmz, sa);
-        }
-        __syncthreads();
-        MC_STAMP(e, 5);
     }
     // ---- epilogue ------------------------------------------------------------------------------------------------
     if (!sm.abort) lm_finalize_cov(sm.lm, tid);   // the six columns of Cholesky<6>(JtJ).get_inverse() side by side

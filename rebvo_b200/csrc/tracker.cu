@@ -1314,8 +1314,13 @@ int rb_minimizer_cluster_setup(rb_ctx *c) {
     }
     int kpc = (c->kcap + MC_C - 1) / MC_C;
     kpc = (kpc + 31) & ~31;
+    if (kpc > MC_T * MC_MAXJ) return RB_OK;   // more keylines per thread than the kernel's virtual-warp tables hold
+    int kfast = MC_KPC_FAST;                   // keylines per CTA kept in shared memory (the rest works from global memory)
+    const char *kf = getenv("REBVO_B200_MIN_KPC");
+    if (kf && atoi(kf) >= 32) kfast = atoi(kf) & ~31;
+    if (kpc > kfast) kpc = kfast;
     const size_t dyn = (size_t)kpc * MC_BYTES_PER_KL + 64;
-    if (kpc > MC_T * MC_MAXJ || dyn + fa.sharedSizeBytes > (size_t)dev_max) return RB_OK;
+    if (dyn + fa.sharedSizeBytes > (size_t)dev_max) return RB_OK;
     bool ok = true;
     ok = ok && cudaFuncSetAttribute(k_minimizer_cluster<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_minimizer_cluster<0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
@@ -1351,11 +1356,13 @@ static int launch_minimizer_cluster(rb_ctx *c, rb_map *fmap, rb_map *old, const 
     cfg.attrs = attr;
     cfg.numAttrs = c->pdl ? 1 : 0;
     c->launches++;
+    ResPtrs rp;
+    for (int i = 0; i < 3; i++) rp.r[i] = fmap->res[i];
     auto kern = c->min_cluster_xchg ? k_minimizer_cluster<1> : k_minimizer_cluster<0>;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, old->kl, (const MapState *)old->st,
                                              (const unsigned long long *)fmap->field, (const float4 *)fmap->kl.pack,
                                              fmap->st, &fmap->ts->lm, &fmap->ts_host.ctl->abort, make_cam(c), plan, su,
-                                             post_fs, c->min_cluster_kpc);
+                                             post_fs, c->min_cluster_kpc, rp);
     if (e != cudaSuccess) {
         snprintf(c->err, sizeof(c->err), "Minimizer_RV cluster launch: %s", cudaGetErrorString(e));
         return RB_ERR_CUDA;
