@@ -97,6 +97,9 @@ struct rb_ctx {
     bool min_cluster;    // Minimizer_RV in one 16-CTA cluster (min_cluster.cuh); env REBVO_B200_MIN_CLUSTER=0 disables
     int min_cluster_kpc; // keylines per CTA its shared memory is sized for (0: not available on this device / capacity)
     size_t min_cluster_dyn;
+    int min_cluster_g;   // clusters per minimisation (env REBVO_B200_MIN_G, default 4; 1 = one cluster, co-residency guaranteed)
+    int min_cluster_kpc_multi;
+    size_t min_cluster_dyn_multi;
     int min_cluster_xchg; // 1: st.async + mbarrier exchange, 0: DSMEM stores + barrier.cluster (env REBVO_B200_MIN_XCHG)
     int rowscan_mode;    // env REBVO_B200_ROWSCAN: 1 = register-prefetch kernel, 2 = cp.async shared-memory ring
 };

@@ -17,15 +17,22 @@
 //     their LM steps run on two warps side by side, so 2*(init_iter+1) dependent rounds become init_iter+1.
 // Sums: per thread in keyline order, transposing warp butterfly, warps in order, ranks in order -- fixed, deterministic,
 // not the reference's pairwise tree (tests: rel 1e-10 on JtJ/JtF, V/W abs 1e-9).
-#pragma once
-
-#define MC_C 16                      // CTAs per cluster (non-portable size, one CTA per SM)
+// This header is included once per CTA size (MC_T, namespace MC_NS): 512 threads for the one-cluster form, 256 for the
+// multi-cluster form (see k_minimizer_cluster).
 #ifndef MC_T
-#define MC_T 384                     // 12 warps: measured best (512: the warp butterflies and barriers cost more than the extra warps hide)
+#error "define MC_T and MC_NS before including min_cluster.cuh"
 #endif
+#undef MC_NW
+#undef MC_MAXJ
+#undef MC_NV
 #define MC_NW (MC_T / 32)
-#define MC_MAXJ (3584 / MC_T)         // keylines per thread: kcap <= MC_C * MC_T * MC_MAXJ = 57344 >= KEYLINE_MAX
+#define MC_MAXJ (3584 / MC_T)         // keylines per thread of the one-cluster form: MC_C * MC_T * MC_MAXJ = 57344 >= KEYLINE_MAX
 #define MC_NV (MC_MAXJ * MC_NW)      // "virtual warps" of a CTA (32 consecutive keylines each)
+
+#ifndef MC_COMMON_PART
+#define MC_COMMON_PART
+#define MC_C 16                      // CTAs per cluster (non-portable size, one CTA per SM)
+#define MC_GMAX 8                    // clusters of one minimisation
 #define MC_PW 30                     // doubles per pose and CTA in the exchange: 28 sums, has-a-match, last matched fi
 #define MC_XW 60
 #ifndef MC_KPC_FAST
@@ -35,9 +42,19 @@
 #define MC_BYTES_PER_KL 57           // x0,y0,z0,s_rho, 3 residual buffers (double) + 1 flag byte
 
 #ifdef RB_TVR_PROF   // stamps: [CTA][round (15 = kernel level)][16]
-#define MC_STAMP(e, k) do { if (threadIdx.x == 0) g_tvr_prof[(blockIdx.x * 16 + (e)) * 16 + (k)] = clock64(); } while (0)
+#define MC_STAMP(e, k) do { if (threadIdx.x == 0 && blockIdx.x < 16) g_tvr_prof[(blockIdx.x * 16 + (e)) * 16 + (k)] = clock64(); } while (0)
 #else
 #define MC_STAMP(e, k) do { } while (0)
+#endif
+#ifdef RB_TVR_PROF   // %globaltimer of "sums published" / "column gathered" per CTA and round (inter-cluster skew vs mechanism)
+#ifndef MC_GT_DEFINED
+#define MC_GT_DEFINED
+__device__ long long g_mc_gt[128 * 16 * 2];
+extern "C" int rb_debug_fetch_gt(long long *out) { return (int)cudaMemcpyFromSymbol(out, g_mc_gt, sizeof(g_mc_gt)); }
+#endif
+#define MC_GT(e, k) do { if (threadIdx.x == 0 && blockIdx.x < 128) g_mc_gt[(blockIdx.x * 16 + (e)) * 2 + (k)] = tvr_gtime(); } while (0)
+#else
+#define MC_GT(e, k) do { } while (0)
 #endif
 #if defined(RB_TVR_PROF) && defined(MC_BODY_STAMPS)   // stage stamps of thread 0's first keyline of the last evaluation (CTA 0, round slot 14)
 #define MC_BSTAMP(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_tvr_prof[(14) * 16 + (k)] = clock64(); } while (0)
@@ -49,20 +66,6 @@ struct McPlan {
     int n, merge_round;              // merge_round: the round after which the better init try is picked (-1: none)
     unsigned char sa[MIN_MAX_EVALS]; // zero-init try's step of the round (STEP_NONE when the round has one pose)
     unsigned char sb[MIN_MAX_EVALS]; // prior-init try / main loop step
-};
-
-struct __align__(16) McSmem {
-    double gather[2][MC_C][MC_XW];   // [round parity][source rank][value]
-    double part[MC_NW][32];
-    double xout[64];
-    double req[2][16];               // per pose: R[9] V[3] RotM[4]
-    int req_res[2][2];               // per pose: res_in, res_out
-    double wcarry[3][MC_NV];         // per residual buffer: the stale fi that leading misses of a virtual warp inherit
-    double vw_last[2][MC_NV];
-    int vw_has[2][MC_NV];
-    unsigned long long mbar[2];
-    LMState lm, lmz;                 // main / prior-init chain, zero-init chain
-    int abort;
 };
 
 __device__ __forceinline__ unsigned int mc_smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
@@ -269,6 +272,121 @@ __device__ __forceinline__ void mc_body(const double (&x0)[U], const double (&y0
     }
 }
 
+// LM steps of the two init tries evaluated side by side (global_tracker.cpp:651-683 and :700-732)
+__device__ __forceinline__ void mc_lm_step_zero(LMState &z, int step) {
+    switch (step) {
+        case STEP_INIT_FIRST_ZERO:
+            lm_take_first(z);
+            if (z.init_iter > 0) {
+                lm_solve(z, true);
+                lm_request(z, z.Xnew, -1, z.iRt);
+            }
+            break;
+        case STEP_INIT_ITER_ZERO:
+            lm_update(z, true);
+            lm_solve(z, true);
+            lm_request(z, z.Xnew, -1, z.iRt);
+            break;
+        case STEP_INIT_LAST_ZERO:
+            lm_update(z, false);
+            break;
+        default:
+            break;
+    }
+}
+__device__ __forceinline__ void mc_lm_step_main(LMState &s, int step, MapState *fst) {
+    switch (step) {
+        case STEP_INIT_FIRST_PRIOR:
+            lm_take_first(s);
+            s.v = 2;
+            if (s.init_iter > 0) {
+                lm_solve(s, true);
+                lm_request(s, s.Xnew, -1, s.iRN);
+            }
+            break;
+        case STEP_INIT_ITER_PRIOR:
+            lm_update(s, true);
+            lm_solve(s, true);
+            lm_request(s, s.Xnew, -1, s.iRN);
+            break;
+        case STEP_INIT_LAST_PRIOR:
+            lm_update(s, false);
+            break;
+        default:
+            lm_step(s, step, fst);
+            break;
+    }
+}
+// "Save the scores in temporals" (:686-691) + "Check for the lowest score" (:734-747) once both tries are done
+__device__ __forceinline__ void mc_lm_merge(LMState &s, const LMState &z) {
+    for (int i = 0; i < 6; i++) s.Xt[i] = z.X[i];
+    s.Ft = z.F;
+    s.F0t = z.F0;
+    s.ut = z.u;
+    s.vt = z.v;
+    s.eff_steps_t = z.eff_steps;
+    lm_after_prior_pass(s);
+}
+
+
+// ---- exchange between clusters: self-validating 8-byte {sequence number, payload word} slots in global memory ----------
+// (a poller that sees the sequence number has the payload: no fence, no counter -- the NCCL-LL idea).  A double takes two
+// slots.  Slot block of (round parity, cluster, rank, pose): 64 words.
+__device__ __forceinline__ unsigned long long *mc_slots(unsigned long long *ll, int G, int par, int c, int rank, int p) {
+    return ll + ((size_t)(((par * G + c) * MC_C + rank) * 2 + p)) * 64;
+}
+__device__ __forceinline__ void mc_slot_put(unsigned long long *s, int k, unsigned int seq, double v) {
+    st_volatile_u64(s + 2 * k, ((unsigned long long)seq << 32) | (unsigned int)__double2loint(v));
+    st_volatile_u64(s + 2 * k + 1, ((unsigned long long)seq << 32) | (unsigned int)__double2hiint(v));
+}
+// value k of every other cluster's same-rank CTA; own value at position c.  false: timed out
+__device__ __forceinline__ bool mc_slot_gather(unsigned long long *ll, int G, int par, int c, int rank, int p, int k,
+                                               unsigned int seq, double own, double (&v)[MC_GMAX]) {
+    bool done[MC_GMAX];
+#pragma unroll
+    for (int q = 0; q < MC_GMAX; q++) {
+        done[q] = q >= G || q == c;
+        v[q] = q == c ? own : 0.0;
+    }
+    const long long t0 = clock64();
+    for (;;) {
+        bool all = true;
+#pragma unroll
+        for (int q = 0; q < MC_GMAX; q++)
+            if (!done[q]) {
+                const unsigned long long *s = mc_slots(ll, G, par, q, rank, p);
+                unsigned long long lo, hi;   // one 16-byte request for the two slots (each slot validates itself)
+                asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(s + 2 * k) : "memory");
+                if ((unsigned int)(lo >> 32) == seq && (unsigned int)(hi >> 32) == seq) {
+                    v[q] = __hiloint2double((int)(unsigned int)hi, (int)(unsigned int)lo);
+                    done[q] = true;
+                } else {
+                    all = false;
+                }
+            }
+        if (all) return true;
+        if (clock64() - t0 > MC_SPIN_LIMIT) return false;
+    }
+}
+#endif   // MC_COMMON_PART
+
+namespace MC_NS {
+
+struct __align__(16) McSmem {
+    double gather[2][MC_C][MC_XW];   // [round parity][source rank][value]
+    double part[MC_NW][32];
+    double xout[64];
+    double xcol[64];                 // column sums (this CTA's sums + those of the equal-rank CTAs of the other clusters)
+    double req[2][16];               // per pose: R[9] V[3] RotM[4]
+    int req_res[2][2];               // per pose: res_in, res_out
+    double wcarry[3][MC_NV];         // per residual buffer: the stale fi that leading misses of a virtual warp inherit
+    double vw_last[2][MC_NV];
+    int vw_has[2][MC_NV];
+    unsigned long long mbar[2];
+    LMState lm, lmz;                 // main / prior-init chain, zero-init chain
+    int abort;
+};
+
 // one TryVelRot evaluation of pose slot p over this CTA's keylines; leaves the CTA's 28 sums and stale-fi summary in
 // sm.xout[p * MC_PW ..]
 #ifndef MC_U
@@ -396,62 +514,6 @@ __device__ __forceinline__ void mc_eval_pose(McSmem &sm, const McView &v, int p,
     }
 }
 
-// LM steps of the two init tries evaluated side by side (global_tracker.cpp:651-683 and :700-732)
-__device__ __forceinline__ void mc_lm_step_zero(LMState &z, int step) {
-    switch (step) {
-        case STEP_INIT_FIRST_ZERO:
-            lm_take_first(z);
-            if (z.init_iter > 0) {
-                lm_solve(z, true);
-                lm_request(z, z.Xnew, -1, z.iRt);
-            }
-            break;
-        case STEP_INIT_ITER_ZERO:
-            lm_update(z, true);
-            lm_solve(z, true);
-            lm_request(z, z.Xnew, -1, z.iRt);
-            break;
-        case STEP_INIT_LAST_ZERO:
-            lm_update(z, false);
-            break;
-        default:
-            break;
-    }
-}
-__device__ __forceinline__ void mc_lm_step_main(LMState &s, int step, MapState *fst) {
-    switch (step) {
-        case STEP_INIT_FIRST_PRIOR:
-            lm_take_first(s);
-            s.v = 2;
-            if (s.init_iter > 0) {
-                lm_solve(s, true);
-                lm_request(s, s.Xnew, -1, s.iRN);
-            }
-            break;
-        case STEP_INIT_ITER_PRIOR:
-            lm_update(s, true);
-            lm_solve(s, true);
-            lm_request(s, s.Xnew, -1, s.iRN);
-            break;
-        case STEP_INIT_LAST_PRIOR:
-            lm_update(s, false);
-            break;
-        default:
-            lm_step(s, step, fst);
-            break;
-    }
-}
-// "Save the scores in temporals" (:686-691) + "Check for the lowest score" (:734-747) once both tries are done
-__device__ __forceinline__ void mc_lm_merge(LMState &s, const LMState &z) {
-    for (int i = 0; i < 6; i++) s.Xt[i] = z.X[i];
-    s.Ft = z.F;
-    s.F0t = z.F0;
-    s.ut = z.u;
-    s.vt = z.v;
-    s.eff_steps_t = z.eff_steps;
-    lm_after_prior_pass(s);
-}
-
 // next pose of a chain: R = exp(W), V, residual buffer ids (:309-311) / the z rotation RotM = exp((0,0,W.z)) (:313-314)
 __device__ __forceinline__ void mc_req_R(McSmem &sm, int p, const LMState &s) {
     so3_exp(s.Xeval + 3, sm.req[p]);
@@ -472,7 +534,8 @@ template <int XCHG>   // 1: st.async + mbarrier complete_tx; 0: plain DSMEM stor
 __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
     k_minimizer_cluster(KLSoA old, const MapState *__restrict__ old_st, const unsigned long long *__restrict__ field,
                         const float4 *__restrict__ fpack, MapState *f_st, LMState *lm_out, int *abort_out, CamC cam,
-                        McPlan plan, MinSetup su, FrameState *post_fs, int kpc_cap, ResPtrs gres) {
+                        McPlan plan, MinSetup su, FrameState *post_fs, int kpc_cap, ResPtrs gres,
+                        unsigned long long *ll, MinCtl *ctl) {
     MC_STAMP(15, 0);
     pdl_wait();
     pdl_launch();
@@ -481,6 +544,9 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
     __shared__ McSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int rank = (int)mc_cluster_rank();
+    const int G = (int)(gridDim.x / MC_C), cl = (int)(blockIdx.x / MC_C);   // clusters of this minimisation, mine
+    const bool first_cta = blockIdx.x == 0;
+    const unsigned int seq0 = G > 1 ? __ldcg(&ctl->gen) : 0u;   // sequence numbers of this minimisation: seq0 + 1 + round
     const int K0 = old_st->kn;
     McView v;
     {
@@ -497,10 +563,10 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
         v.gres[0] = gres.r[0];
         v.gres[1] = gres.r[1];
         v.gres[2] = gres.r[2];
-        int kpc = (K0 + MC_C - 1) / MC_C;
+        int kpc = (K0 + MC_C * G - 1) / (MC_C * G);
         kpc = (kpc + 31) & ~31;               // whole virtual warps
         if (kpc > MC_T * MC_MAXJ) kpc = MC_T * MC_MAXJ;   // (the host only launches this kernel when the capacity fits)
-        v.base = rank * kpc;
+        v.base = (rank * G + cl) * kpc;        // slices in (rank, cluster) order: a column = the CTAs of equal rank
         v.cnt = K0 - v.base;
         v.cnt = v.cnt < 0 ? 0 : (v.cnt > kpc ? kpc : v.cnt);
         v.J = (kpc + MC_T - 1) / MC_T;
@@ -583,16 +649,51 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
         }
         __syncthreads();
         MC_STAMP(e, 1);
-        // ---- all-to-all of the CTAs' sums through distributed shared memory ------------------------------------
+        // ---- exchange.  Several clusters: the CTAs of equal rank first exchange their sums through L2 slots (published
+        // right after the keyline pass, so that the store latency hides behind the slowest CTA) and add them in cluster
+        // order; then every CTA sends its column sum to every CTA of its cluster through distributed shared memory.
+        const unsigned int seq = seq0 + 1u + (unsigned int)e;
         if (XCHG && tid == 0) mc_mbar_expect_tx(&sm.mbar[par], nval * MC_C * 8u);
-        {
-            const unsigned int np = nval / 2;
-            for (unsigned int idx = tid; idx < np * MC_C; idx += MC_T) {
-                const unsigned int dst = idx / np, pair = idx - dst * np;
-                const unsigned int la = mc_smem_u32(&sm.gather[par][rank][2 * pair]);
-                if (XCHG) mc_st_async_v2(mc_mapa(la, dst), sm.xout[2 * pair], sm.xout[2 * pair + 1],
-                                         mc_mapa(mc_smem_u32(&sm.mbar[par]), dst));
-                else mc_st_remote_v2(mc_mapa(la, dst), sm.xout[2 * pair], sm.xout[2 * pair + 1]);
+        if (wid < 2 && (wid == 0 || two)) {
+            const int p = wid;
+            double t = lane < MC_PW ? sm.xout[p * MC_PW + lane] : 0.0;
+            if (G > 1) {
+                double vq[MC_GMAX];
+                if (lane < MC_PW) {
+                    mc_slot_put(mc_slots(ll, G, par, cl, rank, p), lane, seq, t);
+                    MC_GT(e, 0);
+                    if (!mc_slot_gather(ll, G, par, cl, rank, p, lane, seq, t, vq)) sm.abort = 1;
+                    MC_GT(e, 1);
+                }
+                if (lane < 28) {
+                    t = vq[0];
+#pragma unroll
+                    for (int q = 1; q < MC_GMAX; q++)
+                        if (q < G) t += vq[q];
+                }
+                // column summary for the later columns: the last cluster of this column that has a match
+                int qs = -1;
+                if (lane == 28)
+#pragma unroll
+                    for (int q = 0; q < MC_GMAX; q++)
+                        if (q < G && vq[q] != 0.0) qs = q;
+                qs = __shfl_sync(0xffffffffu, qs, 28);
+                if (lane == 28) t = qs >= 0 ? 1.0 : 0.0;
+                if (lane == 29) {
+                    t = 0.0;
+#pragma unroll
+                    for (int q = 0; q < MC_GMAX; q++)
+                        if (q == qs) t = vq[q];
+                }
+            }
+            if (lane < MC_PW) sm.xcol[p * MC_PW + lane] = t;
+            __syncwarp();
+            for (int idx = lane; idx < (MC_PW / 2) * MC_C; idx += 32) {
+                const unsigned int dst = idx / (MC_PW / 2), pair = idx - dst * (MC_PW / 2);
+                const unsigned int la = mc_smem_u32(&sm.gather[par][rank][p * MC_PW + 2 * pair]);
+                const double a = sm.xcol[p * MC_PW + 2 * pair], b = sm.xcol[p * MC_PW + 2 * pair + 1];
+                if (XCHG) mc_st_async_v2(mc_mapa(la, dst), a, b, mc_mapa(mc_smem_u32(&sm.mbar[par]), dst));
+                else mc_st_remote_v2(mc_mapa(la, dst), a, b);
             }
         }
         MC_STAMP(e, 2);
@@ -610,6 +711,39 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
             }
             MC_STAMP(e, 3);
             if (wid == 2) {   // stale-fi carries of this CTA's virtual warps
+                // what enters this CTA from the earlier clusters of its column: their {has a match, last matched fi}
+                double ccarry[2] = {0.0, 0.0};
+                bool chas[2] = {false, false};
+                if (G > 1) {
+                    for (int p = 0; p < (two ? 2 : 1); p++) {
+                        // lane q = 4 * cluster + word reads one slot word of {has, last} of an earlier cluster
+                        const int qc = lane >> 2, qw = lane & 3;
+                        unsigned int w32 = 0;
+                        if (qc < cl) {
+                            const unsigned long long *sl = mc_slots(ll, G, par, qc, rank, p) + 2 * 28 + qw;
+                            const long long t0 = clock64();
+                            unsigned long long x;
+                            while ((unsigned int)((x = ld_volatile_u64(sl)) >> 32) != seq)
+                                if (clock64() - t0 > MC_SPIN_LIMIT) {
+                                    sm.abort = 1;
+                                    break;
+                                }
+                            w32 = (unsigned int)x;
+                        }
+                        bool found = false;
+                        for (int q = cl - 1; q >= 0; q--) {   // (uniform)
+                            const double has = __hiloint2double((int)__shfl_sync(0xffffffffu, w32, 4 * q + 1),
+                                                                (int)__shfl_sync(0xffffffffu, w32, 4 * q));
+                            const double lst = __hiloint2double((int)__shfl_sync(0xffffffffu, w32, 4 * q + 3),
+                                                                (int)__shfl_sync(0xffffffffu, w32, 4 * q + 2));
+                            if (!found && has != 0.0) {
+                                ccarry[p] = lst;
+                                chas[p] = true;
+                                found = true;
+                            }
+                        }
+                    }
+                }
                 const int nvw = v.J * MC_NW;
                 for (int q = lane; q < (two ? 2 : 1) * nvw; q += 32) {
                     const int p = q / nvw, vw = q - p * nvw;
@@ -620,7 +754,11 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
                             cy = sm.vw_last[p][w2];
                             found = true;
                         }
-                    for (int r = rank - 1; r >= 0 && !found; r--)
+                    if (!found && chas[p]) {
+                        cy = ccarry[p];
+                        found = true;
+                    }
+                    for (int r = rank - 1; r >= 0 && !found; r--)   // earlier columns (their summaries came with the sums)
                         if (sm.gather[par][r][p * MC_PW + 28] != 0.0) {
                             cy = sm.gather[par][r][p * MC_PW + 29];
                             found = true;
@@ -636,7 +774,7 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
                     for (int r = 1; r < MC_C; r++) t += sm.gather[par][r][p * MC_PW + lane];
                     if (lane == 27) {
                         L.last_score = t;
-                    } else if (PJ) {
+                    } else if (PJ && lane < 27) {
                         if (lane < 21) {
                             int a = 0, b = lane;
                             while (b >= 6 - a) {
@@ -660,7 +798,7 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
                     L.n_eval++;
                     MC_STAMP(e, 5);
                     if (p == 0) {
-                        mc_lm_step_main(sm.lm, sb, rank == 0 ? f_st : nullptr);
+                        mc_lm_step_main(sm.lm, sb, first_cta ? f_st : nullptr);
                         MC_STAMP(e, 6);
                     } else {
                         mc_lm_step_zero(sm.lmz, sa);
@@ -701,7 +839,8 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
         for (int k = 0; k < 3; k++) sm.lm.Vel[k] = sm.lm.W0[k] = __longlong_as_double(0x7FF8000000000000ll);
     }
     __syncthreads();
-    if (rank == 0) {
+    if (first_cta) {
+        if (tid == 0 && G > 1) ctl->gen = seq0 + MIN_MAX_EVALS + 1u;   // the next minimisation gets fresh sequence numbers
         const double *src = reinterpret_cast<const double *>(&sm.lm);
         double *dst = reinterpret_cast<double *>(lm_out);
         for (int k = tid; k < (int)(sizeof(LMState) / sizeof(double)); k += MC_T) dst[k] = src[k];
@@ -711,3 +850,5 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
     mc_cluster_sync();   // no CTA exits while a peer may still send to it
     MC_STAMP(15, 4);
 }
+
+}   // namespace MC_NS

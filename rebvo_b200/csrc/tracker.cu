@@ -62,8 +62,9 @@ int rb_track_state_alloc(rb_ctx *c, rb_map *m) {
     RB_CUDA(cudaMemsetAsync(host.carry, 0, sizeof(double) * 3 * TVR_T, c->stream));
     RB_CUDA(cudaMalloc(&host.ctl, sizeof(MinCtl)));
     RB_CUDA(cudaMemsetAsync(host.ctl, 0, sizeof(MinCtl), c->stream));
-    RB_CUDA(cudaMalloc(&host.ll, sizeof(unsigned long long) * 64 * TVR_T));
-    RB_CUDA(cudaMemsetAsync(host.ll, 0, sizeof(unsigned long long) * 64 * TVR_T, c->stream));
+    // slots of the persistent kernels: [64][TVR_T] (multi-block form) / [2][MC_GMAX][16][2][64] (multi-cluster form)
+    RB_CUDA(cudaMalloc(&host.ll, sizeof(unsigned long long) * 2 * 8 * 16 * 2 * 64));
+    RB_CUDA(cudaMemsetAsync(host.ll, 0, sizeof(unsigned long long) * 2 * 8 * 16 * 2 * 64, c->stream));
     RB_CUDA(cudaMalloc(&host.fm_best, sizeof(unsigned long long) * K));
     RB_CUDA(cudaMalloc(&host.fm_idx, sizeof(int) * K));
     RB_CUDA(cudaMalloc(&host.reg_r, sizeof(double) * K));
@@ -1269,7 +1270,17 @@ __global__ void __launch_bounds__(TVR_T, 2) k_minimizer_persist(KLSoA old, const
 #endif
 }
 
+// one-cluster form (16 CTAs x 512 threads: co-residency guaranteed, 16 SMs) and multi-cluster form (G x 16 CTAs x 256 threads)
+#define MC_T 512
+#define MC_NS mc_one
 #include "min_cluster.cuh"
+#undef MC_T
+#undef MC_NS
+#define MC_T 256
+#define MC_NS mc_multi
+#include "min_cluster.cuh"
+#undef MC_T
+#undef MC_NS
 
 static TrackPtrs track_ptrs(const rb_map *fmap) {
     TrackPtrs tp;
@@ -1301,54 +1312,78 @@ static int launch_eval_step(rb_ctx *c, rb_map *fmap, rb_map *old, int step) {
 
 // per-device set-up of the cluster minimiser (rb_ctx_create, after cudaSetDevice): opt-ins + how many keylines per CTA
 // fit.  Leaves c->min_cluster_kpc = 0 when the device cannot run it (the one-launch-per-evaluation path serves then).
+template <typename K>
+static bool mc_prepare(K kern, int threads, int clusters, size_t dyn, int dev_max) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) return false;
+    if (dyn + fa.sharedSizeBytes > (size_t)dev_max) return false;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return false;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return false;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(MC_C * clusters);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = dyn;
+    int ncl = 0;
+    return cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) == cudaSuccess && ncl >= clusters;
+}
 int rb_minimizer_cluster_setup(rb_ctx *c) {
     c->min_cluster_kpc = 0;
+    c->min_cluster_g = 1;
     const char *xe = getenv("REBVO_B200_MIN_XCHG");
     c->min_cluster_xchg = xe ? atoi(xe) : 1;
     int dev_max = 0;
     if (cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device) != cudaSuccess) return RB_OK;
-    cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, k_minimizer_cluster<1>) != cudaSuccess) {
-        cudaGetLastError();
-        return RB_OK;
-    }
-    int kpc = (c->kcap + MC_C - 1) / MC_C;
-    kpc = (kpc + 31) & ~31;
-    if (kpc > MC_T * MC_MAXJ) return RB_OK;   // more keylines per thread than the kernel's virtual-warp tables hold
-    int kfast = MC_KPC_FAST;                   // keylines per CTA kept in shared memory (the rest works from global memory)
+    int kfast = MC_KPC_FAST;                   // keylines per cluster rank kept in shared memory (the rest works from global memory)
     const char *kf = getenv("REBVO_B200_MIN_KPC");
     if (kf && atoi(kf) >= 32) kfast = atoi(kf) & ~31;
-    if (kpc > kfast) kpc = kfast;
-    const size_t dyn = (size_t)kpc * MC_BYTES_PER_KL + 64;
-    if (dyn + fa.sharedSizeBytes > (size_t)dev_max) return RB_OK;
-    bool ok = true;
-    ok = ok && cudaFuncSetAttribute(k_minimizer_cluster<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_minimizer_cluster<0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_minimizer_cluster<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_minimizer_cluster<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) == cudaSuccess;
-    if (ok) {   // can the device place one such cluster at all?
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(MC_C);
-        cfg.blockDim = dim3(MC_T);
-        cfg.dynamicSmemBytes = dyn;
-        int ncl = 0;
-        ok = cudaOccupancyMaxActiveClusters(&ncl, k_minimizer_cluster<1>, &cfg) == cudaSuccess && ncl >= 1;
+    // one cluster: always possible when the capacity fits its virtual-warp tables
+    {
+        int kpc = (c->kcap + MC_C - 1) / MC_C;
+        kpc = (kpc + 31) & ~31;
+        if (kpc <= 512 * (3584 / 512)) {
+            if (kpc > kfast) kpc = kfast;
+            const size_t dyn = (size_t)kpc * MC_BYTES_PER_KL + 64;
+            if (mc_prepare(mc_one::k_minimizer_cluster<1>, 512, 1, dyn, dev_max) &&
+                mc_prepare(mc_one::k_minimizer_cluster<0>, 512, 1, dyn, dev_max)) {
+                c->min_cluster_kpc = kpc;
+                c->min_cluster_dyn = dyn;
+            }
+        }
     }
-    if (!ok) {
-        cudaGetLastError();
-        return RB_OK;
+    cudaGetLastError();
+    // several clusters (default 4 = 64 SMs): the per-evaluation keyline pass is the longest part of a round and scales with
+    // the SMs; the clusters exchange their sums through L2.  Needs all clusters co-resident: checked here for an idle
+    // device (spins are bounded and abort otherwise), so contexts that share a GPU should ask for REBVO_B200_MIN_G=1.
+    int G = 4;
+    const char *ge = getenv("REBVO_B200_MIN_G");
+    if (ge) G = atoi(ge);
+    if (G > MC_GMAX) G = MC_GMAX;
+    if (c->min_cluster_kpc > 0 && G > 1) {
+        int kpc = (c->kcap + MC_C * G - 1) / (MC_C * G);
+        kpc = (kpc + 31) & ~31;
+        if (kpc <= 256 * (3584 / 256)) {
+            int kf2 = (kfast / G + 31) & ~31;
+            if (kpc > kf2) kpc = kf2;
+            const size_t dyn = (size_t)kpc * MC_BYTES_PER_KL + 64;
+            if (mc_prepare(mc_multi::k_minimizer_cluster<1>, 256, G, dyn, dev_max) &&
+                mc_prepare(mc_multi::k_minimizer_cluster<0>, 256, G, dyn, dev_max)) {
+                c->min_cluster_g = G;
+                c->min_cluster_kpc_multi = kpc;
+                c->min_cluster_dyn_multi = dyn;
+            }
+        }
     }
-    c->min_cluster_kpc = kpc;
-    c->min_cluster_dyn = dyn;
+    cudaGetLastError();
     return RB_OK;
 }
 
 static int launch_minimizer_cluster(rb_ctx *c, rb_map *fmap, rb_map *old, const McPlan &plan, const MinSetup &su,
                                     FrameState *post_fs) {
+    const int G = c->min_cluster_g;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(MC_C);
-    cfg.blockDim = dim3(MC_T);
-    cfg.dynamicSmemBytes = c->min_cluster_dyn;
+    cfg.gridDim = dim3(MC_C * G);
+    cfg.blockDim = dim3(G > 1 ? 256 : 512);
+    cfg.dynamicSmemBytes = G > 1 ? c->min_cluster_dyn_multi : c->min_cluster_dyn;
     cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1358,11 +1393,13 @@ static int launch_minimizer_cluster(rb_ctx *c, rb_map *fmap, rb_map *old, const 
     c->launches++;
     ResPtrs rp;
     for (int i = 0; i < 3; i++) rp.r[i] = fmap->res[i];
-    auto kern = c->min_cluster_xchg ? k_minimizer_cluster<1> : k_minimizer_cluster<0>;
+    auto kern = G > 1 ? (c->min_cluster_xchg ? mc_multi::k_minimizer_cluster<1> : mc_multi::k_minimizer_cluster<0>)
+                      : (c->min_cluster_xchg ? mc_one::k_minimizer_cluster<1> : mc_one::k_minimizer_cluster<0>);
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, old->kl, (const MapState *)old->st,
                                              (const unsigned long long *)fmap->field, (const float4 *)fmap->kl.pack,
                                              fmap->st, &fmap->ts->lm, &fmap->ts_host.ctl->abort, make_cam(c), plan, su,
-                                             post_fs, c->min_cluster_kpc, rp);
+                                             post_fs, G > 1 ? c->min_cluster_kpc_multi : c->min_cluster_kpc, rp,
+                                             fmap->ts_host.ll, fmap->ts_host.ctl);
     if (e != cudaSuccess) {
         snprintf(c->err, sizeof(c->err), "Minimizer_RV cluster launch: %s", cudaGetErrorString(e));
         return RB_ERR_CUDA;

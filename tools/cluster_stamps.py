@@ -34,3 +34,22 @@ if b[0]:
 if b[10]:
     print('eval (thread 0, last evaluation): first iteration %d, remaining iterations %d, wait for the CTA %d, butterfly %d, sync %d' %
           (b[11] - b[10], b[12] - b[11], b[13] - b[12], b[14] - b[13], b[15] - b[14]))
+try:
+    gt = np.zeros(128 * 16 * 2, np.int64)
+    L.rb_debug_fetch_gt(gt.ctypes.data_as(C.c_void_p))
+    g = gt.reshape(128, 16, 2)
+    n = int((g[:, 5, 0] != 0).sum())
+    print('inter-cluster exchange, %d CTAs (ns, %%globaltimer):' % n)
+    for e in (3, 5, 7):
+        pub, got = g[:n, e, 0], g[:n, e, 1]
+        G = n // 16
+        lat = []
+        for b in range(n):
+            r = b % 16
+            partners = [c * 16 + r for c in range(G)]
+            lat.append(got[b] - max(pub[q] for q in partners))
+        print('  round %d: publish spread %d ns (first %d .. last +%d); gathered - last partner publish: min %d mean %d max %d ns; per cluster mean publish offset %s' %
+              (e, pub.max() - pub.min(), 0, pub.max() - pub.min(), min(lat), int(np.mean(lat)), max(lat),
+               [int(pub[c * 16:(c + 1) * 16].mean() - pub.min()) for c in range(G)]))
+except Exception as ex:
+    print('no gt stamps', ex)
