@@ -99,7 +99,7 @@ typedef struct rb_nav {
     double score;   /* Minimizer_RV return value */
     int32_t kn;     /* keylines in this edge map */
     int32_t matches; /* directed_matching() return */
-    int32_t fwd_matches;
+    int32_t fwd_matches; /* distinct new keylines matched by FordwardMatch (see rb_forward_match) */
     int32_t estimation_ok;
     float thresh;   /* detector threshold used for this frame */
     float retuned_thresh;
@@ -166,7 +166,11 @@ int rb_minimizer_rv(rb_map *fmap, rb_map *old, double V[3], double W[3], double 
                     double match_thresh, int iter_max, int init_type, double reweight_distance,
                     double *rel_error, double *rel_error_score, double max_s_rho,
                     uint32_t match_num_thresh, int init_iter, double W_X[36], double *score);
-/* edge_tracker::FordwardMatch (edge_tracker.cpp:380-436): old -> new along m_id_f */
+/* edge_tracker::FordwardMatch (edge_tracker.cpp:380-436): old -> new along m_id_f.  The keyline contents follow the
+ * reference's sequential rule (arg-max rho, ties -> largest index) bit for bit.  *nmatch counts DISTINCT matched new
+ * keylines; the reference's return value also counts the writes that a later old keyline overwrites (its nmatch++ runs
+ * per write), so it is larger when several old keylines hit one new keyline.  The count is diagnostic only: the
+ * reference overwrites it with directed_matching()'s before anything reads it (rebvo_second_t.cpp:354,410). */
 int rb_forward_match(rb_map *old, rb_map *neu, int *nmatch);
 /* edge_tracker::rotate_keylines (edge_tracker.cpp:42-76) */
 int rb_map_rotate_keylines(rb_map *m, const double R[9]);

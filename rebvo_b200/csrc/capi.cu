@@ -195,8 +195,8 @@ extern "C" int rb_ctx_create(rb_ctx **out, int device, const rb_camera *cam, dou
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
-    c->min_resident = rb_minimizer_resident_blocks(c->sm_count);
     rb_minimizer_cluster_setup(c);
+    if ((r = rb_dog_device_setup(c))) return fail(r);
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->nseg = c->h * rb_div_up(c->w, 32);
     CK(cudaMalloc(&c->seg_cnt, sizeof(int) * c->nseg));
@@ -315,7 +315,10 @@ extern "C" int rb_map_create(rb_ctx *c, rb_map **out) {
 // global_tracker.cpp:42-47): a new ring-slot-like object holding a copy of the keylines, the id mask, the match field
 // (+ its search radius) and FrameCount.  Device-to-device copies on the context's stream; scale-space planes and the
 // minimiser scratch are not part of the reference's copy either.
+extern "C" void rb_map_destroy(rb_map *m);
 extern "C" int rb_map_clone(const rb_map *src, rb_map **out) {
+    if (!src) return RB_ERR_ARG;
+    cudaSetDevice(src->c->device);
     if (!src || !out) return RB_ERR_ARG;
     rb_ctx *c = src->c;
     int r = rb_map_alloc(c, out, false);
@@ -324,7 +327,17 @@ extern "C" int rb_map_clone(const rb_map *src, rb_map **out) {
     const size_t N = c->N, K = c->kcap + 32;
     const KLSoA &a = src->kl;
     KLSoA &b = m->kl;
-#define CP(dst, srcp, bytes) RB_CUDA(cudaMemcpyAsync(dst, srcp, bytes, cudaMemcpyDeviceToDevice, c->stream))
+    // on a failed copy the half-initialised map is destroyed here and *out is nulled
+#define CP(dst, srcp, bytes)                                                                                 \
+    do {                                                                                                     \
+        cudaError_t e__ = cudaMemcpyAsync(dst, srcp, bytes, cudaMemcpyDeviceToDevice, c->stream);            \
+        if (e__ != cudaSuccess) {                                                                            \
+            snprintf(c->err, sizeof(c->err), "rb_map_clone: %s", cudaGetErrorString(e__));                   \
+            rb_map_destroy(m);                                                                               \
+            *out = nullptr;                                                                                  \
+            return RB_ERR_CUDA;                                                                              \
+        }                                                                                                    \
+    } while (0)
     CP(m->mask, src->mask, sizeof(int) * N);
     CP(m->field, src->field, sizeof(unsigned long long) * N);
     CP(b.p_inx, a.p_inx, sizeof(int) * K);
@@ -349,7 +362,12 @@ extern "C" int rb_map_clone(const rb_map *src, rb_map **out) {
     CP(m->st, src->st, sizeof(MapState));
 #undef CP
     m->field_radius = src->field_radius;
-    RB_CUDA(cudaStreamSynchronize(c->stream));
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        snprintf(c->err, sizeof(c->err), "rb_map_clone: copy failed");
+        rb_map_destroy(m);
+        *out = nullptr;
+        return RB_ERR_CUDA;
+    }
     return RB_OK;
 }
 
@@ -374,6 +392,8 @@ extern "C" void rb_map_destroy(rb_map *m) {
 }
 
 extern "C" int rb_map_upload_rgb(rb_map *m, const uint8_t *rgb) {
+    if (!m) return RB_ERR_ARG;
+    cudaSetDevice(m->c->device);
     rb_ctx *c = m->c;
     if (!m->owns_ws) return RB_ERR_STATE;
     RB_CUDA(cudaMemcpyAsync(m->ws.rgb, rgb, (size_t)3 * c->N, cudaMemcpyHostToDevice, c->stream));
@@ -381,6 +401,8 @@ extern "C" int rb_map_upload_rgb(rb_map *m, const uint8_t *rgb) {
 }
 
 extern "C" int rb_map_upload_gray(rb_map *m, const float *gray) {
+    if (!m) return RB_ERR_ARG;
+    cudaSetDevice(m->c->device);
     rb_ctx *c = m->c;
     if (!m->owns_ws) return RB_ERR_STATE;
     RB_CUDA(cudaMemcpyAsync(m->ws.gray, gray, (size_t)4 * c->N, cudaMemcpyHostToDevice, c->stream));
@@ -388,11 +410,15 @@ extern "C" int rb_map_upload_gray(rb_map *m, const float *gray) {
 }
 
 extern "C" int rb_map_dog_build(rb_map *m) {
+    if (!m) return RB_ERR_ARG;
+    cudaSetDevice(m->c->device);
     if (!m->owns_ws) return RB_ERR_STATE;
     return rb_dog_build_batch(m->c, &m->ws, 1);
 }
 
 extern "C" int rb_map_get_plane(rb_map *m, int which, float *out) {
+    if (!m) return RB_ERR_ARG;
+    cudaSetDevice(m->c->device);
     rb_ctx *c = m->c;
     if (!m->owns_ws || which < 0 || which > 5) return RB_ERR_ARG;
     const float *src = nullptr;
@@ -420,10 +446,14 @@ static int read_state(rb_map *m, MapState *host) {
 extern "C" int rb_map_detect_ss(rb_map *m, rb_map *ss, const rb_detect_params *p, double *tresh, int *l_kl_num,
                                 int *kn_out);
 extern "C" int rb_map_detect(rb_map *m, const rb_detect_params *p, double *tresh, int *l_kl_num, int *kn_out) {
+    if (!m) return RB_ERR_ARG;
+    cudaSetDevice(m->c->device);
     return rb_map_detect_ss(m, m, p, tresh, l_kl_num, kn_out);
 }
 extern "C" int rb_map_detect_ss(rb_map *m, rb_map *ss, const rb_detect_params *p, double *tresh, int *l_kl_num,
                                 int *kn_out) {
+    if (!m) return RB_ERR_ARG;
+    cudaSetDevice(m->c->device);
     if (!m || !ss) return RB_ERR_ARG;
     rb_ctx *c = m->c;
     if (!ss->img0 || ss->c != c || !p || !tresh || !l_kl_num) return RB_ERR_ARG;
@@ -444,6 +474,8 @@ extern "C" int rb_map_detect_ss(rb_map *m, rb_map *ss, const rb_detect_params *p
 }
 
 extern "C" int rb_map_reestimate_thresh(rb_map *m, int knum, int nbins, float *out_thresh) {
+    if (!m) return RB_ERR_ARG;
+    cudaSetDevice(m->c->device);
     int r = rb_reestimate_enqueue(m->c, m, knum, nbins);
     if (r) return r;
     MapState s;
@@ -453,6 +485,8 @@ extern "C" int rb_map_reestimate_thresh(rb_map *m, int knum, int nbins, float *o
 }
 
 extern "C" int rb_map_knum(rb_map *m, int *kn) {
+    if (!m) return RB_ERR_ARG;
+    cudaSetDevice(m->c->device);
     MapState s;
     int r = read_state(m, &s);
     if (r) return r;
@@ -461,6 +495,8 @@ extern "C" int rb_map_knum(rb_map *m, int *kn) {
 }
 
 extern "C" int rb_map_sync_host_keylines(rb_map *m, rb_keyline *dst, int capacity, int *kn) {
+    if (!m) return RB_ERR_ARG;
+    cudaSetDevice(m->c->device);
     rb_ctx *c = m->c;
     MapState s;
     int r = read_state(m, &s);
@@ -483,6 +519,8 @@ extern "C" int rb_map_sync_host_keylines(rb_map *m, rb_keyline *dst, int capacit
 }
 
 extern "C" int rb_map_load_keylines(rb_map *m, const rb_keyline *src, int kn, const int32_t *mask) {
+    if (!m) return RB_ERR_ARG;
+    cudaSetDevice(m->c->device);
     rb_ctx *c = m->c;
     if (kn < 0 || kn > c->kcap) return RB_ERR_ARG;
     rb_keyline *tmp = nullptr;
@@ -497,13 +535,20 @@ extern "C" int rb_map_load_keylines(rb_map *m, const rb_keyline *src, int kn, co
     }
     k_unpack_aos<<<rb_div_up(kn > 0 ? kn : 1, 128), 128, 0, c->stream>>>(m->kl, m->st, tmp, kn);
     c->launches++;
-    if (mask) RB_CUDA(cudaMemcpyAsync(m->mask, mask, sizeof(int) * (size_t)c->N, cudaMemcpyHostToDevice, c->stream));
-    RB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaError_t e = cudaSuccess;
+    if (mask) e = cudaMemcpyAsync(m->mask, mask, sizeof(int) * (size_t)c->N, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(tmp);
+    if (e != cudaSuccess) {
+        snprintf(c->err, sizeof(c->err), "load_keylines: %s", cudaGetErrorString(e));
+        return RB_ERR_CUDA;
+    }
     return RB_OK;
 }
 
 extern "C" int rb_map_get_mask(rb_map *m, int32_t *out) {
+    if (!m) return RB_ERR_ARG;
+    cudaSetDevice(m->c->device);
     rb_ctx *c = m->c;
     RB_CUDA(cudaMemcpyAsync(out, m->mask, sizeof(int) * (size_t)c->N, cudaMemcpyDeviceToHost, c->stream));
     RB_CUDA(cudaStreamSynchronize(c->stream));

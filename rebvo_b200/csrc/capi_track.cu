@@ -24,6 +24,8 @@ static int stage_in(rb_ctx *c, const double *src, int n, int off) {
 
 extern "C" int rb_map_quantile(rb_map *m, double s_rho_min, double s_rho_max, double percentile, int nbins,
                                double *out) {
+    if (!m) return RB_ERR_ARG;
+    cudaSetDevice(m->c->device);
     int r = rb_quantile_enqueue(m->c, m, s_rho_min, s_rho_max, percentile, nbins);
     if (r) return r;
     MapState s;
@@ -33,6 +35,8 @@ extern "C" int rb_map_quantile(rb_map *m, double s_rho_min, double s_rho_max, do
 }
 
 extern "C" int rb_map_build_field(rb_map *m, int radius, float min_mod) {
+    if (!m) return RB_ERR_ARG;
+    cudaSetDevice(m->c->device);
     int r = rb_build_field_enqueue(m->c, m, radius, min_mod, false);
     if (r) return r;
     return rb_ctx_sync(m->c);
@@ -54,6 +58,8 @@ __global__ void k_field_unpack(const unsigned long long *__restrict__ f, int2 *_
 }
 
 extern "C" int rb_map_get_field(rb_map *m, int32_t *out) {
+    if (!m) return RB_ERR_ARG;
+    cudaSetDevice(m->c->device);
     rb_ctx *c = m->c;
     int2 *tmp = nullptr;
     RB_CUDA(cudaMalloc(&tmp, sizeof(int2) * (size_t)c->N));
@@ -70,6 +76,8 @@ extern "C" int rb_map_get_field(rb_map *m, int32_t *out) {
 }
 
 extern "C" int rb_map_set_frame_count(rb_map *m, uint32_t fc) {
+    if (!m) return RB_ERR_ARG;
+    cudaSetDevice(m->c->device);
     rb_ctx *c = m->c;
     RB_CUDA(cudaMemcpyAsync(&m->st->frame_count, &fc, sizeof(fc), cudaMemcpyHostToDevice, c->stream));
     RB_CUDA(cudaStreamSynchronize(c->stream));
@@ -79,6 +87,8 @@ extern "C" int rb_map_set_frame_count(rb_map *m, uint32_t fc) {
 extern "C" int rb_try_vel_rot(rb_map *fmap, rb_map *old, const double X[6], int reweight, int procjf,
                               double match_thresh, double s_rho_min, uint32_t match_num_thresh, double k_huber,
                               const double *res_in, double *res_out, double JtJ[36], double JtF[6], double *score) {
+    if (!fmap || !old) return RB_ERR_ARG;
+    cudaSetDevice(fmap->c->device);
     rb_ctx *c = fmap->c;
     MapState so, sf;
     int r;
@@ -108,6 +118,8 @@ extern "C" int rb_minimizer_rv(rb_map *fmap, rb_map *old, double V[3], double W[
                                double match_thresh, int iter_max, int init_type, double reweight_distance,
                                double *rel_error, double *rel_error_score, double max_s_rho,
                                uint32_t match_num_thresh, int init_iter, double W_X[36], double *score) {
+    if (!fmap || !old) return RB_ERR_ARG;
+    cudaSetDevice(fmap->c->device);
     rb_ctx *c = fmap->c;
     int r;
     double vw[6] = {V[0], V[1], V[2], W[0], W[1], W[2]};
@@ -122,7 +134,7 @@ extern "C" int rb_minimizer_rv(rb_map *fmap, rb_map *old, double V[3], double W[
     if ((r = rb_minimizer_enqueue(c, fmap, old, args_dev(c), &a, max_s_rho, false, 0, true))) return r;
     LMState *lmh = (LMState *)((char *)c->pinned + 4096);
     RB_CUDA(cudaMemcpyAsync(lmh, &fmap->ts->lm, sizeof(LMState), cudaMemcpyDeviceToHost, c->stream));
-    RB_CUDA(cudaStreamSynchronize(c->stream));
+    if ((r = rb_minimizer_check_abort(c, fmap))) return r;   // (synchronises)
     memcpy(V, lmh->Vel, sizeof(double) * 3);
     memcpy(W, lmh->W0, sizeof(double) * 3);
     if (RVel) memcpy(RVel, lmh->RVel, sizeof(double) * 9);
@@ -135,6 +147,8 @@ extern "C" int rb_minimizer_rv(rb_map *fmap, rb_map *old, double V[3], double W[
 }
 
 extern "C" int rb_forward_match(rb_map *old, rb_map *neu, int *nmatch) {
+    if (!old || !neu) return RB_ERR_ARG;
+    cudaSetDevice(old->c->device);
     int r = rb_forward_match_enqueue(old->c, old, neu);
     if (r) return r;
     MapState s;
@@ -144,6 +158,8 @@ extern "C" int rb_forward_match(rb_map *old, rb_map *neu, int *nmatch) {
 }
 
 extern "C" int rb_map_rotate_keylines(rb_map *m, const double R[9]) {
+    if (!m) return RB_ERR_ARG;
+    cudaSetDevice(m->c->device);
     rb_ctx *c = m->c;
     int r;
     if ((r = stage_in(c, R, 9, 16))) return r;
@@ -154,6 +170,8 @@ extern "C" int rb_map_rotate_keylines(rb_map *m, const double R[9]) {
 extern "C" int rb_directed_matching(rb_map *neu, rb_map *old, const double Vel[3], const double RVel[9],
                                     const double BackRot[9], double min_thr_mod, double min_thr_ang,
                                     double max_radius, double loc_uncertainty, int *nmatch) {
+    if (!neu || !old) return RB_ERR_ARG;
+    cudaSetDevice(neu->c->device);
     rb_ctx *c = neu->c;
     // Vel=BackRot*Vel; RVel=BackRot*RVel*BackRot.T()  (edge_tracker.cpp:324-325), TooN dot order
     DMatchArgs a;
@@ -188,6 +206,8 @@ extern "C" int rb_directed_matching(rb_map *neu, rb_map *old, const double Vel[3
 }
 
 extern "C" int rb_map_regularize(rb_map *m, double thresh, int *r_num) {
+    if (!m) return RB_ERR_ARG;
+    cudaSetDevice(m->c->device);
     int r = rb_regularize_enqueue(m->c, m, thresh, nullptr);
     if (r) return r;
     MapState s;
@@ -197,6 +217,8 @@ extern "C" int rb_map_regularize(rb_map *m, double thresh, int *r_num) {
 }
 
 extern "C" int rb_map_ekf_update(rb_map *m, const double vel[3], double reshape_q_abs, double loc_uncertainty) {
+    if (!m) return RB_ERR_ARG;
+    cudaSetDevice(m->c->device);
     rb_ctx *c = m->c;
     int r;
     if ((r = stage_in(c, vel, 3, 64))) return r;
@@ -206,6 +228,8 @@ extern "C" int rb_map_ekf_update(rb_map *m, const double vel[3], double reshape_
 
 extern "C" int rb_map_rescale_opt(rb_map *m, double s_rho_min, uint32_t match_num_min, int re_escale, double *Kp,
                                   double *RKp) {
+    if (!m) return RB_ERR_ARG;
+    cudaSetDevice(m->c->device);
     int r = rb_rescale_enqueue(m->c, m, s_rho_min, match_num_min, re_escale, nullptr);
     if (r) return r;
     MapState s;

@@ -92,8 +92,7 @@ struct rb_ctx {
     bool counters_preset; // set by rb_pipeline: match / regularise counters are zeroed by k_frame_pre
     int dog_sub;         // frames per scale-space sub-batch, env REBVO_B200_DOG_SUB (0 = whole batch, the default)
     bool pdl;            // programmatic dependent launch of the per-frame chain (env REBVO_B200_PDL=0 disables)
-    bool min_persist;    // whole Minimizer_RV in one persistent launch (env REBVO_B200_MIN_PERSIST=0 disables)
-    int min_resident;    // blocks of that kernel the device keeps resident at once
+    bool min_persist;    // whole Minimizer_RV in one launch (env REBVO_B200_MIN_PERSIST=0: one launch per evaluation)
     bool min_cluster;    // Minimizer_RV in one 16-CTA cluster (min_cluster.cuh); env REBVO_B200_MIN_CLUSTER=0 disables
     int min_cluster_kpc; // keylines per CTA its shared memory is sized for (0: not available on this device / capacity)
     size_t min_cluster_dyn;
@@ -142,7 +141,7 @@ struct TrackState {
     double *carry;        // [3][256]: per residual buffer and block, the stale-fi value its leading misses inherit
     int nblk;
     struct MinCtl *ctl;   // request slots / sequence base of the persistent minimiser kernel
-    unsigned long long *ll;   // its per-block partial-sum slots
+    unsigned long long *ll;   // its inter-cluster slots
     // scratch for FordwardMatch / Regularize_1_iter
     unsigned long long *fm_best;
     int *fm_idx;
@@ -234,6 +233,7 @@ int rb_dog_gray(rb_ctx *c, DogWS *ws, int nimg, const void *const *src_pp = null
 int rb_dog_build_batch(rb_ctx *c, DogWS *ws, int nimg);          // gray -> img0, dog
 int rb_dog_aux_planes(rb_ctx *c, DogWS *ws, int img);            // Img(1), dx, dy into ws->aux
 int rb_dog_make_tables(rb_ctx *c);
+int rb_dog_device_setup(rb_ctx *c);
 // detect.cu
 int rb_detect_enqueue(rb_ctx *c, rb_map *m, const float *img0, const float *dog,
                       const rb_detect_params *p, DetChain *chain_dev);

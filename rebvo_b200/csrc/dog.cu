@@ -396,6 +396,14 @@ __global__ void __launch_bounds__(32 * RING_WARPS) k_rowscan_ring(const float *_
     cp_async_wait<0>();
 }
 
+// per-device opt-ins of this file's kernels (function attributes are per device: called from rb_ctx_create after
+// cudaSetDevice, so that contexts on several GPUs of one process all get them)
+int rb_dog_device_setup(rb_ctx *c) {
+    RB_CUDA(cudaFuncSetAttribute(k_rowscan_ring<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    RB_CUDA(cudaFuncSetAttribute(k_rowscan_ring<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return RB_OK;
+}
+
 static int rowscan_ring(rb_ctx *c, int stage, const float *in, float *out, int nimg, int in_mod, int nper) {
     const int bands = (c->h + 31) / 32;
     const int blocks = rb_div_up(nimg * bands, RING_WARPS);
@@ -403,20 +411,10 @@ static int rowscan_ring(rb_ctx *c, int stage, const float *in, float *out, int n
     const int rmax = 32 + dmax;
     const size_t smem = (size_t)RING_WARPS * (RING_NS * rmax * 32 + 32 * 33 + BOX_TAB_N) * sizeof(float);
     if (stage >= 0) {
-        static bool attr_avg = false;
-        if (!attr_avg) {
-            RB_CUDA(cudaFuncSetAttribute(k_rowscan_ring<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_avg = true;
-        }
         k_rowscan_ring<true><<<blocks, 32 * RING_WARPS, smem, c->stream>>>(
             in, out, c->w, c->h, nimg, in_mod, nper, c->plan.d[0][stage], c->plan.d[1][stage],
             c->boxtab + (0 * 3 + stage) * BOX_TAB_N, c->boxtab + (1 * 3 + stage) * BOX_TAB_N, rmax);
     } else {
-        static bool attr_plain = false;
-        if (!attr_plain) {
-            RB_CUDA(cudaFuncSetAttribute(k_rowscan_ring<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_plain = true;
-        }
         k_rowscan_ring<false><<<blocks, 32 * RING_WARPS, smem, c->stream>>>(in, out, c->w, c->h, nimg, in_mod, nper, 1, 1,
                                                                           nullptr, nullptr, rmax);
     }

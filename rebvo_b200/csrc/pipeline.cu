@@ -62,6 +62,7 @@ struct rb_pipeline {
     FrameState *fs;       // device
     rb_nav *nav_dev;
     rb_nav *nav_pin;
+    int *abort_pin;       // pinned: abort flags of the three maps' minimisers, read back with every push
     uint8_t *rgb_pin;     // optional pinned staging (unused when the caller's buffer is pinned)
     long long n_pushed;   // frames pushed so far
     double t_prev;
@@ -144,6 +145,8 @@ static int pl_reset_state(rb_pipeline *pl) {
     ch.l_kl_num = 0;
     ch.pad = 0;
     RB_CUDA(cudaMemcpy(pl->chain, &ch, sizeof(ch), cudaMemcpyHostToDevice));
+    for (int k = 0; k < RB_NMAPS; k++)
+        if (pl->maps[k]) RB_CUDA(cudaMemset(&pl->maps[k]->ts_host.ctl->abort, 0, sizeof(int)));
     pl->n_pushed = 0;
     pl->t_prev = 0;
     return RB_OK;
@@ -177,6 +180,8 @@ extern "C" int rb_pipeline_create(rb_pipeline **out, int device, const rb_params
     RB_CUDA(cudaMalloc(&pl->fs, sizeof(FrameState)));
     RB_CUDA(cudaMalloc(&pl->nav_dev, sizeof(rb_nav) * max_batch));
     RB_CUDA(cudaMallocHost(&pl->nav_pin, sizeof(rb_nav) * max_batch));
+    RB_CUDA(cudaMallocHost(&pl->abort_pin, sizeof(int) * RB_NMAPS));
+    memset(pl->abort_pin, 0, sizeof(int) * RB_NMAPS);
     RB_CUDA(cudaMalloc(&pl->fa_dev, sizeof(FrameArgs) * max_batch));
     RB_CUDA(cudaMallocHost(&pl->fa_pin, sizeof(FrameArgs) * max_batch));
     pl->gexec = new (std::nothrow) cudaGraphExec_t[RB_NMAPS * (max_batch + 1)];
@@ -260,6 +265,7 @@ extern "C" void rb_pipeline_destroy(rb_pipeline *pl) {
     cudaFree(pl->fs);
     cudaFree(pl->nav_dev);
     if (pl->nav_pin) cudaFreeHost(pl->nav_pin);
+    if (pl->abort_pin) cudaFreeHost(pl->abort_pin);
     cudaFree(pl->fa_dev);
     if (pl->fa_pin) cudaFreeHost(pl->fa_pin);
     if (pl->gexec) {
@@ -498,6 +504,9 @@ static int push_impl(rb_pipeline *pl, const uint8_t *rgb, bool on_device, const 
         }
         RB_CUDA(cudaMemcpyAsync(pl->nav_pin + off, pl->nav_dev, sizeof(rb_nav) * nj, cudaMemcpyDeviceToHost, c->stream));
     }
+    for (int k = 0; k < RB_NMAPS; k++)
+        RB_CUDA(cudaMemcpyAsync(&pl->abort_pin[k], &pl->maps[k]->ts_host.ctl->abort, sizeof(int), cudaMemcpyDeviceToHost,
+                                c->stream));
     pl->t_prev = ts[n - 1];
     pl->n_pushed += n;
     prof_mark(pl, ST_NAV);
@@ -512,14 +521,13 @@ static int push_impl(rb_pipeline *pl, const uint8_t *rgb, bool on_device, const 
         pl->pframes += n;
     }
     if (nav_out) memcpy(nav_out, pl->nav_pin, sizeof(rb_nav) * n);
-    if (pl->nav_pin[n - 1].Pos[0] != pl->nav_pin[n - 1].Pos[0]) {   // NaN pose: did the persistent minimiser abort?
-        for (int k = 0; k < RB_NMAPS; k++) {
-            int ab = 0;
-            cudaMemcpy(&ab, &pl->maps[k]->ts_host.ctl->abort, sizeof(int), cudaMemcpyDeviceToHost);
-            if (ab) {
-                snprintf(c->err, sizeof(c->err), "Minimizer_RV: persistent kernel timed out waiting for its grid");
-                return RB_ERR_CUDA;
-            }
+    {   // did a minimiser of this push abort (an exchange between its CTAs timed out)?  Checked on every push.
+        bool aborted = false;
+        for (int k = 0; k < RB_NMAPS; k++) aborted = aborted || pl->abort_pin[k] != 0;
+        if (aborted) {
+            for (int k = 0; k < RB_NMAPS; k++) cudaMemset(&pl->maps[k]->ts_host.ctl->abort, 0, sizeof(int));
+            snprintf(c->err, sizeof(c->err), "Minimizer_RV: an exchange between the kernel's CTAs timed out (poses are NaN)");
+            return RB_ERR_CUDA;
         }
     }
     float ms;

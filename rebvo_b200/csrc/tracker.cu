@@ -62,7 +62,7 @@ int rb_track_state_alloc(rb_ctx *c, rb_map *m) {
     RB_CUDA(cudaMemsetAsync(host.carry, 0, sizeof(double) * 3 * TVR_T, c->stream));
     RB_CUDA(cudaMalloc(&host.ctl, sizeof(MinCtl)));
     RB_CUDA(cudaMemsetAsync(host.ctl, 0, sizeof(MinCtl), c->stream));
-    // slots of the persistent kernels: [64][TVR_T] (multi-block form) / [2][MC_GMAX][16][2][64] (multi-cluster form)
+    // slots of the multi-cluster minimiser: [2][MC_GMAX][16][2][64]
     RB_CUDA(cudaMalloc(&host.ll, sizeof(unsigned long long) * 2 * 8 * 16 * 2 * 64));
     RB_CUDA(cudaMemsetAsync(host.ll, 0, sizeof(unsigned long long) * 2 * 8 * 16 * 2 * 64, c->stream));
     RB_CUDA(cudaMalloc(&host.fm_best, sizeof(unsigned long long) * K));
@@ -610,7 +610,7 @@ struct TrackPtrs {         // the pointers inside TrackState, passed by value (n
     int *blk_has;
     double *blk_last_fi, *partials, *carry;
     struct MinCtl *ctl;
-    unsigned long long *ll;   // [MIN_LL_WORDS][TVR_T] self-validating partial-sum slots of the persistent kernel
+    unsigned long long *ll;
 };
 
 // per-keyline part: projection, field lookup, residual, Jacobian products
@@ -977,25 +977,11 @@ __global__ void __launch_bounds__(TVR_T) k_tvr_eval(KLSoA old, const MapState *_
 }
 
 // =====================================================================================================
-// Whole Minimizer_RV in ONE launch.  The ~12 evaluations of a frame are strictly dependent (each request comes out
-// of the LM step on the previous sums), so with one launch per evaluation a frame pays 12x (launch + operand
-// re-load + last-block hand-over through L2).  Here the blocks stay resident: block b keeps the operands of
-// keylines [256b, 256b+256) in registers, block 0 ("master") additionally owns the LM state in shared memory.
-// Per evaluation: the master publishes the request {R, V, RotM, res_in, res_out} through 8-byte {data32, seq32}
-// slots (one L2 trip: a poller that sees the sequence number has the payload, the NCCL-LL idea); every block
-// evaluates its keylines and writes its 28 partial sums; workers bump an arrival counter; the master reduces,
-// computes the stale-fi carries, runs the LM step and publishes the next request.  Only blocks that own keylines
-// (b < ceil(kn/256)) take part, the rest exit at once.  All spins are bounded (MIN_SPIN_LIMIT cycles): a stuck grid
-// aborts with ctl->abort set instead of hanging the device.  Requires all blocks co-resident (checked at alloc).
+// Whole Minimizer_RV in ONE launch (min_cluster.cuh).  The ~12 evaluations of a frame are strictly dependent (each pose
+// comes out of the LM step on the previous sums), so with one launch per evaluation a frame pays 12x (launch + operand
+// re-load + last-block hand-over through L2).  Shared declarations of the persistent forms:
 // =====================================================================================================
 #define MIN_MAX_EVALS 32
-#define MIN_REQ_WORDS 34           // 32-bit words: R[9] V[3] RotM[4] as doubles, then res_in, res_out
-#define MIN_LL_WORDS 59            // per block: 28 sums as doubles, has-a-match, last matched fi
-#define MIN_SPIN_LIMIT (1ll << 31)
-struct MinPlan {
-    int n;
-    unsigned char step[MIN_MAX_EVALS];
-};
 struct MinSetup {
     rb_minimizer_args a;
     double max_r, max_s_rho;
@@ -1016,258 +1002,6 @@ __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int *p) {
     unsigned int v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
-}
-
-__global__ void __launch_bounds__(TVR_T, 2) k_minimizer_persist(KLSoA old, const MapState *__restrict__ old_st,
-                                                                const unsigned long long *__restrict__ field,
-                                                                const float4 *__restrict__ fpack, MapState *f_st,
-                                                                TrackPtrs tp, ResPtrs res, CamC cam, MinPlan plan,
-                                                                MinSetup su, FrameState *post_fs) {
-    pdl_wait();
-    pdl_launch();
-    __shared__ TvrSmem sm;
-    __shared__ __align__(8) unsigned int s_req[MIN_REQ_WORDS + 2];
-    __shared__ double s_carry[3];       // this block's stale-fi carry per residual buffer (block 0: always 0)
-    __shared__ double s_tot[28];        // this block's sums (every block), then the grid's (master)
-    __shared__ double s_lastfi;
-    __shared__ int s_has;
-    __shared__ double s_blast[TVR_T];
-    __shared__ unsigned int s_wmask[TVR_T / 32];
-    __shared__ LMState s_lm;
-    __shared__ int s_abort;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int K0 = old_st->kn;
-    const int n_act = K0 > 0 ? (K0 + TVR_T - 1) / TVR_T : 1;
-    if ((int)blockIdx.x >= n_act) return;
-    const bool master = blockIdx.x == 0;
-    MinCtl *ctl = tp.ctl;
-    const unsigned int seq0 = __ldcg(&ctl->gen);   // sequence numbers of this minimisation: seq0 + 1 + evaluation
-    const int i = blockIdx.x * TVR_T + tid;
-    const bool active = i < K0;
-    KlOp o;
-    o.m = make_float2(0.f, 0.f);
-    o.x0 = o.y0 = o.z0 = o.s_rho = 1;
-    o.m_num = 0;
-    o.n_m = 0;
-    if (active) {
-        o = load_klop(old, i, cam);
-        res.r[0][i] = 0.0;   // for (auto &r : Residual) r = 0   (:625)
-    }
-    double rr0 = 0.0, rr1 = 0.0, rr2 = 0.0;   // this keyline's entry of Res0 / Res1 / Rest; Residual starts at 0 (:625)
-    TvrConst tc;
-    tc.max_r = su.max_r;
-    tc.match_thresh = su.a.match_thresh;
-    tc.k_huber = su.a.reweight_distance;
-    tc.s_rho_min = su.s_rho_from_state ? old_st->s_rho_q : su.max_s_rho;
-    {
-        const unsigned int fc = su.fc_from_state ? f_st->frame_count : su.frame_count;
-        tc.mnt = su.a.match_num_thresh < fc ? su.a.match_num_thresh : fc;
-    }
-    int prev_out = 0;
-    if (tid == 0) {
-        s_abort = 0;
-        s_carry[0] = s_carry[1] = s_carry[2] = 0;
-        if (master)
-            lm_begin(s_lm, old_st, f_st, su.VW, su.a, su.max_r, su.max_s_rho, su.s_rho_from_state, su.frame_count,
-                     su.fc_from_state);
-    }
-    __syncthreads();
-    const double *rq = reinterpret_cast<const double *>(s_req);
-    const double *sR = rq, *sV = rq + 9, *sRM = rq + 12;
-
-    for (int e = 0; e < plan.n; e++) {
-        const int step = plan.step[e];
-        const bool RW = step >= STEP_MAIN_FIRST;
-        const bool PJ = !(step == STEP_INIT_LAST_ZERO || step == STEP_INIT_LAST_PRIOR);
-        const unsigned int seq = seq0 + 1u + (unsigned int)e;
-        TVR_STAMP(0);
-        // ---- request of this evaluation -------------------------------------------------------------
-        if (master) {
-            double *wq = reinterpret_cast<double *>(s_req);
-            if (tid == 0) {   // the two exponentials run on two warps side by side
-                so3_exp(s_lm.Xeval + 3, wq);                    // SO3<> RotW0(VelRot.slice<3,3>())
-                for (int k = 0; k < 3; k++) wq[9 + k] = s_lm.Xeval[k];
-                s_req[32] = (unsigned int)s_lm.res_in;
-                s_req[33] = (unsigned int)s_lm.res_out;
-            } else if (tid == 32) {
-                double wz[3] = {0, 0, s_lm.Xeval[5]}, RMf[9];
-                so3_exp(wz, RMf);                               // SO3<> RotM(makeVector(0,0,VelRot[5]))
-                wq[12] = RMf[0];
-                wq[13] = RMf[1];
-                wq[14] = RMf[3];
-                wq[15] = RMf[4];
-            }
-            __syncthreads();
-            if (tid < MIN_REQ_WORDS && n_act > 1) {
-                st_volatile_u64(&ctl->slot[tid], ((unsigned long long)seq << 32) | s_req[tid]);
-            }
-            TVR_GSTAMP(12);   // request published
-        } else if (tid < MIN_REQ_WORDS + 2) {
-            // words 34, 35: this block's stale-fi carry of the previous evaluation, published with the request
-            const unsigned long long *src = tid < MIN_REQ_WORDS
-                                                ? &ctl->slot[tid]
-                                                : tp.ll + (size_t)(MIN_LL_WORDS + tid - MIN_REQ_WORDS) * TVR_T + blockIdx.x;
-            if (tid < MIN_REQ_WORDS || e > 0) {
-                const long long t0 = clock64();
-                unsigned long long v;
-                while ((unsigned int)((v = ld_volatile_u64(src)) >> 32) != seq) {
-                    if (clock64() - t0 > MIN_SPIN_LIMIT) {
-                        s_abort = 1;
-                        break;
-                    }
-                }
-                s_req[tid] = (unsigned int)v;
-            }
-        }
-        __syncthreads();
-        if (s_abort) break;
-        TVR_STAMP(1);
-        if (!master) TVR_GSTAMP(12);   // request observed
-        if (!master && e > 0 && tid == 0)
-            s_carry[prev_out] = __hiloint2double((int)s_req[MIN_REQ_WORDS + 1], (int)s_req[MIN_REQ_WORDS]);
-        const int res_in = (int)s_req[32], res_out = (int)s_req[33];
-        prev_out = res_out;
-        if (!master && e > 0) __syncthreads();
-        const bool has_rin = RW && res_in >= 0;
-        double *rout = res.r[res_out];
-        // ---- keylines ---------------------------------------------------------------------------------
-        double acc[28];
-#pragma unroll
-        for (int k = 0; k < 28; k++) acc[k] = 0;
-        bool matched = false, need = false, wrote = false;
-        double fi_own = 0, r_w = 0;
-        if (active) {
-            double r_prev = has_rin ? (res_in == 0 ? rr0 : res_in == 1 ? rr1 : rr2) : 0.0;
-            if (has_rin && (unsigned long long)__double_as_longlong(r_prev) == RES_SENTINEL)
-                r_prev = s_carry[res_in];
-            if (RW)
-                tvr_body<true, true>(o, has_rin, r_prev, sR, sV, sRM, tc, cam, field, fpack, rout, old.m_id_f, i, acc,
-                                     matched, need, fi_own, wrote, r_w);
-            else if (PJ)
-                tvr_body<false, true>(o, false, 0.0, sR, sV, sRM, tc, cam, field, fpack, rout, old.m_id_f, i, acc,
-                                      matched, need, fi_own, wrote, r_w);
-            else
-                tvr_body<false, false>(o, false, 0.0, sR, sV, sRM, tc, cam, field, fpack, rout, old.m_id_f, i, acc,
-                                       matched, need, fi_own, wrote, r_w);
-        }
-        TVR_STAMP(2);
-        if (PJ)
-            tvr_block_tail<true>(active, matched, need, fi_own, rout, i, acc, sm, s_tot, 1, &s_has, &s_lastfi, tid,
-                                 lane, wid, wrote, r_w);
-        else
-            tvr_block_tail<false>(active, matched, need, fi_own, rout, i, acc, sm, s_tot, 1, &s_has, &s_lastfi, tid,
-                                  lane, wid, wrote, r_w);
-        if (wrote) {   // the register copy of the residual entry follows the buffer
-            if (res_out == 0) rr0 = r_w;
-            else if (res_out == 1) rr1 = r_w;
-            else rr2 = r_w;
-        }
-        __syncthreads();
-        // ---- this block's sums + stale-fi summary -> self-validating 8-byte slots (no fence, no counter) ---------
-        if (tid < MIN_LL_WORDS) {
-            unsigned int w;
-            if (tid < 56) {
-                const double v = s_tot[tid >> 1];
-                w = (tid & 1) ? (unsigned int)__double2hiint(v) : (unsigned int)__double2loint(v);
-            } else if (tid == 56) {
-                w = (unsigned int)s_has;
-            } else {
-                w = (tid == 57) ? (unsigned int)__double2loint(s_lastfi) : (unsigned int)__double2hiint(s_lastfi);
-            }
-            st_volatile_u64(tp.ll + (size_t)tid * TVR_T + blockIdx.x, ((unsigned long long)seq << 32) | w);
-        }
-        TVR_STAMP(3);
-        TVR_GSTAMP(13);   // partial sums stored
-        if (!master) continue;
-        // ---- master: gather (thread b polls block b's slots), carries, grid sums, LM step ------------------
-        double pv[28];
-#pragma unroll
-        for (int k = 0; k < 28; k++) pv[k] = 0;
-        int has = 0;
-        double lastv = 0;
-        if (tid < n_act) {
-            const unsigned long long *src = tp.ll + tid;
-            const long long t0 = clock64();
-            bool ok;
-            do {
-                ok = true;
-                if (PJ) {
-#pragma unroll
-                    for (int k = 0; k < 27; k++) {
-                        const unsigned long long lo = ld_volatile_u64(src + (size_t)(2 * k) * TVR_T);
-                        const unsigned long long hi = ld_volatile_u64(src + (size_t)(2 * k + 1) * TVR_T);
-                        ok = ok && (unsigned int)(lo >> 32) == seq && (unsigned int)(hi >> 32) == seq;
-                        pv[k] = __hiloint2double((int)(unsigned int)hi, (int)(unsigned int)lo);
-                    }
-                }
-                const unsigned long long lo = ld_volatile_u64(src + (size_t)54 * TVR_T);
-                const unsigned long long hi = ld_volatile_u64(src + (size_t)55 * TVR_T);
-                const unsigned long long wh = ld_volatile_u64(src + (size_t)56 * TVR_T);
-                const unsigned long long l0 = ld_volatile_u64(src + (size_t)57 * TVR_T);
-                const unsigned long long l1 = ld_volatile_u64(src + (size_t)58 * TVR_T);
-                ok = ok && (unsigned int)(lo >> 32) == seq && (unsigned int)(hi >> 32) == seq &&
-                     (unsigned int)(wh >> 32) == seq && (unsigned int)(l0 >> 32) == seq &&
-                     (unsigned int)(l1 >> 32) == seq;
-                pv[27] = __hiloint2double((int)(unsigned int)hi, (int)(unsigned int)lo);
-                has = (int)(unsigned int)wh;
-                lastv = __hiloint2double((int)(unsigned int)l1, (int)(unsigned int)l0);
-                if (!ok && clock64() - t0 > MIN_SPIN_LIMIT) {
-                    s_abort = 1;
-                    break;
-                }
-            } while (!ok);
-        }
-        TVR_STAMP(4);
-        TVR_GSTAMP(14);   // all partial sums gathered (master)
-        {
-            const double cy = tvr_carries(has, lastv, tp.carry + res_out * TVR_T, n_act, s_blast, s_wmask, tid, lane, wid);
-            if (tid < n_act && tid > 0) {   // travels with the next request (same sequence number), no fence needed
-                const unsigned long long sq = (unsigned long long)(seq + 1u) << 32;
-                st_volatile_u64(tp.ll + (size_t)MIN_LL_WORDS * TVR_T + tid, sq | (unsigned int)__double2loint(cy));
-                st_volatile_u64(tp.ll + (size_t)(MIN_LL_WORDS + 1) * TVR_T + tid, sq | (unsigned int)__double2hiint(cy));
-            }
-        }
-        TVR_STAMP(5);
-        if (PJ) reduce28<true>(pv, sm.red, tid, lane, wid, s_tot, 1);
-        else reduce28<false>(pv, sm.red, tid, lane, wid, s_tot, 1);
-        __syncthreads();
-        if (s_abort) break;
-        TVR_STAMP(6);
-        if (tid == 0) {
-            if (PJ) lm_ingest<true>(s_lm, s_tot);
-            else lm_ingest<false>(s_lm, s_tot);
-            lm_step(s_lm, step, f_st);
-        }
-        __syncthreads();
-        if (step == STEP_MAIN_LAST || (step == STEP_MAIN_FIRST && plan.n == e + 1)) {
-            lm_finalize_cov(s_lm, tid);   // the six columns of Cholesky<6>(JtJ).get_inverse() side by side
-            __syncthreads();
-        }
-        TVR_STAMP(7);
-    }
-    if (!master) return;
-    // ---- master epilogue: results to global, next minimisation gets fresh sequence numbers --------------------
-    __syncthreads();
-    if (s_abort) {
-        if (tid == 0) {
-            ctl->abort = 1;
-            for (int k = 0; k < 3; k++) s_lm.Vel[k] = s_lm.W0[k] = __longlong_as_double(0x7FF8000000000000ll);
-        }
-        __syncthreads();
-    }
-    {
-        const double *src = reinterpret_cast<const double *>(&s_lm);
-        double *dst = reinterpret_cast<double *>(tp.lm);
-        for (int k = tid; k < (int)(sizeof(LMState) / sizeof(double)); k += TVR_T) dst[k] = src[k];
-    }
-    if (tid == 0) {
-        ctl->gen = seq0 + MIN_MAX_EVALS + 1u;
-        if (post_fs) d_frame_post_min(post_fs, s_lm);   // folded one-thread stage of the per-frame pipeline
-    }
-    TVR_STAMP(8);
-#ifdef RB_TVR_PROF
-    if (tid == 0) g_tvr_prof[255 * 16 + 15] = n_act;
-#endif
 }
 
 // one-cluster form (16 CTAs x 512 threads: co-residency guaranteed, 16 SMs) and multi-cluster form (G x 16 CTAs x 256 threads)
@@ -1407,13 +1141,6 @@ static int launch_minimizer_cluster(rb_ctx *c, rb_map *fmap, rb_map *old, const 
     return RB_OK;
 }
 
-// how many 256-thread blocks of the persistent kernel the device keeps resident at once
-int rb_minimizer_resident_blocks(int sm_count) {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minimizer_persist, TVR_T, 0) != cudaSuccess) return 0;
-    return per_sm * sm_count;
-}
-
 int rb_minimizer_enqueue(rb_ctx *c, rb_map *fmap, rb_map *old, const double *VW_dev, const rb_minimizer_args *a,
                          double max_s_rho, bool s_rho_from_state, unsigned int frame_count, bool fc_from_state,
                          FrameState *post_fs, bool *post_folded) {
@@ -1465,26 +1192,6 @@ int rb_minimizer_enqueue(rb_ctx *c, rb_map *fmap, rb_map *old, const double *VW_
         if (post_folded) *post_folded = post_fs != nullptr;
         return RB_OK;
     }
-    if (c->min_persist && ns <= MIN_MAX_EVALS && nblk <= c->min_resident) {
-        MinPlan plan;
-        memset(&plan, 0, sizeof(plan));
-        plan.n = ns;
-        for (int i = 0; i < ns; i++) plan.step[i] = (unsigned char)steps[i];
-        MinSetup su;
-        su.a = *a;
-        su.max_r = (double)fmap->field_radius;
-        su.max_s_rho = max_s_rho;
-        su.VW = VW_dev;
-        su.frame_count = frame_count;
-        su.s_rho_from_state = s_rho_from_state ? 1 : 0;
-        su.fc_from_state = fc_from_state ? 1 : 0;
-        ResPtrs rp;
-        for (int i = 0; i < 3; i++) rp.r[i] = fmap->res[i];
-        RB_KLAUNCH(k_minimizer_persist, nblk, TVR_T, 0, old->kl, old->st, fmap->field, fmap->kl.pack, fmap->st,
-                   track_ptrs(fmap), rp, make_cam(c), plan, su, post_fs);
-        if (post_folded) *post_folded = post_fs != nullptr;
-        return RB_OK;
-    }
     RB_CUDA(cudaMemsetAsync(fmap->res[0], 0, sizeof(double) * (size_t)c->kcap, c->stream));   // Residual[i]=0 (:625)
     k_lm_begin<<<1, 1, 0, c->stream>>>(fmap->ts, old->st, fmap->st, VW_dev, *a, (double)fmap->field_radius,
                                        max_s_rho, s_rho_from_state ? 1 : 0, frame_count, fc_from_state ? 1 : 0);
@@ -1492,6 +1199,17 @@ int rb_minimizer_enqueue(rb_ctx *c, rb_map *fmap, rb_map *old, const double *VW_
     for (int i = 0; i < ns; i++)
         if ((r = launch_eval_step(c, fmap, old, steps[i]))) return r;
     return RB_OK;
+}
+
+int rb_minimizer_check_abort(rb_ctx *c, rb_map *fmap) {
+    int ab = 0;
+    RB_CUDA(cudaMemcpyAsync(&ab, &fmap->ts_host.ctl->abort, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    RB_CUDA(cudaStreamSynchronize(c->stream));
+    if (!ab) return RB_OK;
+    RB_CUDA(cudaMemsetAsync(&fmap->ts_host.ctl->abort, 0, sizeof(int), c->stream));
+    RB_CUDA(cudaStreamSynchronize(c->stream));
+    snprintf(c->err, sizeof(c->err), "Minimizer_RV: an exchange between the kernel's CTAs timed out (results are NaN)");
+    return RB_ERR_CUDA;
 }
 
 // materialise the lazily resolved entries of a residual buffer (host export of DResidualNew in rb_try_vel_rot)

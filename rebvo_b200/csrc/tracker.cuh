@@ -15,15 +15,15 @@ enum LMStep {
     STEP_MAIN_LAST          // last iteration + uncertainties / outputs (:793-816)
 };
 
-// control block of the persistent Minimizer_RV kernel (tracker.cu), one per TrackState, in device memory
+// control block of the cluster Minimizer_RV kernel (min_cluster.cuh), one per TrackState, in device memory
 struct MinCtl {
-    unsigned long long slot[40];   // {hi: sequence number, lo: payload word}; all zero between minimisations
-    unsigned int gen;              // base of the sequence numbers of the next minimisation
-    int abort;                     // sticky: a spin timed out
+    unsigned int gen;              // base of the slot sequence numbers of the next minimisation
+    int abort;                     // an exchange timed out (results are NaN); read and cleared by rb_minimizer_check_abort
 };
 
-int rb_minimizer_resident_blocks(int sm_count);
 int rb_minimizer_cluster_setup(rb_ctx *c);
+// reads (and clears) the abort flag of a map's minimiser; returns RB_ERR_CUDA with a message when it was set.  Synchronises.
+int rb_minimizer_check_abort(rb_ctx *c, rb_map *fmap);
 int rb_track_state_alloc(rb_ctx *c, rb_map *m);
 void rb_track_state_free(rb_map *m);
 
