@@ -30,7 +30,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "frames/sec @752x480 EuRoC replay (synthetic stand-in), detect+track+map"
+METRIC = "frames/sec @752x480 EuRoC replay (synthetic stand-in), detect+track+map; pose ATE vs reference in `parity`"
 WORKLOAD = ("configs[1]: EuRoC MH_01-like 752x480 full replay, 1xB200 per sequence, IMU off (pure edge VO); "
             "synthetic two-layer parallax stream seed 7")
 
@@ -104,6 +104,10 @@ class ClockSampler:
 TRAFFIC = {"k_rowscan_ring<avg>": 3.19e8}   # 307-331 MB over the two launches of a 64-frame batch
 
 
+def peak_gbs():
+    return peaks()[0]
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -114,14 +118,25 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def run_reference(frames_file_dir, ts, base, idx, n_frames, warm_frames, affinity=True):
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(frames_file_dir, ts, base, idx, n_frames, warm_frames, affinity=True, gpu_params=None):
     """The reference's own CPU implementation (3 pipeline threads) on n_frames of the stream."""
     from oracle import refapi
     from rebvo_b200 import synth
     path = os.path.join(frames_file_dir, "rebvo_b200_bench_frames_%d.bin" % os.getpid())
     synth.write_frames_file(path, ts[:n_frames], base[idx[:n_frames]])
     ncpu = os.cpu_count() or 1
-    params = {"Warmup": warm_frames}
+    params = refapi.ref_params_from(gpu_params) if gpu_params is not None else {}
+    params["Warmup"] = warm_frames
     if affinity and ncpu >= 3:
         params.update(SetAffinity=1, CPU0=0, CPU1=1, CPU2=2)
     try:
@@ -152,7 +167,7 @@ def bench_reference(args):
            "vs_baseline": None, "dtype": "f32 scale space/detector + f64 tracker/EKF", "data": "synthetic",
            "impl": "reference",
            "config": {"workload": WORKLOAD, "frames_per_step": per, "note": "bounded sample of the bench stream"},
-           "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 3, "kind": "reference",
+           "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 3, "kind": "reference", "cpu_model": cpu_model(),
                             "sample": "%d frames (%d timed) through the unmodified 3-thread REBVO, %d host cpus visible"
                             % (total, info["timed_callbacks"], ncpu),
                             "mean_dtp0_ms": info["mean_dtp0_ms"], "mean_dtp1_ms": info["mean_dtp1_ms"]},
@@ -259,27 +274,59 @@ def bench_ours(args):
     # timed column pass is the 2B-image one, the B-image one counts half
     per_step = {"k_rgb2gray": 1, rs + "<plain>": 1, rs + "<avg>": 2, "k_colscan": 2.5, "k_blur_dog": 1}
     dog_ms = sum(passes[k]["ms_per_launch"] * n for k, n in per_step.items())
+    # ---- roofline of the TIME-dominant kernel: Minimizer_RV (one launch per frame).  Algorithmic bytes per launch =
+    # SURVEY.md 8(d) tryvelrot_bytes = E * (K0 * 104 + 224), E = TryVelRot evaluations (2*(init_iter+1) + 1 + iter), K0 = old
+    # keylines; duration = CUDA events around the kernel in the eager stage-profile pass of this same run.
+    kn_mean = float(nav_dev["kn"].mean())
+    evals = (2 * (params.TrackerInitIterNum + 1) if params.TrackerInitType not in (0, 1) else 0) + 1 + params.TrackerIterNum
+    tvr_bytes = evals * (kn_mean * 104.0 + 224.0)
+    min_us = stage_us["minimizer"] if stage_us else None
+    min_gbs = tvr_bytes / (min_us * 1e-6) / 1e9 if min_us else None
+    N = h * w
+    stage_gbs = {}
+    if stage_us:
+        # field: 8N + (20 + 2r*8) K_f (K_f ~ TrackPoints); mapper: rotate 64 K0 + fwdmatch 24 K0 + 80 M + dmatch (40 K + 128 M)
+        # + regularize 96 K + ekf 84 M + rescale 5*32 K (mask probes / candidates of the search are not counted: lower bound)
+        m_mean = float(nav_dev["matches"][1:].mean())
+        field_b = 8.0 * N + (20 + 2 * params.SearchRange * 8) * min(kn_mean, params.TrackPoints)
+        mapper_b = 64 * kn_mean + 24 * kn_mean + 80 * m_mean + 40 * kn_mean + 128 * m_mean + 96 * kn_mean + 84 * m_mean + 160 * kn_mean
+        mapper_us = sum(stage_us[k] for k in ("fwdmatch+rotate", "directed_match", "regularize+ekf", "rescale"))
+        stage_gbs = {"minimizer": {"us": min_us, "algorithmic_bytes": tvr_bytes, "gbs": min_gbs, "frac": min_gbs / peak_gbs()},
+                     "quantile+field": {"us": stage_us["quantile+field"], "algorithmic_bytes": field_b,
+                                        "gbs": field_b / (stage_us["quantile+field"] * 1e-6) / 1e9},
+                     "mapper": {"us": mapper_us, "algorithmic_bytes_lower_bound": mapper_b,
+                                "gbs": mapper_b / (mapper_us * 1e-6) / 1e9}}
     dom = rs + "<avg>"
-    roof = {"bound": "hbm", "kernel": dom, "achieved": passes[dom]["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": passes[dom]["gbs"] / peak, "traffic": TRAFFIC.get(dom), "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": passes[dom]["bytes_per_launch"],
-            "ms_per_launch": passes[dom]["ms_per_launch"], "all_passes": passes,
-            "note": "roofline of the kernel that moves the most bytes (the batched scale space carries >95% of a step's "
-                    "HBM traffic). By TIME the step is dominated by k_minimizer_persist, a latency-bound kernel (12 "
-                    "dependent grid-wide reductions per frame over ~1.6 MB of keyline data): see time_dominant and "
-                    "DESIGN.md section 4.",
-            "scale_space_share_of_step": dog_ms / (t_max / K) if t_max > 0 else None,
-            "time_dominant": {"kernel": "k_minimizer_persist", "bound": "latency (L2 round trips between dependent "
-                              "evaluations)", "stage_us_per_frame_eager": stage_us}}
+    roof = {"bound": "hbm", "kernel": "k_minimizer_cluster (Minimizer_RV, one launch per frame)",
+            "achieved": min_gbs, "peak": peak, "unit": "GB/s", "frac": (min_gbs / peak) if min_gbs else None,
+            "traffic": TRAFFIC.get("k_minimizer_cluster"), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": tvr_bytes, "ms_per_launch": (min_us * 1e-3) if min_us else None,
+            "evaluations_per_launch": evals,
+            "note": "time-dominant kernel of the step. It is LATENCY-bound, not bandwidth-bound: its rounds are strictly "
+                    "dependent (the pose of an evaluation is the LM step on the sums over all keylines of the previous one); "
+                    "the bandwidth fraction is reported because SURVEY 8(d) defines the metric, see DESIGN.md section 4 for "
+                    "the per-round breakdown. The kernels that carry the step's HBM traffic are under scale_space.",
+            "stages": stage_gbs,
+            "scale_space": {"kernel": dom, "achieved": passes[dom]["gbs"], "frac": passes[dom]["gbs"] / peak,
+                            "traffic": TRAFFIC.get(dom), "all_passes": passes,
+                            "share_of_step": dog_ms / (t_max / K) if t_max > 0 else None,
+                            "whole_scale_space_gbs": 103.0 * N * B / (dog_ms * 1e-3) / 1e9,
+                            "whole_scale_space_frac": 103.0 * N * B / (dog_ms * 1e-3) / 1e9 / peak},
+            "stage_us_per_frame_eager": stage_us}
     cpu = None
+    parity = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            n = 150
-            info, _ = run_reference("/tmp", ts, base, idx, n, 20)
-            cpu = {"value": info["fps"], "unit": "frames/s", "cores": 3, "kind": "reference",
+            n = min(620, total)
+            info, rec = run_reference("/tmp", ts, base, idx, n, 20, gpu_params=params)
+            cpu = {"value": info["fps"], "unit": "frames/s", "cores": 3, "kind": "reference", "cpu_model": cpu_model(),
                    "sample": "first %d frames of the bench stream (20 warm-up) through the unmodified 3-thread REBVO "
                              "built from /root/reference sources; %d host cpus visible" % (n, os.cpu_count() or 1),
                    "mean_dtp0_ms": info["mean_dtp0_ms"], "mean_dtp1_ms": info["mean_dtp1_ms"]}
+            from oracle import refapi
+            parity = refapi.trajectory_parity(rec, nav_dev)
+            parity["vs"] = "reference CPU build, same %d frames of the bench stream, same parameters" % n
+            parity["e2e_arm"] = refapi.trajectory_parity(rec, nav_e2e)
         except Exception as e:  # the oracle is test infrastructure; its absence must not break the bench
             cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (e,)}
     ok = nav_dev["estimation_ok"]
@@ -295,7 +342,7 @@ def bench_ours(args):
            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * fbytes,
                    "d2h_bytes_per_step": B * capi.NAV.itemsize, "ms_per_step": t_e2e_max / K},
            "gpu_launches": int(launches), "gpu_launches_per_frame": launches / (K * B),
-           "roofline": roof, "cpu_baseline": cpu}
+           "parity": parity, "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

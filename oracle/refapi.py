@@ -291,3 +291,38 @@ def run_full_rebvo(frames_file, out_file, params=None, timeout=600):
         assert sz == OUTREC.itemsize, (sz, OUTREC.itemsize)
         rec = np.frombuffer(f.read(), OUTREC, count=n)
     return info, rec
+
+
+def ref_params_from(p, **extra):
+    """key=value arguments of oracle/ref_driver.cpp for a rebvo_b200.capi.Params (same parameter set on both sides)."""
+    kv = dict(ZfX=p.cam.zfx, ZfY=p.cam.zfy, PPx=p.cam.ppx, PPy=p.cam.ppy, FPS=p.config_fps, Sigma0=p.Sigma0,
+              KSigma=p.KSigma, DetectorPlaneFitSize=p.det.plane_fit_size, DetectorPosNegThresh=p.det.pos_neg_thresh,
+              DetectorDoGThresh=p.det.dog_thresh, ReferencePoints=p.det.kl_ref, TrackPoints=p.TrackPoints,
+              MaxPoints=p.det.kl_max, DetectorThresh=p.DetectorThresh, DetectorAutoGain=p.det.gain,
+              DetectorMaxThresh=p.det.thresh_max, DetectorMinThresh=p.det.thresh_min,
+              GlobalMatchThreshold=p.MatchThreshold, SearchRange=p.SearchRange, QCutOffNumBins=p.QCutOffNumBins,
+              QCutOffQuantile=p.QCutOffQuantile, TrackerIterNum=p.TrackerIterNum,
+              TrackerInitIterNum=p.TrackerInitIterNum, TrackerInitType=p.TrackerInitType,
+              TrackerMatchThresh=p.TrackerMatchThresh, LocationUncertaintyMatch=p.LocationUncertaintyMatch,
+              MatchThreshModule=p.MatchThreshModule, MatchThreshAngle=p.MatchThreshAngle,
+              ReweigthDistance=p.ReweigthDistance, MatchNumThresh=p.MatchNumThresh, RegularizeThresh=p.RegularizeThresh,
+              ReshapeQAbsolute=p.ReshapeQAbsolute, ReshapeQRelative=p.ReshapeQRelative,
+              LocationUncertainty=p.LocationUncertainty, DoReScaling=p.DoReScaling)
+    kv.update(extra)
+    return kv
+
+
+def trajectory_parity(rec, nav):
+    """Pose / count agreement of a GPU run (rb_nav records) with the reference's run (OUTREC) on the same frames.
+    Both trajectories come from identical inputs in the same camera frame: no alignment step."""
+    n = min(len(rec), len(nav))
+    d = rec["Pos"][:n] - nav["Pos"][:n]
+    e = np.sqrt((d ** 2).sum(1))
+    return {"frames": int(n), "ate_m": float(np.sqrt((e ** 2).mean())), "max_pos_err_m": float(e.max()),
+            "max_poselie_err_rad": float(np.abs(rec["PoseLie"][:n] - nav["PoseLie"][:n]).max()),
+            "path_length_m": float(np.linalg.norm(np.diff(rec["Pos"][:n], axis=0), axis=1).sum()),
+            "kn_equal": bool(np.array_equal(rec["kn"][:n], nav["kn"][:n])),
+            "matches_equal": bool(np.array_equal(rec["matches"][1:n], nav["matches"][1:n])),
+            "estimation_ok_equal": bool(np.array_equal(rec["est_ok"][1:n] != 0, nav["estimation_ok"][1:n] != 0)),
+            "first_kn_mismatch": int(np.nonzero(rec["kn"][:n] != nav["kn"][:n])[0][0])
+            if not np.array_equal(rec["kn"][:n], nav["kn"][:n]) else -1}

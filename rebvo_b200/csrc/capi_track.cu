@@ -135,6 +135,10 @@ extern "C" int rb_minimizer_rv(rb_map *fmap, rb_map *old, double V[3], double W[
     LMState *lmh = (LMState *)((char *)c->pinned + 4096);
     RB_CUDA(cudaMemcpyAsync(lmh, &fmap->ts->lm, sizeof(LMState), cudaMemcpyDeviceToHost, c->stream));
     if ((r = rb_minimizer_check_abort(c, fmap))) return r;   // (synchronises)
+    if (lmh->no_keylines) {   // "if(klist.KNum()<=0) return 0;": every output keeps the caller's value
+        if (score) *score = 0;
+        return RB_OK;
+    }
     memcpy(V, lmh->Vel, sizeof(double) * 3);
     memcpy(W, lmh->W0, sizeof(double) * 3);
     if (RVel) memcpy(RVel, lmh->RVel, sizeof(double) * 9);

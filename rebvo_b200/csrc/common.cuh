@@ -99,6 +99,7 @@ struct rb_ctx {
     int min_cluster_g;   // clusters per minimisation (env REBVO_B200_MIN_G, default 4; 1 = one cluster, co-residency guaranteed)
     int min_cluster_kpc_multi;
     size_t min_cluster_dyn_multi;
+    int min_debug_abort;  // test hook (env REBVO_B200_MIN_FORCE_ABORT=1): the kernel raises its abort flag at once
     int min_cluster_xchg; // 1: st.async + mbarrier exchange, 0: DSMEM stores + barrier.cluster (env REBVO_B200_MIN_XCHG)
     int rowscan_mode;    // env REBVO_B200_ROWSCAN: 1 = register-prefetch kernel, 2 = cp.async shared-memory ring
 };
@@ -131,6 +132,7 @@ struct LMState {
     double Vel[3], W0[3], RVel[9], RW0[9], W_X[36];
     double rel_error, rel_error_score, score;
     double last_score;    // score of the most recent evaluation
+    int no_keylines, pad_;   // Minimizer_RV returned at once ("if(klist.KNum()<=0) return 0", :601): outputs are not valid
 };
 
 struct TrackState {

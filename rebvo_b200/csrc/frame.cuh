@@ -54,13 +54,15 @@ __device__ __forceinline__ void d_frame_pre(FrameState *fs, const FrameArgs *fa,
 
 // after Minimizer_RV (:346-398): outputs, R0 = exp(W), R.T() = R0*R.T(), NaN guard, directed-matching args
 __device__ __forceinline__ void d_frame_post_min(FrameState *fs, const LMState &lm) {
-    for (int i = 0; i < 3; i++) {
-        fs->V[i] = lm.Vel[i];
-        fs->W[i] = lm.W0[i];
-    }
-    for (int i = 0; i < 9; i++) {
-        fs->P_V[i] = lm.RVel[i];
-        fs->P_W[i] = lm.RW0[i];
+    if (!lm.no_keylines) {                  // (an empty old map leaves V, W, P_V, P_W as they were, global_tracker.cpp:601)
+        for (int i = 0; i < 3; i++) {
+            fs->V[i] = lm.Vel[i];
+            fs->W[i] = lm.W0[i];
+        }
+        for (int i = 0; i < 9; i++) {
+            fs->P_V[i] = lm.RVel[i];
+            fs->P_W[i] = lm.RW0[i];
+        }
     }
     so3_exp(fs->W, fs->R0);                 // SO3<> R0(W)
     double Rt[9], RtT[9];

@@ -548,6 +548,18 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
     const bool first_cta = blockIdx.x == 0;
     const unsigned int seq0 = G > 1 ? __ldcg(&ctl->gen) : 0u;   // sequence numbers of this minimisation: seq0 + 1 + round
     const int K0 = old_st->kn;
+    if (K0 <= 0) {   // "if(klist.KNum()<=0) return 0;" (:601): Vel / W0 / RVel / RW0 stay what the caller passed, no FrameCount++
+        if (first_cta && tid == 0) {
+            lm_out->no_keylines = 1;
+            lm_out->score = 0;
+            for (int i = 0; i < 3; i++) {
+                lm_out->Vel[i] = su.VW[i];
+                lm_out->W0[i] = su.VW[3 + i];
+            }
+            if (post_fs) d_frame_post_min(post_fs, *lm_out);
+        }
+        return;   // (every CTA of every cluster: nobody reaches a barrier)
+    }
     McView v;
     {
         double *d = reinterpret_cast<double *>(mc_dyn);
@@ -596,7 +608,7 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
     }
     const bool fused = plan.merge_round >= 0;
     if (tid == 0) {
-        sm.abort = 0;
+        sm.abort = su.debug_abort;
         lm_begin(sm.lm, old_st, f_st, su.VW, su.a, su.max_r, su.max_s_rho, su.s_rho_from_state, su.frame_count,
                  su.fc_from_state);
         if (fused) {   // the prior-initialised try starts beside the zero-initialised one (:696-700)

@@ -543,6 +543,8 @@ __device__ void lm_begin(LMState &s, const MapState *old_st, const MapState *f_s
     s.u = 0;
     s.eff_steps = 0;
     s.n_eval = 0;
+    s.no_keylines = 0;
+    s.pad_ = 0;
     s.F = s.F0 = s.Fnew = 0;
     for (int i = 0; i < 6; i++) s.h[i] = 0;
     if (a.init_type == 1) {
@@ -988,6 +990,7 @@ struct MinSetup {
     const double *VW;
     unsigned int frame_count;
     int s_rho_from_state, fc_from_state;
+    int debug_abort;
 };
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
@@ -1063,6 +1066,8 @@ static bool mc_prepare(K kern, int threads, int clusters, size_t dyn, int dev_ma
 int rb_minimizer_cluster_setup(rb_ctx *c) {
     c->min_cluster_kpc = 0;
     c->min_cluster_g = 1;
+    const char *fa_ = getenv("REBVO_B200_MIN_FORCE_ABORT");
+    c->min_debug_abort = fa_ ? atoi(fa_) : 0;
     const char *xe = getenv("REBVO_B200_MIN_XCHG");
     c->min_cluster_xchg = xe ? atoi(xe) : 1;
     int dev_max = 0;
@@ -1188,6 +1193,7 @@ int rb_minimizer_enqueue(rb_ctx *c, rb_map *fmap, rb_map *old, const double *VW_
         su.frame_count = frame_count;
         su.s_rho_from_state = s_rho_from_state ? 1 : 0;
         su.fc_from_state = fc_from_state ? 1 : 0;
+        su.debug_abort = c->min_debug_abort;
         if ((r = launch_minimizer_cluster(c, fmap, old, plan, su, post_fs))) return r;
         if (post_folded) *post_folded = post_fs != nullptr;
         return RB_OK;

@@ -131,11 +131,11 @@ def _run_stage_parity(cfg):
     m_g = new_g.minimizer_rv(old_g, V0, W0, cfg["match_thresh"], cfg["iter_max"], cfg["init_type"], cfg["reweight"],
                              q_r, cfg["match_num_thresh"], cfg["init_iter"])
     rep.add("Minimizer_RV values", True, "ref V=%s W=%s F=%.6g" % (m_r["V"], m_r["W"], m_r["F"]))
-    rep.close("Minimizer_RV V", m_r["V"], m_g["V"], 1e-8, atol=1e-10)
-    rep.close("Minimizer_RV W", m_r["W"], m_g["W"], 1e-8, atol=1e-10)
+    rep.close("Minimizer_RV V", m_r["V"], m_g["V"], 0.0, atol=1e-9)     # abs 1e-9
+    rep.close("Minimizer_RV W", m_r["W"], m_g["W"], 0.0, atol=1e-9)
     rep.close("Minimizer_RV F", m_r["F"], m_g["F"], 1e-8)
-    rep.close("Minimizer_RV RVel", m_r["RVel"], m_g["RVel"], 1e-6, atol=1e-9 * np.abs(m_r["RVel"]).max())
-    rep.close("Minimizer_RV RW0", m_r["RW0"], m_g["RW0"], 1e-6, atol=1e-9 * np.abs(m_r["RW0"]).max())
+    rep.close("Minimizer_RV RVel", m_r["RVel"], m_g["RVel"], 1e-8, atol=1e-9 * np.abs(m_r["RVel"]).max())
+    rep.close("Minimizer_RV RW0", m_r["RW0"], m_g["RW0"], 1e-8, atol=1e-9 * np.abs(m_r["RW0"]).max())
     rep.close("Minimizer_RV W_X", m_r["W_X"], m_g["W_X"], 1e-8, atol=1e-9 * np.abs(m_r["W_X"]).max())
     rep.close("Minimizer_RV rel_err_score", m_r["rel_err_score"], m_g["rel_err_score"], 1e-8)
     rep.exact("Minimizer_RV m_id_f", old_r.keylines()["m_id_f"], old_g.keylines()["m_id_f"])
