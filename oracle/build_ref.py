@@ -173,6 +173,70 @@ def build_shim_driver(force=False):
     return True
 
 
+HOT_PATH_TUS = ("mtracklib/sspace", "mtracklib/iigauss", "mtracklib/iimage", "mtracklib/edge_finder",
+                "mtracklib/edge_tracker", "mtracklib/global_tracker")
+FORWARDED_HEADERS = ("mtracklib/sspace.h", "mtracklib/edge_finder.h", "mtracklib/edge_tracker.h", "mtracklib/global_tracker.h")
+B_NAMES = ["rebvo/rebvo", "rebvo/rebvo_first_t", "rebvo/rebvo_second_t", "rebvo/rebvo_third_t",
+           "mtracklib/sspace", "mtracklib/iigauss", "mtracklib/iimage", "mtracklib/edge_finder",
+           "mtracklib/edge_tracker", "mtracklib/global_tracker", "UtilLib/ne10wrapper",
+           "mtracklib/keyframe", "mtracklib/kfvo", "mtracklib/pose_graph", "mtracklib/scaleestimator",
+           "UtilLib/imugrabber", "UtilLib/configurator", "VideoLib/image_undistort",
+           "CommLib/net_keypoint", "VideoLib/customcam", "VideoLib/simcam", "VideoLib/videocam",
+           "VideoLib/video_encoder", "VideoLib/video_mfc", "VideoLib/video_mjpeg",
+           "VideoLib/datasetcam", "VideoLib/v4lcam", "UtilLib/ttimer", "CommLib/udp_port",
+           "visualizer/depth_filler"]
+
+
+def build_shim_rebvo(force=False):
+    """The drop-in claim, executed: every UNMODIFIED translation unit of the reference's library except the six hot-path
+    ones (rebvo*.cpp with its three threads, keyframe / kfvo / pose_graph, scaleestimator, CommLib, VideoLib, ...) is
+    compiled where it lies against include/rebvo_b200_shim.hpp -- through a copy of the reference's include tree in which
+    only the four hot-path headers are replaced by forwarding includes -- and linked with
+    librebvo_b200.so and the same driver as level B.  Output: oracle/_ref/shim_rebvo."""
+    if not os.path.isdir(REF):
+        return False
+    repo = os.path.dirname(HERE)
+    exe = os.path.join(OUT, "shim_rebvo")
+    lib = os.path.join(repo, "rebvo_b200", "librebvo_b200.so")
+    deps = [os.path.join(HERE, "ref_driver.cpp"), os.path.join(repo, "include", "rebvo_b200_shim.hpp"),
+            os.path.join(repo, "include", "rebvo_b200.h"), lib, __file__]
+    if not force and os.path.exists(exe) and all(os.path.getmtime(exe) > os.path.getmtime(d) for d in deps):
+        return True
+    ov = os.path.join(OUT, "include_overlay")
+    inc = os.path.join(REF, "include")
+    for d, _, fs in os.walk(inc):
+        rel = os.path.relpath(d, inc)
+        os.makedirs(os.path.join(ov, rel), exist_ok=True)
+        for f in fs:
+            r = os.path.normpath(os.path.join(rel, f))
+            dst = os.path.join(ov, r)
+            if os.path.lexists(dst):
+                os.remove(dst)
+            if r in FORWARDED_HEADERS:
+                open(dst, "w").write("#pragma once\n#include <rebvo_b200_shim.hpp>\n")
+            else:
+                os.symlink(os.path.join(d, f), dst)   # untouched reference header
+    toon = os.path.join(OUT, "toon")
+    blas_dir, blas = openblas()
+    cxx = ["g++", "-std=c++11", "-O2", "-m64", "-fPIC", "-w", "-include", os.path.join(OUT, "shim", "fix_gcc13.h"),
+           "-I" + ov, "-I" + os.path.join(repo, "include"), "-I" + os.path.join(OUT, "shim"),
+           "-I" + os.path.join(REF, "src"), "-I" + toon]
+    srcs = [os.path.join(REF, "src", n + ".cpp") for n in B_NAMES if n not in HOT_PATH_TUS]
+    srcs += [os.path.join(OUT, "shim", "stubs.cpp"), os.path.join(HERE, "ref_driver.cpp")]
+    os.makedirs(os.path.join(OUT, "obj"), exist_ok=True)
+
+    def obj(src):
+        o = os.path.join(OUT, "obj", "s_" + os.path.basename(src).replace(".cpp", ".o"))
+        run(cxx + ["-c", src, "-o", o])
+        return o
+
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        objs = list(ex.map(obj, srcs))
+    run(["g++", "-o", exe] + objs + [lib, "-Wl,-rpath,$ORIGIN/../../rebvo_b200", blas, "-Wl,-rpath," + blas_dir,
+                                      "-Wl,--allow-shlib-undefined", "-lpthread"])
+    return True
+
+
 if __name__ == "__main__":
     ok = build(level_b="--no-level-b" not in sys.argv, force="--force" in sys.argv)
     print("reference oracle built" if ok else "reference sources not present; using prebuilt oracle/_ref if any")

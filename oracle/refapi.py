@@ -267,8 +267,9 @@ OUTREC = np.dtype([("t", "f8"), ("Pos", "f8", 3), ("PoseLie", "f8", 3), ("Pose",
                    ("s_rho_p", "f8"), ("kn", "i4"), ("matches", "i4"), ("est_ok", "i4"), ("pad", "i4")])
 
 
-def run_full_rebvo(frames_file, out_file, params=None, timeout=600):
-    """Level B: run the reference's whole 3-thread REBVO on a raw frame file (oracle/ref_driver.cpp)."""
+def run_full_rebvo(frames_file, out_file, params=None, timeout=600, exe=None):
+    """Level B: run the reference's whole 3-thread REBVO on a raw frame file (oracle/ref_driver.cpp).
+    exe: another build of the same driver (oracle/_ref/shim_rebvo = the unmodified REBVO sources on the GPU library)."""
     import json
     import resource
     import subprocess
@@ -277,7 +278,7 @@ def run_full_rebvo(frames_file, out_file, params=None, timeout=600):
         # finite, large stack: the reference keeps O(27*8*K) byte VLAs on thread stacks
         resource.setrlimit(resource.RLIMIT_STACK, (1000000 * 1024, resource.RLIM_INFINITY))
 
-    args = [EXE, frames_file, out_file] + ["%s=%r" % (k, v) for k, v in (params or {}).items()]
+    args = [exe or EXE, frames_file, out_file] + ["%s=%r" % (k, v) for k, v in (params or {}).items()]
     env = dict(os.environ)
     env["LD_LIBRARY_PATH"] = _blas_dir() + ":" + env.get("LD_LIBRARY_PATH", "")
     env.setdefault("OPENBLAS_NUM_THREADS", "1")

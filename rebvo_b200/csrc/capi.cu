@@ -149,6 +149,11 @@ extern "C" int rb_ctx_create(rb_ctx **out, int device, const rb_camera *cam, dou
     rb_ctx *c = new (std::nothrow) rb_ctx;
     if (!c) return RB_ERR_ARG;
     memset(c, 0, sizeof(*c));
+    c->mtx = new (std::nothrow) std::recursive_mutex;
+    if (!c->mtx) {
+        delete c;
+        return RB_ERR_ARG;
+    }
     c->device = device;
     c->cam = *cam;
     c->w = cam->w;
@@ -233,12 +238,15 @@ extern "C" void rb_ctx_destroy(rb_ctx *c) {
     cudaFree(c->dev_small);
     cudaFree(c->boxtab);
     if (c->pinned) cudaFreeHost(c->pinned);
+    delete c->mtx;
     delete c;
 }
 
 extern "C" const char *rb_last_error(const rb_ctx *c) { return c ? c->err : "null context"; }
 
 extern "C" int rb_ctx_sync(rb_ctx *c) {
+    if (!c) return RB_ERR_ARG;
+    RB_ENTER(c);
     RB_CUDA(cudaStreamSynchronize(c->stream));
     return RB_OK;
 }
@@ -307,6 +315,8 @@ int rb_map_alloc(rb_ctx *c, rb_map **out, bool with_ws) {
 }
 
 extern "C" int rb_map_create(rb_ctx *c, rb_map **out) {
+    if (!c) return RB_ERR_ARG;
+    RB_ENTER(c);
     if (!c || !out) return RB_ERR_ARG;
     return rb_map_alloc(c, out, true);
 }
@@ -318,7 +328,7 @@ extern "C" int rb_map_create(rb_ctx *c, rb_map **out) {
 extern "C" void rb_map_destroy(rb_map *m);
 extern "C" int rb_map_clone(const rb_map *src, rb_map **out) {
     if (!src) return RB_ERR_ARG;
-    cudaSetDevice(src->c->device);
+    RB_ENTER(src->c);
     if (!src || !out) return RB_ERR_ARG;
     rb_ctx *c = src->c;
     int r = rb_map_alloc(c, out, false);
@@ -374,7 +384,7 @@ extern "C" int rb_map_clone(const rb_map *src, rb_map **out) {
 extern "C" void rb_map_destroy(rb_map *m) {
     if (!m) return;
     rb_ctx *c = m->c;
-    cudaSetDevice(c->device);
+    RB_ENTER(c);
     cudaStreamSynchronize(c->stream);
     if (m->owns_ws) rb_dogws_free(&m->ws);
     cudaFree(m->mask);
@@ -393,7 +403,7 @@ extern "C" void rb_map_destroy(rb_map *m) {
 
 extern "C" int rb_map_upload_rgb(rb_map *m, const uint8_t *rgb) {
     if (!m) return RB_ERR_ARG;
-    cudaSetDevice(m->c->device);
+    RB_ENTER(m->c);
     rb_ctx *c = m->c;
     if (!m->owns_ws) return RB_ERR_STATE;
     RB_CUDA(cudaMemcpyAsync(m->ws.rgb, rgb, (size_t)3 * c->N, cudaMemcpyHostToDevice, c->stream));
@@ -402,7 +412,7 @@ extern "C" int rb_map_upload_rgb(rb_map *m, const uint8_t *rgb) {
 
 extern "C" int rb_map_upload_gray(rb_map *m, const float *gray) {
     if (!m) return RB_ERR_ARG;
-    cudaSetDevice(m->c->device);
+    RB_ENTER(m->c);
     rb_ctx *c = m->c;
     if (!m->owns_ws) return RB_ERR_STATE;
     RB_CUDA(cudaMemcpyAsync(m->ws.gray, gray, (size_t)4 * c->N, cudaMemcpyHostToDevice, c->stream));
@@ -411,14 +421,14 @@ extern "C" int rb_map_upload_gray(rb_map *m, const float *gray) {
 
 extern "C" int rb_map_dog_build(rb_map *m) {
     if (!m) return RB_ERR_ARG;
-    cudaSetDevice(m->c->device);
+    RB_ENTER(m->c);
     if (!m->owns_ws) return RB_ERR_STATE;
     return rb_dog_build_batch(m->c, &m->ws, 1);
 }
 
 extern "C" int rb_map_get_plane(rb_map *m, int which, float *out) {
     if (!m) return RB_ERR_ARG;
-    cudaSetDevice(m->c->device);
+    RB_ENTER(m->c);
     rb_ctx *c = m->c;
     if (!m->owns_ws || which < 0 || which > 5) return RB_ERR_ARG;
     const float *src = nullptr;
@@ -447,13 +457,13 @@ extern "C" int rb_map_detect_ss(rb_map *m, rb_map *ss, const rb_detect_params *p
                                 int *kn_out);
 extern "C" int rb_map_detect(rb_map *m, const rb_detect_params *p, double *tresh, int *l_kl_num, int *kn_out) {
     if (!m) return RB_ERR_ARG;
-    cudaSetDevice(m->c->device);
+    RB_ENTER(m->c);
     return rb_map_detect_ss(m, m, p, tresh, l_kl_num, kn_out);
 }
 extern "C" int rb_map_detect_ss(rb_map *m, rb_map *ss, const rb_detect_params *p, double *tresh, int *l_kl_num,
                                 int *kn_out) {
     if (!m) return RB_ERR_ARG;
-    cudaSetDevice(m->c->device);
+    RB_ENTER(m->c);
     if (!m || !ss) return RB_ERR_ARG;
     rb_ctx *c = m->c;
     if (!ss->img0 || ss->c != c || !p || !tresh || !l_kl_num) return RB_ERR_ARG;
@@ -475,7 +485,7 @@ extern "C" int rb_map_detect_ss(rb_map *m, rb_map *ss, const rb_detect_params *p
 
 extern "C" int rb_map_reestimate_thresh(rb_map *m, int knum, int nbins, float *out_thresh) {
     if (!m) return RB_ERR_ARG;
-    cudaSetDevice(m->c->device);
+    RB_ENTER(m->c);
     int r = rb_reestimate_enqueue(m->c, m, knum, nbins);
     if (r) return r;
     MapState s;
@@ -486,7 +496,7 @@ extern "C" int rb_map_reestimate_thresh(rb_map *m, int knum, int nbins, float *o
 
 extern "C" int rb_map_knum(rb_map *m, int *kn) {
     if (!m) return RB_ERR_ARG;
-    cudaSetDevice(m->c->device);
+    RB_ENTER(m->c);
     MapState s;
     int r = read_state(m, &s);
     if (r) return r;
@@ -496,7 +506,7 @@ extern "C" int rb_map_knum(rb_map *m, int *kn) {
 
 extern "C" int rb_map_sync_host_keylines(rb_map *m, rb_keyline *dst, int capacity, int *kn) {
     if (!m) return RB_ERR_ARG;
-    cudaSetDevice(m->c->device);
+    RB_ENTER(m->c);
     rb_ctx *c = m->c;
     MapState s;
     int r = read_state(m, &s);
@@ -520,7 +530,7 @@ extern "C" int rb_map_sync_host_keylines(rb_map *m, rb_keyline *dst, int capacit
 
 extern "C" int rb_map_load_keylines(rb_map *m, const rb_keyline *src, int kn, const int32_t *mask) {
     if (!m) return RB_ERR_ARG;
-    cudaSetDevice(m->c->device);
+    RB_ENTER(m->c);
     rb_ctx *c = m->c;
     if (kn < 0 || kn > c->kcap) return RB_ERR_ARG;
     rb_keyline *tmp = nullptr;
@@ -548,7 +558,7 @@ extern "C" int rb_map_load_keylines(rb_map *m, const rb_keyline *src, int kn, co
 
 extern "C" int rb_map_get_mask(rb_map *m, int32_t *out) {
     if (!m) return RB_ERR_ARG;
-    cudaSetDevice(m->c->device);
+    RB_ENTER(m->c);
     rb_ctx *c = m->c;
     RB_CUDA(cudaMemcpyAsync(out, m->mask, sizeof(int) * (size_t)c->N, cudaMemcpyDeviceToHost, c->stream));
     RB_CUDA(cudaStreamSynchronize(c->stream));

@@ -25,7 +25,7 @@ static int stage_in(rb_ctx *c, const double *src, int n, int off) {
 extern "C" int rb_map_quantile(rb_map *m, double s_rho_min, double s_rho_max, double percentile, int nbins,
                                double *out) {
     if (!m) return RB_ERR_ARG;
-    cudaSetDevice(m->c->device);
+    RB_ENTER(m->c);
     int r = rb_quantile_enqueue(m->c, m, s_rho_min, s_rho_max, percentile, nbins);
     if (r) return r;
     MapState s;
@@ -36,7 +36,7 @@ extern "C" int rb_map_quantile(rb_map *m, double s_rho_min, double s_rho_max, do
 
 extern "C" int rb_map_build_field(rb_map *m, int radius, float min_mod) {
     if (!m) return RB_ERR_ARG;
-    cudaSetDevice(m->c->device);
+    RB_ENTER(m->c);
     int r = rb_build_field_enqueue(m->c, m, radius, min_mod, false);
     if (r) return r;
     return rb_ctx_sync(m->c);
@@ -59,7 +59,7 @@ __global__ void k_field_unpack(const unsigned long long *__restrict__ f, int2 *_
 
 extern "C" int rb_map_get_field(rb_map *m, int32_t *out) {
     if (!m) return RB_ERR_ARG;
-    cudaSetDevice(m->c->device);
+    RB_ENTER(m->c);
     rb_ctx *c = m->c;
     int2 *tmp = nullptr;
     RB_CUDA(cudaMalloc(&tmp, sizeof(int2) * (size_t)c->N));
@@ -77,7 +77,7 @@ extern "C" int rb_map_get_field(rb_map *m, int32_t *out) {
 
 extern "C" int rb_map_set_frame_count(rb_map *m, uint32_t fc) {
     if (!m) return RB_ERR_ARG;
-    cudaSetDevice(m->c->device);
+    RB_ENTER(m->c);
     rb_ctx *c = m->c;
     RB_CUDA(cudaMemcpyAsync(&m->st->frame_count, &fc, sizeof(fc), cudaMemcpyHostToDevice, c->stream));
     RB_CUDA(cudaStreamSynchronize(c->stream));
@@ -88,7 +88,7 @@ extern "C" int rb_try_vel_rot(rb_map *fmap, rb_map *old, const double X[6], int 
                               double match_thresh, double s_rho_min, uint32_t match_num_thresh, double k_huber,
                               const double *res_in, double *res_out, double JtJ[36], double JtF[6], double *score) {
     if (!fmap || !old) return RB_ERR_ARG;
-    cudaSetDevice(fmap->c->device);
+    RB_ENTER(fmap->c);
     rb_ctx *c = fmap->c;
     MapState so, sf;
     int r;
@@ -119,7 +119,7 @@ extern "C" int rb_minimizer_rv(rb_map *fmap, rb_map *old, double V[3], double W[
                                double *rel_error, double *rel_error_score, double max_s_rho,
                                uint32_t match_num_thresh, int init_iter, double W_X[36], double *score) {
     if (!fmap || !old) return RB_ERR_ARG;
-    cudaSetDevice(fmap->c->device);
+    RB_ENTER(fmap->c);
     rb_ctx *c = fmap->c;
     int r;
     double vw[6] = {V[0], V[1], V[2], W[0], W[1], W[2]};
@@ -152,7 +152,7 @@ extern "C" int rb_minimizer_rv(rb_map *fmap, rb_map *old, double V[3], double W[
 
 extern "C" int rb_forward_match(rb_map *old, rb_map *neu, int *nmatch) {
     if (!old || !neu) return RB_ERR_ARG;
-    cudaSetDevice(old->c->device);
+    RB_ENTER(old->c);
     int r = rb_forward_match_enqueue(old->c, old, neu);
     if (r) return r;
     MapState s;
@@ -163,7 +163,7 @@ extern "C" int rb_forward_match(rb_map *old, rb_map *neu, int *nmatch) {
 
 extern "C" int rb_map_rotate_keylines(rb_map *m, const double R[9]) {
     if (!m) return RB_ERR_ARG;
-    cudaSetDevice(m->c->device);
+    RB_ENTER(m->c);
     rb_ctx *c = m->c;
     int r;
     if ((r = stage_in(c, R, 9, 16))) return r;
@@ -175,7 +175,7 @@ extern "C" int rb_directed_matching(rb_map *neu, rb_map *old, const double Vel[3
                                     const double BackRot[9], double min_thr_mod, double min_thr_ang,
                                     double max_radius, double loc_uncertainty, int *nmatch) {
     if (!neu || !old) return RB_ERR_ARG;
-    cudaSetDevice(neu->c->device);
+    RB_ENTER(neu->c);
     rb_ctx *c = neu->c;
     // Vel=BackRot*Vel; RVel=BackRot*RVel*BackRot.T()  (edge_tracker.cpp:324-325), TooN dot order
     DMatchArgs a;
@@ -211,7 +211,7 @@ extern "C" int rb_directed_matching(rb_map *neu, rb_map *old, const double Vel[3
 
 extern "C" int rb_map_regularize(rb_map *m, double thresh, int *r_num) {
     if (!m) return RB_ERR_ARG;
-    cudaSetDevice(m->c->device);
+    RB_ENTER(m->c);
     int r = rb_regularize_enqueue(m->c, m, thresh, nullptr);
     if (r) return r;
     MapState s;
@@ -222,7 +222,7 @@ extern "C" int rb_map_regularize(rb_map *m, double thresh, int *r_num) {
 
 extern "C" int rb_map_ekf_update(rb_map *m, const double vel[3], double reshape_q_abs, double loc_uncertainty) {
     if (!m) return RB_ERR_ARG;
-    cudaSetDevice(m->c->device);
+    RB_ENTER(m->c);
     rb_ctx *c = m->c;
     int r;
     if ((r = stage_in(c, vel, 3, 64))) return r;
@@ -233,7 +233,7 @@ extern "C" int rb_map_ekf_update(rb_map *m, const double vel[3], double reshape_
 extern "C" int rb_map_rescale_opt(rb_map *m, double s_rho_min, uint32_t match_num_min, int re_escale, double *Kp,
                                   double *RKp) {
     if (!m) return RB_ERR_ARG;
-    cudaSetDevice(m->c->device);
+    RB_ENTER(m->c);
     int r = rb_rescale_enqueue(m->c, m, s_rho_min, match_num_min, re_escale, nullptr);
     if (r) return r;
     MapState s;

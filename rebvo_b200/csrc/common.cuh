@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "../../include/rebvo_b200.h"
 
 #define RB_RHO_MAX 20.0   // include/mtracklib/edge_finder.h:38
@@ -66,6 +68,7 @@ struct DogWS {           // batched scale-space workspace, B images of N floats 
 };
 
 struct rb_ctx {
+    std::recursive_mutex *mtx;   // the stage-level C ABI may be called from several host threads (RB_ENTER)
     int device;
     cudaStream_t stream;
     rb_camera cam;
@@ -167,6 +170,14 @@ struct rb_map {
     TrackState ts_host;  // host copy of the pointers inside *ts
     int field_radius;
 };
+
+// Every stage-level entry point starts with RB_ENTER(ctx): the calls of one context share its stream and its pinned /
+// device staging areas, and the reference's detector thread and tracker thread call into the library concurrently
+// (include/UtilLib/pipeline.h:42-89 only serialises per ring slot).  The lock makes each call atomic with respect to the
+// context; it also selects the context's device for the calling thread.
+#define RB_ENTER(ctxp)                                                \
+    std::lock_guard<std::recursive_mutex> rb_lock__(*(ctxp)->mtx);    \
+    cudaSetDevice((ctxp)->device)
 
 #define RB_CUDA(call)                                                                          \
     do {                                                                                       \

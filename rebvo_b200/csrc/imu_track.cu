@@ -228,7 +228,7 @@ extern "C" int rb_try_vel(rb_map *fmap, rb_map *old, const double Vel[3], double
                           uint32_t match_num_thresh, double *residuals, double reweigth_distance, float min_mod,
                           double JtJ[9], double JtF[3], double *score) {
     if (!fmap || !old) return RB_ERR_ARG;
-    cudaSetDevice(fmap->c->device);
+    RB_ENTER(fmap->c);
     rb_ctx *c = fmap->c;
     if (fmap->field_radius <= 0) return RB_ERR_STATE;
     MapState so;
@@ -251,7 +251,7 @@ extern "C" int rb_minimizer_v(rb_map *fmap, rb_map *old, double Vel[3], double R
                               double s_rho_min, uint32_t match_num_thresh, double reweigth_distance, float min_mod,
                               double *score) {
     if (!fmap || !old) return RB_ERR_ARG;
-    cudaSetDevice(fmap->c->device);
+    RB_ENTER(fmap->c);
     rb_ctx *c = fmap->c;
     if (fmap->field_radius <= 0) return RB_ERR_STATE;
     int r;
@@ -352,7 +352,7 @@ __global__ void k_fold27(const double *__restrict__ partials, int nb, double *ou
 extern "C" int rb_ext_rot_vel(rb_map *m, const double vel[3], double Wx[36], double Rx[36], double X[6],
                               double loc_uncertainty, double hub_reweight, int *ok) {
     if (!m) return RB_ERR_ARG;
-    cudaSetDevice(m->c->device);
+    RB_ENTER(m->c);
     rb_ctx *c = m->c;
     double *args = (double *)((char *)c->dev_small + RB_DS_ARGS), *pin = (double *)((char *)c->pinned + RB_DS_ARGS);
     memcpy(pin, vel, sizeof(double) * 3);

@@ -160,6 +160,7 @@ int rb_undistort_enqueue(rb_undistort *u, const uint8_t *in_dev, uint8_t *out_de
 
 extern "C" int rb_undistort_rgb_dev(rb_undistort *u, const uint8_t *in_dev, uint8_t *out_dev, int nimg) {
     if (!u || !in_dev || !out_dev || nimg < 1 || in_dev == out_dev) return RB_ERR_ARG;
+    RB_ENTER(u->c);
     return rb_undistort_enqueue(u, in_dev, out_dev, nimg);
 }
 
@@ -167,6 +168,7 @@ extern "C" int rb_undistort_rgb_dev(rb_undistort *u, const uint8_t *in_dev, uint
 extern "C" int rb_undistort_rgb(rb_undistort *u, const uint8_t *in, uint8_t *out) {
     if (!u || !in || !out) return RB_ERR_ARG;
     rb_ctx *c = u->c;
+    RB_ENTER(c);
     RB_CUDA(cudaMemcpyAsync(u->tmp_in, in, (size_t)3 * c->N, cudaMemcpyHostToDevice, c->stream));
     int r = rb_undistort_enqueue(u, u->tmp_in, u->tmp_out, 1);
     if (r) return r;
