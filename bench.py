@@ -348,8 +348,172 @@ def bench_ours(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: synthetic 1280x960, ~30 k keylines, 8 frames per batch, several independent sequences per GPU
+# (each its own rb_pipeline: own context, streams and CUDA graphs; one-cluster minimiser so that co-residency is
+# guaranteed whatever the other pipelines do) x N GPUs.  Throughput test: frames of all sequences / device time.
+# ---------------------------------------------------------------------------------------------------------------------
+BIG_CAM = dict(w=1280, h=960, zfx=780.0, zfy=778.0, ppx=640.5, ppy=479.25)
+WORKLOAD4 = ("configs[3]: synthetic 1280x960 stream, ~30k keylines per frame (ReferencePoints=30000, MaxPoints=40000), "
+             "batches of 8 frames, %d independent sequences per GPU")
+METRIC4 = "frames/sec @1280x960 synthetic 30k-keyline streams, 8-frame batches, several sequences per GPU, detect+track+map"
+
+
+def big_params(capi):
+    return capi.default_params(BIG_CAM, kl_ref=30000, kl_max=40000, TrackPoints=24000, kl_capacity=40000)
+
+
+def big_stream(seed, total, base_n=24):
+    from rebvo_b200 import synth
+    seq = synth.Sequence(w=BIG_CAM["w"], h=BIG_CAM["h"], seed=seed, zf=BIG_CAM["zfx"], nrect_bg=1500, nrect_fg=200)
+    base_n = min(base_n, total)
+    _, base = seq.frames(base_n)
+    return base
+
+
+def walk_index(total, base_n, start):
+    period = max(1, 2 * (base_n - 1))
+    idx = (np.arange(total) + start) % period
+    return np.where(idx < base_n, idx, period - idx)
+
+
+def bench_config4(args):
+    import threading as th
+    import torch
+    from rebvo_b200 import multi
+    rank, local_rank, world = multi.rank_info()
+    dist = None
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist = multi.init("nccl", device=torch.device("cuda", local_rank))
+    dev = local_rank if world > 1 else 0
+    torch.cuda.set_device(dev)
+    os.environ.setdefault("REBVO_B200_MIN_G", "1")       # one cluster per minimisation: pipelines share the GPU
+    os.environ.setdefault("REBVO_B200_MIN_KPC", "2528")  # 40 k keylines per map in shared memory
+    from rebvo_b200 import capi
+    S, B, K, W = args.seqs, 8, args.steps, args.warmup
+    total = B * (K + W)
+    base = big_stream(100 + rank, total)
+    base_n = len(base)
+    h, w = BIG_CAM["h"], BIG_CAM["w"]
+    fbytes = h * w * 3
+    ts = np.arange(total) / 20.0
+    params = big_params(capi)
+    host, devb, pls = [], [], []
+    for s in range(S):   # sequence s walks the rendered frames from its own starting point
+        idx = walk_index(total, base_n, 3 * s)
+        hb = torch.empty((total, h, w, 3), dtype=torch.uint8, pin_memory=True)
+        hb.numpy()[:] = base[idx]
+        host.append(hb)
+        devb.append(hb.to("cuda:%d" % dev))
+        pls.append(capi.Pipeline(params, max_batch=B, device=dev))
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(on_device):
+        navs = [[] for _ in range(S)]
+        errs = []
+
+        def worker(s, lo, hi):
+            try:
+                for k in range(lo, hi):
+                    sl = slice(k * B, (k + 1) * B)
+                    if on_device:
+                        navs[s].append(pls[s].push_dev(devb[s][k * B].data_ptr(), ts[sl]))
+                    else:
+                        navs[s].append(pls[s].push(host[s][k * B].data_ptr(), ts[sl]))
+            except Exception as e:   # noqa
+                errs.append(e)
+
+        def phase(lo, hi):
+            thr = [th.Thread(target=worker, args=(s, lo, hi)) for s in range(S)]
+            for t in thr:
+                t.start()
+            for t in thr:
+                t.join()
+            if errs:
+                raise errs[0]
+
+        for p in pls:
+            p.reset()
+        phase(0, W)
+        barrier()
+        l0 = sum(p.launches() for p in pls)
+        pls[0].event_record(0)
+        phase(W, W + K)
+        for p in pls:
+            p.event_record(1)
+        barrier()
+        ms = max(p.event_elapsed_from(pls[0], 0, 1) for p in pls)
+        return ms, sum(p.launches() for p in pls) - l0, [np.concatenate(n) for n in navs]
+
+    sampler = ClockSampler(dev)
+    c0 = sampler.mark()
+    t_dev_ms, launches, nav_dev = run(True)
+    c1 = sampler.mark()
+    t_e2e_ms, _, nav_e2e = run(False)
+    sampler.stop()
+    clocks = sampler.summary(c0, c1)
+    t_max, t_e2e_max = multi.max_over_ranks(dist, [t_dev_ms, t_e2e_ms], device="cuda:%d" % dev)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    frames = S * K * B
+    value = multi.aggregate_fps(frames, world, t_max)
+    e2e = multi.aggregate_fps(frames, world, t_e2e_max)
+    cpu = None
+    parity = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import refapi
+            from rebvo_b200 import synth
+            n = min(40, total)
+            idx = walk_index(total, base_n, 0)
+            path = "/tmp/rebvo_b200_bench4_%d.bin" % os.getpid()
+            synth.write_frames_file(path, ts[:n], base[idx[:n]])
+            kv = refapi.ref_params_from(params, Warmup=8)
+            if (os.cpu_count() or 1) >= 3:
+                kv.update(SetAffinity=1, CPU0=0, CPU1=1, CPU2=2)
+            try:
+                info, rec = refapi.run_full_rebvo(path, path + ".out", kv, timeout=1800)
+            finally:
+                for f in (path, path + ".out"):
+                    if os.path.exists(f):
+                        os.remove(f)
+            cpu = {"value": info["fps"], "unit": "frames/s", "cores": 3, "kind": "reference", "cpu_model": cpu_model(),
+                   "sample": "%d frames of sequence 0 (8 warm-up) through the unmodified 3-thread REBVO" % n}
+            parity = refapi.trajectory_parity(rec, nav_dev[0])
+        except Exception as e:
+            cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (e,)}
+    out = {"metric": METRIC4, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+           "ms_per_step": t_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32 scale space/detector + f64 tracker/EKF", "data": "synthetic",
+           "config": {"workload": WORKLOAD4 % S, "frames_per_step": S * B, "sequences_per_gpu": S, "sequences": S * world,
+                      "parallelism": "replicas x%d, %d pipelines per GPU" % (world, S),
+                      "l2": "inputs larger than L2: %.0f MB of frames + scale-space planes in flight per step" % (S * B * 38 * h * w / 1e6),
+                      "keylines_mean": float(np.mean([n["kn"].mean() for n in nav_dev])),
+                      "tracked_ok_frac": float(np.mean([n["estimation_ok"][1:].mean() for n in nav_dev])),
+                      "minimizer": "one 16-CTA cluster per sequence (REBVO_B200_MIN_G=1)",
+                      "dev_vs_e2e_identical_pose": bool(all(np.array_equal(a["Pos"], b["Pos"]) for a, b in zip(nav_dev, nav_e2e)))},
+           "clocks": clocks,
+           "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": S * B * fbytes,
+                   "d2h_bytes_per_step": S * B * capi.NAV.itemsize, "ms_per_step": t_e2e_max / K},
+           "gpu_launches": int(launches), "gpu_launches_per_frame": launches / frames,
+           "parity": parity, "roofline": None, "cpu_baseline": cpu}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4], help="BASELINE.json configs index + 1 (2: 752x480 replay, 4: 1280x960 multi-sequence)")
+    ap.add_argument("--seqs", type=int, default=8, help="config 4: independent sequences per GPU")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
@@ -359,6 +523,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         bench_reference(args)
+    elif args.config == 4:
+        bench_config4(args)
     else:
         bench_ours(args)
 

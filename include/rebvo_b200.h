@@ -247,6 +247,7 @@ void *rb_pipeline_stream(rb_pipeline *pl);
 /* CUDA-event stopwatch on the pipeline's own stream (bench.py): record slot 0..7, elapsed(a,b) in ms
  * (synchronises on event b) */
 int rb_pipeline_event_record(rb_pipeline *pl, int slot);
+int rb_pipeline_event_elapsed_between(rb_pipeline *pa, int a, rb_pipeline *pb, int b, float *ms);
 int rb_pipeline_event_elapsed(rb_pipeline *pl, int a, int b, float *ms);
 /* Measurement hook: re-run ONE scale-space pass over the pipeline's batched workspace `iters` times and
  * return the mean CUDA-event duration per launch.  pass_id: 0 row pass (plain), 1 row pass with box
@@ -254,6 +255,12 @@ int rb_pipeline_event_elapsed(rb_pipeline *pl, int a, int b, float *ms);
  * bytes_per_launch receives the algorithmic bytes of one launch. */
 int rb_pipeline_bench_pass(rb_pipeline *pl, int pass_id, int nimg, int iters, float *ms_per_launch,
                            double *bytes_per_launch);
+
+/* Wire egress of an edge map (monocular): the 15-byte packed net_keyline records of copy_net_keyline +
+ * copy_net_keyline_nextid (src/CommLib/net_keypoint.cpp:29-107, struct net_keyline include/CommLib/net_keypoint.h:37-62,
+ * NET_RHO_SCALING = 1e4), built on the device from the SoA: dst receives min(kn, capacity) records of 15 bytes, *n_out their
+ * number.  k_prof is the depth scale the third thread passes (pbuf.K, rebvo_third_t.cpp:192). */
+int rb_map_pack_net_keylines(rb_map *m, double k_prof, void *dst, int capacity, int *n_out);
 
 #ifdef __cplusplus
 }

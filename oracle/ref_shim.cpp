@@ -40,6 +40,7 @@ static void M3out(const Matrix<3, 3> &r, double *m) {
         for (int j = 0; j < 3; j++) m[i * 3 + j] = r(i, j);
 }
 
+#include "CommLib/net_keypoint.h"
 extern "C" {
 
 int ref_sizeof_keyline() { return (int)sizeof(KeyLine); }
@@ -219,6 +220,14 @@ int ref_directed_matching(void *pn, void *po, const double *V, const double *RVe
     return mn->ef->directed_matching(makeVector(V[0], V[1], V[2]), M3(RVel), M3(BackRot), mo->ef,
                                      *kf_matchs, thr_mod, thr_ang, max_radius, loc_unc, false);
 }
+// copy_net_keyline + copy_net_keyline_nextid (src/CommLib/net_keypoint.cpp:29-107), monocular; out: 15 bytes per record
+int ref_pack_net(void *p, unsigned char *out, int kl_size, double k_prof) {
+    RefMap *m = (RefMap *)p;
+    const int n = copy_net_keyline(*m->ef, nullptr, (net_keyline *)out, kl_size, k_prof);
+    copy_net_keyline_nextid(*m->ef, (net_keyline *)out, kl_size);
+    return n;
+}
+int ref_sizeof_net_keyline() { return (int)sizeof(net_keyline); }
 int ref_num_matches(void *p) { return ((RefMap *)p)->ef->NumMatches(); }
 // edge_tracker::Regularize_1_iter (edge_tracker.cpp:87-148)
 int ref_regularize(void *p, double thresh) { return ((RefMap *)p)->ef->Regularize_1_iter(thresh); }

@@ -116,6 +116,13 @@ class RefMap:
         self.L.ref_get_keylines(self.h_, _p(out))
         return out
 
+    def pack_net(self, k_prof=1.0):
+        """The reference's wire packer (copy_net_keyline + copy_net_keyline_nextid): uint8 [n, 15]."""
+        assert self.L.ref_sizeof_net_keyline() == 15
+        out = np.zeros((max(self.knum(), 1), 15), np.uint8)
+        n = self.L.ref_pack_net(self.h_, _p(out), len(out), C.c_double(k_prof))
+        return out[:n]
+
     def set_keylines(self, kl):
         kl = np.ascontiguousarray(kl, KEYLINE)
         self.L.ref_set_keylines(self.h_, _p(kl), len(kl))

@@ -65,10 +65,10 @@ SYMBOLS = ["rb_ctx_create", "rb_ctx_destroy", "rb_last_error", "rb_ctx_sync", "r
            "rb_map_rescale_opt", "rb_map_set_frame_count", "rb_pipeline_create", "rb_pipeline_destroy",
            "rb_pipeline_last_error", "rb_pipeline_push", "rb_pipeline_push_dev", "rb_pipeline_reset",
            "rb_pipeline_map", "rb_pipeline_launch_count", "rb_pipeline_stage_ms", "rb_pipeline_stream",
-           "rb_pipeline_event_record", "rb_pipeline_event_elapsed", "rb_pipeline_bench_pass",
+           "rb_pipeline_event_record", "rb_pipeline_event_elapsed", "rb_pipeline_event_elapsed_between", "rb_pipeline_bench_pass",
            "rb_pipeline_stage_profile",
            "rb_undistort_create", "rb_undistort_destroy", "rb_undistort_rgb", "rb_undistort_rgb_dev",
-           "rb_try_vel", "rb_minimizer_v", "rb_ext_rot_vel", "rb_bias_correct"]
+           "rb_try_vel", "rb_minimizer_v", "rb_ext_rot_vel", "rb_bias_correct", "rb_map_pack_net_keylines"]
 
 _lib = None
 
@@ -246,6 +246,14 @@ class Map:
         self.ctx.check(self.L.rb_map_sync_host_keylines(self.h_, _p(out), len(out), C.byref(k)))
         return out[:kn]
 
+    def pack_net(self, k_prof=1.0, capacity=None):
+        """15-byte net_keyline records (uint8 array [n, 15]) packed on the device."""
+        cap = capacity if capacity is not None else max(self.knum(), 1)
+        out = np.zeros((cap, 15), np.uint8)
+        k = C.c_int(0)
+        self.ctx.check(self.L.rb_map_pack_net_keylines(self.h_, C.c_double(k_prof), _p(out), cap, C.byref(k)))
+        return out[:k.value]
+
     def load_keylines(self, kl, mask):
         kl = np.ascontiguousarray(kl, KEYLINE)
         mask = np.ascontiguousarray(mask, np.int32)
@@ -409,6 +417,12 @@ class Pipeline:
 
     def event_record(self, slot):
         self.check(self.L.rb_pipeline_event_record(self.h_, slot))
+
+    def event_elapsed_from(self, other, a, b):
+        """ms between event a of pipeline `other` and event b of this pipeline (pipelines sharing a GPU)."""
+        ms = C.c_float(0)
+        self.check(self.L.rb_pipeline_event_elapsed_between(other.h_, a, self.h_, b, C.byref(ms)))
+        return ms.value
 
     def event_elapsed(self, a, b):
         ms = C.c_float(0)

@@ -564,6 +564,14 @@ extern "C" int rb_pipeline_event_elapsed(rb_pipeline *pl, int a, int b, float *m
     RB_CUDA(cudaEventElapsedTime(ms, pl->user_ev[a], pl->user_ev[b]));
     return RB_OK;
 }
+// elapsed time between an event of one pipeline and an event of another (several pipelines share a GPU: bench.py --config 4)
+extern "C" int rb_pipeline_event_elapsed_between(rb_pipeline *pa, int a, rb_pipeline *pb, int b, float *ms) {
+    if (!pa || !pb || a < 0 || a > 7 || b < 0 || b > 7 || !ms) return RB_ERR_ARG;
+    rb_ctx *c = pb->c;
+    RB_CUDA(cudaEventSynchronize(pb->user_ev[b]));
+    RB_CUDA(cudaEventElapsedTime(ms, pa->user_ev[a], pb->user_ev[b]));
+    return RB_OK;
+}
 extern "C" int rb_pipeline_bench_pass(rb_pipeline *pl, int pass_id, int nimg, int iters, float *ms_per_launch,
                                       double *bytes_per_launch) {
     rb_ctx *c = pl->c;

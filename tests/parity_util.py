@@ -17,6 +17,12 @@ TUM_CFG = dict(name="tum", cam=dict(w=640, h=480, zfx=525.0, zfy=525.0, ppx=320.
                kl_ref=15000, track_points=12000, radius=20, match_thresh=1.0, iter_max=10, init_type=2,
                init_iter=2, reweight=2.0, match_num_thresh=4, thr_mod=1.0, thr_ang=45.0, loc_unc_match=2.0,
                reg_thresh=0.5, q_abs=1e-4, loc_unc=1.0)
+# BASELINE.json configs[3]: synthetic 1280x960, ~30 k keylines
+BIG_CFG = dict(name="big", cam=dict(w=1280, h=960, zfx=780.0, zfy=778.0, ppx=640.5, ppy=479.25),
+               sigma0=3.56359, ksigma=1.2599, thresh=0.01, gain=5e-7, tmax=0.5, tmin=0.005, kl_max=40000,
+               kl_ref=30000, track_points=24000, radius=40, match_thresh=0.5, iter_max=5, init_type=2,
+               init_iter=2, reweight=2.0, match_num_thresh=0, thr_mod=1.0, thr_ang=45.0, loc_unc_match=2.0,
+               reg_thresh=0.5, q_abs=1e-4, loc_unc=1.0)
 POS_NEG, DOG_THRESH, PLANE_FIT = 0.4, 0.095259868922420, 2
 
 # KeyLine fields the reference defines at every stage (m_m0 / n_m0 / score are uninitialised until a match)

@@ -7,7 +7,7 @@ minimiser outputs abs 1e-9."""
 import numpy as np
 import pytest
 
-from parity_util import (DOG_THRESH, EUROC_CFG, KL_EXACT_DETECT, PLANE_FIT, POS_NEG, TUM_CFG, Report,
+from parity_util import (BIG_CFG, DOG_THRESH, EUROC_CFG, KL_EXACT_DETECT, PLANE_FIT, POS_NEG, TUM_CFG, Report,
                          compare_keylines)
 
 pytestmark = pytest.mark.gpu
@@ -18,6 +18,9 @@ def _frames(cfg):
     cam = cfg["cam"]
     if cfg["name"] == "tum":
         return synth.frame_pair(seed=42, w=cam["w"], h=cam["h"], nrect=220, shift=(1.5, 0.7))
+    if cfg["name"] == "big":
+        seq = synth.Sequence(w=cam["w"], h=cam["h"], seed=100, zf=cam["zfx"], nrect_bg=1500, nrect_fg=200)
+        return seq.frame(10)[1], seq.frame(11)[1]
     seq = synth.Sequence(w=cam["w"], h=cam["h"], seed=7, zf=cam["zfx"])
     return seq.frame(10)[1], seq.frame(11)[1]
 
@@ -188,7 +191,7 @@ def _run_stage_parity(cfg):
     return rep
 
 
-@pytest.mark.parametrize("cfg", [TUM_CFG, EUROC_CFG], ids=["tum640", "euroc752"])
+@pytest.mark.parametrize("cfg", [TUM_CFG, EUROC_CFG, BIG_CFG], ids=["tum640", "euroc752", "synthetic1280x960"])
 def test_stage_parity(built, cfg):
     rep = _run_stage_parity(cfg)
     # "EKF (bitwise)" is informative: float64 results may differ in the last ulp only through libm-free code
