@@ -63,11 +63,16 @@ int main(int argc, char **argv) {
         return 2;
     }
     std::map<std::string, double> kv;
+    std::map<std::string, std::string> skv;   // file names (ImuFile=..., SE3File=...)
     for (int i = 3; i < argc; i++) {
         char *eq = strchr(argv[i], '=');
-        if (eq) kv[std::string(argv[i], eq - argv[i])] = atof(eq + 1);
+        if (eq) {
+            kv[std::string(argv[i], eq - argv[i])] = atof(eq + 1);
+            skv[std::string(argv[i], eq - argv[i])] = std::string(eq + 1);
+        }
     }
     auto get = [&](const char *k, double d) { return kv.count(k) ? kv[k] : d; };
+    auto gets = [&](const char *k) { return skv.count(k) ? skv[k] : std::string(); };
 
     FILE *f = fopen(argv[1], "rb");
     if (!f) {
@@ -129,13 +134,14 @@ int main(int argc, char **argv) {
     p.simu_time_step = 0;
     p.simu_time_sweep = 0;
     p.simu_time_start = 0;
-    p.ImuMode = 0;
-    p.ImuFile = "";
-    p.UseCamIMUSE3File = false;
-    p.SE3File = "";
-    p.ImuTimeScale = 1;
-    p.InitBias = false;
-    p.InitBiasFrameNum = 10;
+    // IMU fusion (config 3): ImuMode=2 reads the samples from a csv file "t,gx,gy,gz,ax,ay,az" (imugrabber.cpp:80-132)
+    p.ImuMode = (int)get("ImuMode", 0);
+    p.ImuFile = gets("ImuFile");
+    p.SE3File = gets("SE3File");
+    p.UseCamIMUSE3File = !p.SE3File.empty();
+    p.ImuTimeScale = get("ImuTimeScale", 1);
+    p.InitBias = get("InitBias", 0) != 0;
+    p.InitBiasFrameNum = (int)get("InitBiasFrameNum", 10);
     p.BiasInitGuess = TooN::Zeros;
     p.GiroMeasStdDev = 1.6968e-4;
     p.GiroBiasStdDev = 1.9393e-5;
@@ -147,7 +153,7 @@ int main(int argc, char **argv) {
     p.ScaleStdDevMult = 1e-2;
     p.ScaleStdDevMax = 1e-4;
     p.ScaleStdDevInit = 1.2e-3;
-    p.SampleTime = 0.005;
+    p.SampleTime = get("SampleTime", 0.005);
     p.CircBufferSize = 1000;
     p.TimeDesinc = 0;
     p.cpuSetAffinity = (int)get("SetAffinity", 0);

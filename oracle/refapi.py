@@ -285,7 +285,7 @@ def run_full_rebvo(frames_file, out_file, params=None, timeout=600, exe=None):
         # finite, large stack: the reference keeps O(27*8*K) byte VLAs on thread stacks
         resource.setrlimit(resource.RLIMIT_STACK, (1000000 * 1024, resource.RLIM_INFINITY))
 
-    args = [exe or EXE, frames_file, out_file] + ["%s=%r" % (k, v) for k, v in (params or {}).items()]
+    args = [exe or EXE, frames_file, out_file] + ["%s=%s" % (k, v if isinstance(v, str) else repr(v)) for k, v in (params or {}).items()]
     env = dict(os.environ)
     env["LD_LIBRARY_PATH"] = _blas_dir() + ":" + env.get("LD_LIBRARY_PATH", "")
     env.setdefault("OPENBLAS_NUM_THREADS", "1")

@@ -98,3 +98,31 @@ def write_frames_file(path, ts, frames):
         for i in range(n):
             f.write(np.float64(ts[i]).tobytes())
             f.write(frames[i].tobytes())
+
+
+def imu_samples(seq, n_frames, rate=200.0, gyro_bias=(0.02, -0.015, 0.01), gyro_noise=1.7e-4, acc_noise=2e-3, seed=0,
+                g=9.8):
+    """Synthetic IMU stream for a Sequence (SURVEY.md 8(d) config 3 fallback): samples at `rate` Hz covering the
+    frames, columns t[s], gyro xyz [rad/s], accel xyz [m/s^2] in the camera frame.  The synthetic camera does not rotate:
+    the gyroscope measures bias + noise; the accelerometer measures the second derivative of the camera path minus
+    gravity (0, g, 0) (the filter's model a_s + g = k * a_v, scaleestimator.cpp:119-121)."""
+    rng = np.random.default_rng(seed + 77)
+    t = np.arange(-0.25, n_frames / seq.fps + 0.25, 1.0 / rate)
+    h = 1e-3
+
+    def pos(tt):
+        return np.stack([seq.cam_pos(x * seq.fps) for x in tt])
+
+    acc = (pos(t + h) - 2 * pos(t) + pos(t - h)) / (h * h)
+    acc = acc - np.array([0.0, g, 0.0])
+    acc = acc + rng.normal(0, acc_noise, acc.shape)
+    gyro = np.array(gyro_bias)[None, :] + rng.normal(0, gyro_noise, (len(t), 3))
+    return np.concatenate([t[:, None], gyro, acc], axis=1)
+
+
+def write_imu_csv(path, samples):
+    """csv read by ImuGrabber::LoadDataSet (src/UtilLib/imugrabber.cpp:80-132): t,gx,gy,gz,ax,ay,az per line."""
+    with open(path, "w") as f:
+        f.write("#timestamp,w_x,w_y,w_z,a_x,a_y,a_z\n")
+        for r in samples:
+            f.write(",".join("%.17g" % v for v in r) + "\n")

@@ -30,6 +30,7 @@ def test_net_keylines_bytes_equal_reference(built):
     kl["p_m_0"][sel[350:], 0] += rng.uniform(-30, 30, 50).astype(np.float32)
     r = refapi.RefMap(cam["w"], cam["h"], cam["ppx"], cam["ppy"], cam["zfx"], cam["zfy"], 3.56359, 1.2599)
     r.set_keylines(kl)
+    r.set_mask(mask, len(kl))     # (sets the reference object's keyline count)
     ctx = capi.Ctx(cam, 3.56359, 1.2599, kl_capacity=40000)
     g = ctx.new_map()
     g.load_keylines(kl, mask)
