@@ -251,7 +251,7 @@ def bench_ours(args):
         os.environ["REBVO_B200_STAGE_PROF"] = "1"
         try:
             pl3 = capi.Pipeline(params, max_batch=B, device=dev)
-            for s in range(3):
+            for s in range(min(3, K + W)):
                 pl3.push_dev(devbuf[s * B].data_ptr(), ts[s * B:(s + 1) * B])
             stage_us, _ = pl3.stage_profile()
             pl3.close()

@@ -51,6 +51,8 @@ struct rb_pipeline {
     cudaStream_t det_stream;
     cudaEvent_t ev_dog, *ev_det, *ev_trk;
     bool overlap;
+    bool fm_fused;        // FordwardMatch + rotate_keylines as one cluster kernel (env REBVO_B200_FM_FUSED)
+    bool map_fused;       // gate + Regularize_1_iter + EKF inside the map-update cluster kernel (env REBVO_B200_MAP_FUSED)
     // host-input pushes are cut into a short head and the rest: the H2D copy of the rest (copy stream) runs beside the
     // kernels of the head.  The gray kernel reads its RGB source through rgb_src_dev, so one graph serves every region.
     cudaStream_t copy_stream;
@@ -204,6 +206,10 @@ extern "C" int rb_pipeline_create(rb_pipeline **out, int device, const rb_params
         for (int i = 0; i < pl->pcap; i++) RB_CUDA(cudaEventCreate(&pl->pev[i]));
     }
     {
+        const char *mf = getenv("REBVO_B200_MAP_FUSED");
+        pl->map_fused = mf ? atoi(mf) != 0 : false;   // measured slower than the wide kernels under PDL (7.1 k vs 7.4 k frames/s)
+        const char *ff = getenv("REBVO_B200_FM_FUSED");
+        pl->fm_fused = ff ? atoi(ff) != 0 : false;
         const char *ov = getenv("REBVO_B200_OVERLAP");
         pl->overlap = !(ov && ov[0] == '0') && !pl->prof_on;
         pl->ev_det = new (std::nothrow) cudaEvent_t[max_batch];
@@ -333,8 +339,12 @@ static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, const FrameArg
         RB_LAUNCH_CHECK();
     }
     // :354  FordwardMatch ; :369 rotate_keylines(R0)
-    if ((r = rb_forward_match_enqueue(c, old, neu, pl->overlap))) return r;
-    if ((r = rb_rotate_enqueue(c, old, pl->fs->R0))) return r;
+    if (pl->fm_fused && pl->overlap) {   // (the arg-max scratch of the new map was cleared on the detector stream)
+        if ((r = rb_forward_match_rotate_enqueue(c, old, neu, pl->fs->R0))) return r;
+    } else {
+        if ((r = rb_forward_match_enqueue(c, old, neu, pl->overlap))) return r;
+        if ((r = rb_rotate_enqueue(c, old, pl->fs->R0))) return r;
+    }
     RB_TRACE(c->stream, 11);
     prof_mark(pl, ST_FWD_ROT);
     // :410  directed_matching(V,P_V,R,old_buf.ef,...)
@@ -345,14 +355,15 @@ static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, const FrameArg
     prof_mark(pl, ST_DMATCH);
     // :410-423 match-count gate + :452-470 Regularize_1_iter / UpdateInverseDepthKalman on wide grids, then
     // :480-487 EstimateReScalingOpt and :545-585 pose integration + NavData in one cluster kernel (k_map_update)
-    if ((r = rb_regularize_ekf_enqueue(c, neu, p.RegularizeThresh, pl->fs, p.MatchThreshold, pl->fs->V,
-                                       p.ReshapeQAbsolute, p.LocationUncertainty, &pl->fs->do_map)))
-        return r;
+    if (!pl->map_fused)
+        if ((r = rb_regularize_ekf_enqueue(c, neu, p.RegularizeThresh, pl->fs, p.MatchThreshold, pl->fs->V,
+                                           p.ReshapeQAbsolute, p.LocationUncertainty, &pl->fs->do_map)))
+            return r;
     RB_TRACE(c->stream, 9);
     prof_mark(pl, ST_REG_EKF);
     if ((r = rb_map_update_enqueue(c, neu, p.RegularizeThresh, pl->fs->V, p.ReshapeQAbsolute, p.LocationUncertainty,
                                    RB_RHO_MAX, 1, p.DoReScaling > 0 ? 1 : 0, pl->fs, p.MatchThreshold, old->st,
-                                   nav_slot, fa)))
+                                   nav_slot, fa, pl->map_fused)))
         return r;
     prof_mark(pl, ST_RESCALE);   // rescaling + pose integration / nav record (folded)
     RB_TRACE(c->stream, 5);

@@ -1049,6 +1049,7 @@ static int launch_eval_step(rb_ctx *c, rb_map *fmap, rb_map *old, int step) {
 
 // per-device set-up of the cluster minimiser (rb_ctx_create, after cudaSetDevice): opt-ins + how many keylines per CTA
 // fit.  Leaves c->min_cluster_kpc = 0 when the device cannot run it (the one-launch-per-evaluation path serves then).
+void rb_mapper_cluster_setup();   // (defined after the mapper's cluster kernels)
 template <typename K>
 static bool mc_prepare(K kern, int threads, int clusters, size_t dyn, int dev_max) {
     cudaFuncAttributes fa;
@@ -1064,6 +1065,7 @@ static bool mc_prepare(K kern, int threads, int clusters, size_t dyn, int dev_ma
     return cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) == cudaSuccess && ncl >= clusters;
 }
 int rb_minimizer_cluster_setup(rb_ctx *c) {
+    rb_mapper_cluster_setup();
     c->min_cluster_kpc = 0;
     c->min_cluster_g = 1;
     const char *fa_ = getenv("REBVO_B200_MIN_FORCE_ABORT");
@@ -1384,6 +1386,50 @@ __global__ void __launch_bounds__(256) k_rotate(KLSoA kl, const MapState *st, co
     d_rotate(kl, i, Rp, zf);
 }
 
+// FordwardMatch + rotate_keylines of the per-frame pipeline in ONE 16-CTA cluster kernel: the three passes of the arg-max
+// (atomicMax of rho, atomicMax of the index among the maxima, apply) are separated by grid-wide dependencies; as four
+// launches a frame paid ~12 us for ~2 us of work.  barrier.cluster (release / acquire at cluster scope) orders the L2
+// atomics of one pass before the reads of the next.  The arg-max scratch was cleared on the detector stream.
+#define FR_C 16
+#define FR_T 512
+__global__ void __cluster_dims__(FR_C, 1, 1) __launch_bounds__(FR_T) k_fwd_rotate(KLSoA old, KLSoA neu, const MapState *ost,
+                                                                                 MapState *nst, unsigned long long *best,
+                                                                                 int *idx, const double *__restrict__ Rp,
+                                                                                 double zf) {
+    pdl_wait();
+    pdl_launch();
+    const int t0 = blockIdx.x * FR_T + threadIdx.x, stride = FR_C * FR_T;
+    const int okn = ost->kn, nkn = nst->kn;
+    for (int i = t0; i < okn; i += stride) d_fm_pass1(old, i, nkn, best);
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    for (int i = t0; i < okn; i += stride) d_fm_pass2(old, i, nkn, best, idx);
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    int cnt = 0;
+    for (int f = t0; f < nkn; f += stride) cnt += d_fm_apply(old, neu, f, idx) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&nst->fwd_match, cnt);
+    // every read of the old keylines' p_m / m_m by the apply pass must precede their rotation
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    for (int i = t0; i < okn; i += stride) d_rotate(old, i, Rp, zf);
+}
+int rb_forward_match_rotate_enqueue(rb_ctx *c, rb_map *old, rb_map *neu, const double *R_dev) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(FR_C);
+    cfg.blockDim = dim3(FR_T);
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = c->pdl ? 1 : 0;
+    TrackState &t = neu->ts_host;
+    c->launches++;
+    RB_CUDA(cudaLaunchKernelEx(&cfg, k_fwd_rotate, old->kl, neu->kl, (const MapState *)old->st, neu->st, t.fm_best, t.fm_idx,
+                               R_dev, c->zfm));
+    return RB_OK;
+}
+
 int rb_rotate_enqueue(rb_ctx *c, rb_map *m, const double *R_dev) {
     RB_KLAUNCH(k_rotate, rb_div_up(c->kcap, 256), 256, 0, m->kl, (const MapState *)m->st, R_dev, c->zfm);
     return RB_OK;
@@ -1691,10 +1737,10 @@ int rb_regularize_ekf_enqueue(rb_ctx *c, rb_map *m, double thresh, FrameState *f
 //
 // These stages are light per keyline but separated by grid-wide dependencies (the smoothing reads neighbours, each
 // of the five rescaling iterations needs sums over all keylines): as separate kernels, or as one kernel exchanging
-// through L2, a frame paid ~40 us of launch / hand-over latency for ~3 us of arithmetic.  A cluster of 8 CTAs holds
-// the whole edge map (thread t of CTA r owns keylines (j*8 + r)*MU_T + t), synchronises with barrier.cluster and
+// through L2, a frame paid ~40 us of launch / hand-over latency for ~3 us of arithmetic.  A cluster of 16 CTAs holds
+// the whole edge map (thread t of CTA r owns keylines (j*16 + r)*MU_T + t), synchronises with barrier.cluster and
 // all-reduces the two sums of an iteration through distributed shared memory: every CTA stores its pair into every
-// CTA's slot table, one cluster barrier, every CTA adds the 8 pairs in rank order.  One launch, ~6 cluster barriers.
+// CTA's slot table, one cluster barrier, every CTA adds the 16 pairs in rank order.  One launch, ~6 cluster barriers.
 // Sums: per thread in keyline order, warp xor-tree, warps in order, ranks in order -- fixed, not the reference's
 // sequential order (parity to rounding, as for every other reduction here).
 // The optional head / tail are the per-frame pipeline's scalar glue (frame.cuh), folded in to save their launches.
@@ -1702,8 +1748,8 @@ int rb_regularize_ekf_enqueue(rb_ctx *c, rb_map *m, double thresh, FrameState *f
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 #define MU_T 512
-#define MU_C 8
-#define MU_KJ 4   // keylines per thread whose rescaling operands stay in registers (kn <= MU_KJ*MU_C*MU_T = 16384)
+#define MU_C 16   // (non-portable cluster size, like the minimiser's)
+#define MU_KJ 2   // keylines per thread whose rescaling operands stay in registers (kn <= MU_KJ*MU_C*MU_T = 16384)
 
 struct MapUpdArgs {
     int do_reg, do_ekf, do_rescale, re_escale, gate_post_match;
@@ -1884,10 +1930,12 @@ static int launch_map_update(rb_ctx *c, rb_map *m, const MapUpdArgs &a) {
 // the pipeline's whole map update (gate, smoothing, EKF, rescaling, pose integration / nav record)
 int rb_map_update_enqueue(rb_ctx *c, rb_map *m, double reg_thresh, const double *vel_dev, double q_abs, double loc_unc,
                           double s_rho_min, unsigned int match_num_min, int re_escale, FrameState *fs,
-                          int match_threshold, const MapState *ost, rb_nav *nav, const FrameArgs *fa) {
+                          int match_threshold, const MapState *ost, rb_nav *nav, const FrameArgs *fa, bool fused) {
     MapUpdArgs a;
     memset(&a, 0, sizeof(a));
-    a.do_reg = a.do_ekf = 0;   // the pipeline runs those two on wide grids (rb_regularize_ekf_enqueue)
+    // fused: the match-count gate, Regularize_1_iter and the EKF run inside this cluster kernel too (one launch instead of
+    // three); otherwise the pipeline has run them on wide grids (rb_regularize_ekf_enqueue) and published fs->do_map
+    a.do_reg = a.do_ekf = fused ? 1 : 0;
     a.do_rescale = 1;
     a.re_escale = re_escale;
     a.reg_thresh = reg_thresh;
@@ -1899,7 +1947,7 @@ int rb_map_update_enqueue(rb_ctx *c, rb_map *m, double reg_thresh, const double 
     a.mnm = match_num_min;
     a.fs = fs;
     a.enable = &fs->do_map;   // published by k_regularize_a_gate
-    a.gate_post_match = 0;
+    a.gate_post_match = fused ? 1 : 0;
     a.match_threshold = match_threshold;
     a.ost = ost;
     a.lm = &m->ts->lm;
@@ -1919,4 +1967,11 @@ int rb_rescale_enqueue(rb_ctx *c, rb_map *m, double s_rho_min, unsigned int matc
     a.mnm = match_num_min;
     a.enable = enable_dev;
     return launch_map_update(c, m, a);
+}
+
+// per-device opt-in of the mapper's 16-CTA cluster kernels (called from rb_minimizer_cluster_setup at context creation)
+void rb_mapper_cluster_setup() {
+    cudaFuncSetAttribute(k_map_update, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(k_fwd_rotate, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaGetLastError();
 }

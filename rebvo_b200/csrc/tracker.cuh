@@ -50,6 +50,7 @@ int rb_build_field_enqueue(rb_ctx *c, rb_map *m, int radius, float min_mod, bool
 int rb_forward_match_init_enqueue(rb_ctx *c, rb_map *neu);
 int rb_forward_match_enqueue(rb_ctx *c, rb_map *old, rb_map *neu, bool scratch_ready = false);
 int rb_rotate_enqueue(rb_ctx *c, rb_map *m, const double *R_dev);
+int rb_forward_match_rotate_enqueue(rb_ctx *c, rb_map *old, rb_map *neu, const double *R_dev);   // scratch cleared before
 struct DMatchArgs {       // device-resident arguments of directed_matching (after the back-rotation)
     double Vel[3];        // BackRot*Vel
     double RVel[9];       // BackRot*RVel*BackRot^T
@@ -65,7 +66,7 @@ int rb_regularize_ekf_enqueue(rb_ctx *c, rb_map *m, double thresh, FrameState *f
 int rb_map_update_enqueue(rb_ctx *c, rb_map *m, double reg_thresh, const double *vel_dev, double q_abs,
                           double loc_unc, double s_rho_min, unsigned int match_num_min, int re_escale,
                           FrameState *fs, int match_threshold, const MapState *ost, rb_nav *nav,
-                          const FrameArgs *fa);
+                          const FrameArgs *fa, bool fused = false);
 int rb_ekf_enqueue(rb_ctx *c, rb_map *m, const double *vel_dev, double q_abs, double loc_unc,
                    const int *enable_dev);
 int rb_rescale_enqueue(rb_ctx *c, rb_map *m, double s_rho_min, unsigned int match_num_min, int re_escale,
