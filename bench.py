@@ -39,10 +39,28 @@ def rank_info():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
-def make_stream(seed, total, base_n=160):
+TUM_CAM = dict(w=640, h=480, zfx=525.0, zfy=525.0, ppx=320.0, ppy=240.0)
+METRIC5 = "frames/sec @640x480 TUM desk parameters (synthetic stand-in), detect+track+map; pose ATE vs reference in `parity`"
+WORKLOAD5 = ("configs[4]: TUM fr2_desk-like 640x480 replay, app/rebvorun/GlobalConfig_desk.txt parameters (Sigma0 1.7818, auto-"
+             "threshold gain 1e-6, SearchRange 20, TrackerIterNum 10 = 17 TryVelRot evaluations per frame, MatchNumThresh 4); "
+             "synthetic two-layer parallax stream seed 21")
+
+
+def stream_setup(config):
+    """camera, parameters, metric / workload strings of the single-sequence bench configurations"""
+    from rebvo_b200 import capi, synth
+    if config == 5:
+        p = capi.default_params(TUM_CAM, Sigma0=1.7818, kl_max=25000, kl_ref=15000, gain=1e-6, thresh_max=0.05,
+                                thresh_min=0.03, SearchRange=20, TrackerIterNum=10, TrackerMatchThresh=1.0, MatchNumThresh=4,
+                                ReshapeQRelative=1e-2, kl_capacity=25000)
+        return TUM_CAM, p, METRIC5, WORKLOAD5, 21
+    return synth.EUROC, capi.default_params(synth.EUROC), METRIC, WORKLOAD, 7
+
+
+def make_stream(seed, total, base_n=160, cam=None):
     """total frames of a continuous sequence built from base_n rendered frames walked back and forth."""
     from rebvo_b200 import synth
-    cam = synth.EUROC
+    cam = cam or synth.EUROC
     seq = synth.Sequence(w=cam["w"], h=cam["h"], seed=seed, zf=cam["zfx"])
     base_n = min(base_n, total)
     _, base = seq.frames(base_n)
@@ -158,15 +176,25 @@ def bench_reference(args):
         return
     per = max(20, min(60, 600 // (args.steps + args.warmup)))
     total = per * (args.steps + args.warmup) + 2
-    ts, base, idx = make_stream(7, total)
-    info, rec = run_reference("/tmp", ts, base, idx, total, per * args.warmup)
+    if args.config == 4:   # same 1280x960 stream and parameters as the GPU arm's sequence 0
+        from rebvo_b200 import capi
+        cam, params, metric, workload = BIG_CAM, big_params(capi), METRIC4, WORKLOAD4 % args.seqs
+        per = max(8, min(16, 160 // (args.steps + args.warmup)))
+        total = per * (args.steps + args.warmup) + 2
+        base = big_stream(100, total)
+        idx = walk_index(total, len(base), 0)
+        ts = np.arange(total) / 20.0
+    else:
+        cam, params, metric, workload, seed0 = stream_setup(args.config)
+        ts, base, idx = make_stream(seed0, total, cam=cam)
+    info, rec = run_reference("/tmp", ts, base, idx, total, per * args.warmup, gpu_params=params)
     fps = info["fps"]
     ncpu = os.cpu_count() or 1
-    out = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+    out = {"metric": metric, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * per / fps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32 scale space/detector + f64 tracker/EKF", "data": "synthetic",
            "impl": "reference",
-           "config": {"workload": WORKLOAD, "frames_per_step": per, "note": "bounded sample of the bench stream"},
+           "config": {"workload": workload, "frames_per_step": per, "note": "bounded sample of the bench stream"},
            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 3, "kind": "reference", "cpu_model": cpu_model(),
                             "sample": "%d frames (%d timed) through the unmodified 3-thread REBVO, %d host cpus visible"
                             % (total, info["timed_callbacks"], ncpu),
@@ -189,8 +217,8 @@ def bench_ours(args):
     from rebvo_b200 import capi, synth
     B, K, W = args.batch, args.steps, args.warmup
     total = B * (K + W)
-    ts, base, idx = make_stream(multi.stream_seed(rank), total)
-    cam = synth.EUROC
+    cam, params, metric, workload, seed0 = stream_setup(args.config)
+    ts, base, idx = make_stream(multi.stream_seed(rank) + (seed0 - 7), total, cam=cam)
     h, w = cam["h"], cam["w"]
     fbytes = h * w * 3
     # host (pinned) and device copies of the whole stream, batch-contiguous
@@ -198,7 +226,6 @@ def bench_ours(args):
     host.numpy()[:] = base[idx]
     devbuf = host.to("cuda:%d" % dev)
     torch.cuda.synchronize()
-    params = capi.default_params(cam)
 
     def barrier():
         if dist is not None:
@@ -330,10 +357,10 @@ def bench_ours(args):
         except Exception as e:  # the oracle is test infrastructure; its absence must not break the bench
             cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (e,)}
     ok = nav_dev["estimation_ok"]
-    out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+    out = {"metric": metric, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
            "ms_per_step": t_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32 scale space/detector + f64 tracker/EKF", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "frames_per_step": B, "sequences": world, "parallelism": "replicas x%d" % world,
+           "config": {"workload": workload, "frames_per_step": B, "sequences": world, "parallelism": "replicas x%d" % world,
                       "l2": "inputs larger than L2: per-step working set %.0f MB (RGB %.0f MB + scale-space planes)"
                             % (B * (3 + 32) * h * w / 1e6, B * fbytes / 1e6),
                       "keylines_mean": float(nav_dev["kn"].mean()), "tracked_ok_frac": float(ok[1:].mean()),
@@ -512,7 +539,7 @@ def bench_config4(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", type=int, default=2, choices=[2, 4], help="BASELINE.json configs index + 1 (2: 752x480 replay, 4: 1280x960 multi-sequence)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5], help="BASELINE.json configs index + 1 (2: 752x480 EuRoC-like replay, 4: 1280x960 multi-sequence, 5: 640x480 TUM desk parameters)")
     ap.add_argument("--seqs", type=int, default=8, help="config 4: independent sequences per GPU")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)

@@ -65,6 +65,8 @@ struct DogWS {           // batched scale-space workspace, B images of N floats 
     float *img0;         // B * N    blur 0
     float *dog;          // B * N    blur1 - blur0
     float *aux;          // 3 * N    on-demand planes (Img(1), dx, dy) for the test/debug accessor
+    void *tmaps;         // CUtensorMap[3] (host): I, img0, dog -- TMA-staged last box + DoG (dog.cu)
+    bool tma_ok;
 };
 
 struct rb_ctx {
@@ -110,6 +112,7 @@ struct rb_ctx {
 #define RB_DS_REEST 0        // int[2 + nbins + 1]  reEstimateThresh min/max bits + histogram
 #define RB_DS_CHAIN 32768    // DetChain for the single-map detect API
 #define RB_DS_ARGS 36864     // argument / result staging of the stage-level API (4 KiB)
+#define RB_DS_TMA_FAIL 45056 // int: a TMA-staged kernel timed out waiting for its tile (checked by the tests)
 #define RB_DS_QHISTO 49152   // int[nbins] EstimateQuantile histogram (kept zero between calls)
 
 // Levenberg-Marquardt variables of Minimizer_RV (global_tracker.cpp:596-625), resident in device memory so
@@ -246,6 +249,7 @@ int rb_dog_gray(rb_ctx *c, DogWS *ws, int nimg, const void *const *src_pp = null
 int rb_dog_build_batch(rb_ctx *c, DogWS *ws, int nimg);          // gray -> img0, dog
 int rb_dog_aux_planes(rb_ctx *c, DogWS *ws, int img);            // Img(1), dx, dy into ws->aux
 int rb_dog_make_tables(rb_ctx *c);
+int rb_dog_make_tmaps(rb_ctx *c, DogWS *ws);
 int rb_dog_device_setup(rb_ctx *c);
 // detect.cu
 int rb_detect_enqueue(rb_ctx *c, rb_map *m, const float *img0, const float *dog,

@@ -13,6 +13,9 @@
 //   k_rowscan<AVG> : S(x,y)  = sum_{i<=x} avg(I_prev)(i,y)   warp per 32-row band, smem-transposed tiles
 //   k_colscan      : I(x,y)  = sum_{j<=y} S(x,j)              thread per 4 columns, float4 streams
 // and a final k_blur_dog that evaluates the last box of both filters, Img(0) and the DoG.
+#include <stdlib.h>
+#include <new>
+
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------------
@@ -201,6 +204,164 @@ __global__ void __launch_bounds__(256) k_blur_dog(const float *__restrict__ I, f
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Last box + DoG with TMA-staged tiles.  k_blur_dog above reads its 2 x 4 taps per pixel through L1 with unaligned,
+// overlapping row segments (41 % of the copy peak).  Here a CTA owns a 64 x 32 output tile: ONE elected thread issues two
+// cp.async.bulk.tensor loads (the (64+d) x (32+d) windows of the two filters' integral images, out-of-image parts
+// zero-filled by the TMA unit, completion counted on an mbarrier), every thread evaluates iimage::average from shared
+// memory with box_avg's exact arithmetic, and the two result tiles leave through TMA stores (the unit clips the tiles
+// that stick out of the image).  No per-thread address arithmetic or predication for the window, each integral value is
+// fetched once per tile.
+#include <cuda.h>
+#define BT_W 64
+#define BT_H 32
+#define BT_BW 76            // window width in floats: 64 + 9 (largest box) rounded up to a multiple of 4 (16-byte rows)
+#define BT_BH 41            // 32 + 9
+#define BT_THREADS 256
+struct BlurTmaSmem {       // measured: 64 x 32 tiles (99 us per 64-frame launch); 64 x 16 and 64 x 64 tiles ~120 us; a persistent
+    // two-stage version of this kernel (2 CTAs per SM, next tile's windows in flight) 129 us -- more resident CTAs win
+    alignas(128) float win0[BT_BH][BT_BW];   // (every TMA source / destination tile is 128-byte aligned)
+    alignas(128) float win1[BT_BH][BT_BW];
+    alignas(128) float o0[BT_H][BT_W];
+    alignas(128) float o1[BT_H][BT_W];
+    alignas(8) unsigned long long bar;
+    float tab[2][BOX_TAB_N];
+};
+__device__ __forceinline__ float box_avg_win(const float (*W)[BT_BW], int wx0, int wy0, int x, int y, int w, int h, int d, int d2,
+                                             const float *__restrict__ tab) {
+    // box_avg with the taps read from the staged window (window origin = image (wx0, wy0)); same selects, same order
+    const bool left = x < d2 + 1, right = x >= w - d2;
+    const bool top = y < d2 + 1, bottom = y >= h - d2;
+    const int xr = (right ? w - 1 : x + d2) - wx0, yb = (bottom ? h - 1 : y + d2) - wy0;
+    const int xl = (left ? 0 : x - d2 - 1) - wx0, yt = (top ? 0 : y - d2 - 1) - wy0;
+    const float A = W[yb][xr], B = W[yb][xl], C = W[yt][xr], D = W[yt][xl];
+    const float t1 = bottom ? C : B, t2 = bottom ? B : C;
+    const bool h1 = bottom ? !top : !left, h2 = bottom ? !left : !top;
+    float r = A;
+    r = h1 ? r - t1 : r;
+    r = h2 ? r - t2 : r;
+    r = (!top && !left) ? r + D : r;
+    const int cx = left ? x + d2 + 1 : (right ? w - x + d2 : d);
+    const int cy = top ? y + d2 + 1 : (bottom ? h - y + d2 : d);
+    return r * tab[(cy - d2 - 1) * BOX_TAB_W + (cx - d2 - 1)];
+}
+__global__ void __launch_bounds__(BT_THREADS) k_blur_dog_tma(const __grid_constant__ CUtensorMap tm_in,
+                                                             const __grid_constant__ CUtensorMap tm_img0,
+                                                             const __grid_constant__ CUtensorMap tm_dog, int w, int h,
+                                                             int nimg, int out_slot, int d0, int d1,
+                                                             const float *__restrict__ tab0, const float *__restrict__ tab1,
+                                                             int *fail) {
+    extern __shared__ __align__(128) unsigned char bt_raw[];
+    BlurTmaSmem &sm = *reinterpret_cast<BlurTmaSmem *>((reinterpret_cast<uintptr_t>(bt_raw) + 127) & ~(uintptr_t)127);
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * BT_W, y0 = blockIdx.y * BT_H, b = blockIdx.z;
+    const int d20 = d0 / 2, d21 = d1 / 2;
+    // window origin: the TMA unit wants the first element of a box row 16-byte aligned in global memory, so the windows start
+    // 8 columns left of the tile (left halo <= 5 for the largest box) and are 8 + 64 + 4 = 76 wide
+    const int wx0[2] = {x0 - 8, x0 - 8}, wy0[2] = {y0 - d20 - 1, y0 - d21 - 1};
+    const unsigned int bar = (unsigned int)__cvta_generic_to_shared(&sm.bar);
+    if (tid < BOX_TAB_N) sm.tab[0][tid] = tab0[tid];
+    else if (tid < 2 * BOX_TAB_N) sm.tab[1][tid - BOX_TAB_N] = tab1[tid - BOX_TAB_N];
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int bytes = 2u * BT_BH * BT_BW * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+#pragma unroll
+        for (int f = 0; f < 2; f++) {
+            const unsigned int dst = (unsigned int)__cvta_generic_to_shared(f ? &sm.win1[0][0] : &sm.win0[0][0]);
+            const int z = f * nimg + b;
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                ::"r"(dst), "l"(&tm_in), "r"(wx0[f]), "r"(wy0[f]), "r"(z), "r"(bar)
+                : "memory");
+        }
+    }
+    {   // wait for the two windows (bounded: a broken copy flags an error instead of hanging the device)
+        unsigned int ok = 0;
+        const long long t0 = clock64();
+        while (!ok) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(bar) : "memory");
+            if (!ok && clock64() - t0 > (1ll << 28)) {
+                if (tid == 0) *fail = 1;
+                break;
+            }
+        }
+    }
+    // 64 x 32 pixels, 256 threads: thread = column (tid & 63), rows (tid >> 6) + 4k
+    const int lx = tid & 63, ly0 = tid >> 6;
+    const int x = min(x0 + lx, w - 1);
+#pragma unroll 4
+    for (int k = 0; k < BT_H / 4; k++) {
+        const int ly = ly0 + 4 * k;
+        const int y = min(y0 + ly, h - 1);
+        const float v0 = box_avg_win(sm.win0, wx0[0], wy0[0], x, y, w, h, d0, d20, sm.tab[0]);
+        const float v1 = box_avg_win(sm.win1, wx0[1], wy0[1], x, y, w, h, d1, d21, sm.tab[1]);
+        sm.o0[ly][lx] = v0;
+        sm.o1[ly][lx] = v1 - v0;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA unit
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int s0 = (unsigned int)__cvta_generic_to_shared(&sm.o0[0][0]);
+        const unsigned int s1 = (unsigned int)__cvta_generic_to_shared(&sm.o1[0][0]);
+        const int z = out_slot + b;
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&tm_img0),
+                     "r"(x0), "r"(y0), "r"(z), "r"(s0)
+                     : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&tm_dog), "r"(x0),
+                     "r"(y0), "r"(z), "r"(s1)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory may be released
+    }
+}
+
+// tensor maps of a workspace (driver entry point fetched at run time: the library does not link libcuda)
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool make_tmap3(CUtensorMap *tm, float *base, int w, int h, int nimg, int bw, int bh) {
+    static PFN_tmapEncodeTiled enc = nullptr;
+    if (!enc) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) return false;
+        enc = (PFN_tmapEncodeTiled)fn;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)nimg};
+    const cuuint64_t strides[2] = {(cuuint64_t)w * 4, (cuuint64_t)w * h * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+int rb_dog_make_tmaps(rb_ctx *c, DogWS *ws) {
+    ws->tma_ok = false;
+    const char *e = getenv("REBVO_B200_BLUR_TMA");
+    if (e && atoi(e) == 0) return RB_OK;
+    if ((c->w * 4) % 16) return RB_OK;
+    CUtensorMap *t = new (std::nothrow) CUtensorMap[3];
+    if (!t) return RB_OK;
+    bool ok = make_tmap3(&t[0], ws->I, c->w, c->h, 2 * ws->B, BT_BW, BT_BH) &&
+              make_tmap3(&t[1], ws->img0, c->w, c->h, ws->B, BT_W, BT_H) &&
+              make_tmap3(&t[2], ws->dog, c->w, c->h, ws->B, BT_W, BT_H);
+    ok = ok && cudaFuncSetAttribute(k_blur_dog_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlurTmaSmem) + 128) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        delete[] t;
+        return RB_OK;
+    }
+    ws->tmaps = t;
+    ws->tma_ok = true;
+    return RB_OK;
+}
+
 // sspace::calc_gradient (sspace.cpp:75-85), materialised only for the debug accessor; borders = 0
 __global__ void k_gradient(const float *__restrict__ img0, float *__restrict__ dx, float *__restrict__ dy,
                            int w, int h) {
@@ -229,7 +390,7 @@ int rb_dogws_alloc(rb_ctx *c, DogWS *ws, int B) {
     RB_CUDA(cudaMalloc(&ws->img0, (size_t)B * N * 4));
     RB_CUDA(cudaMalloc(&ws->dog, (size_t)B * N * 4));
     RB_CUDA(cudaMalloc(&ws->aux, (size_t)3 * N * 4));
-    return RB_OK;
+    return rb_dog_make_tmaps(c, ws);
 }
 
 void rb_dogws_free(DogWS *ws) {
@@ -241,6 +402,7 @@ void rb_dogws_free(DogWS *ws) {
     cudaFree(ws->img0);
     cudaFree(ws->dog);
     cudaFree(ws->aux);
+    delete[] (CUtensorMap *)ws->tmaps;
     memset(ws, 0, sizeof(*ws));
 }
 
@@ -439,6 +601,15 @@ static int rowscan(rb_ctx *c, int stage, const float *in, float *out, int nimg, 
 }
 
 static int blur_dog(rb_ctx *c, DogWS *ws, int nimg, float *img1_opt, int out_slot = 0) {
+    if (ws->tma_ok && !img1_opt) {
+        const CUtensorMap *t = (const CUtensorMap *)ws->tmaps;
+        dim3 tg(rb_div_up(c->w, BT_W), rb_div_up(c->h, BT_H), nimg);
+        k_blur_dog_tma<<<tg, BT_THREADS, sizeof(BlurTmaSmem) + 128, c->stream>>>(
+            t[0], t[1], t[2], c->w, c->h, nimg, out_slot, c->plan.d[0][2], c->plan.d[1][2],
+            c->boxtab + (0 * 3 + 2) * BOX_TAB_N, c->boxtab + (1 * 3 + 2) * BOX_TAB_N, (int *)((char *)c->dev_small + RB_DS_TMA_FAIL));
+        RB_LAUNCH_CHECK();
+        return RB_OK;
+    }
     dim3 grid(rb_div_up(c->w, 256), rb_div_up(c->h, BLUR_RY), nimg);
     const size_t off = (size_t)out_slot * c->N;
     k_blur_dog<<<grid, 256, 0, c->stream>>>(ws->I, ws->img0 + off, ws->dog + off, img1_opt, c->w, c->h, nimg,
