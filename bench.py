@@ -46,9 +46,18 @@ WORKLOAD5 = ("configs[4]: TUM fr2_desk-like 640x480 replay, app/rebvorun/GlobalC
              "synthetic two-layer parallax stream seed 21")
 
 
+METRIC3 = ("frames/sec @752x480 EuRoC replay with IMU fusion (ImuMode=2, synthetic stand-in), detect+track+map+scale filter; "
+           "pose ATE vs reference in `parity`")
+WORKLOAD3 = ("configs[2]: EuRoC V1_02-like 752x480 replay with ImuGrabber csv fusion (IMUMode=2), 1xB200; synthetic two-layer "
+             "parallax stream seed 7 + synthetic 200 Hz IMU (gyro bias 0.02 rad/s, noise 1.7e-4)")
+IMU_BASE_N = 160
+
+
 def stream_setup(config):
     """camera, parameters, metric / workload strings of the single-sequence bench configurations"""
     from rebvo_b200 import capi, synth
+    if config == 3:
+        return synth.EUROC, capi.default_params(synth.EUROC), METRIC3, WORKLOAD3, 7
     if config == 5:
         p = capi.default_params(TUM_CAM, Sigma0=1.7818, kl_max=25000, kl_ref=15000, gain=1e-6, thresh_max=0.05,
                                 thresh_min=0.03, SearchRange=20, TrackerIterNum=10, TrackerMatchThresh=1.0, MatchNumThresh=4,
@@ -146,7 +155,7 @@ def cpu_model():
     return "unknown"
 
 
-def run_reference(frames_file_dir, ts, base, idx, n_frames, warm_frames, affinity=True, gpu_params=None):
+def run_reference(frames_file_dir, ts, base, idx, n_frames, warm_frames, affinity=True, gpu_params=None, imu=None):
     """The reference's own CPU implementation (3 pipeline threads) on n_frames of the stream."""
     from oracle import refapi
     from rebvo_b200 import synth
@@ -155,13 +164,18 @@ def run_reference(frames_file_dir, ts, base, idx, n_frames, warm_frames, affinit
     ncpu = os.cpu_count() or 1
     params = refapi.ref_params_from(gpu_params) if gpu_params is not None else {}
     params["Warmup"] = warm_frames
+    csv = None
+    if imu is not None:   # config 3: the reference reads the same samples through ImuGrabber::LoadDataSet
+        csv = path + ".imu.csv"
+        synth.write_imu_csv(csv, imu)
+        params.update(ImuMode=2, ImuFile=csv, ImuTimeScale=1, InitBias=1, InitBiasFrameNum=5)
     if affinity and ncpu >= 3:
         params.update(SetAffinity=1, CPU0=0, CPU1=1, CPU2=2)
     try:
         info, rec = refapi.run_full_rebvo(path, path + ".out", params, timeout=1800)
     finally:
-        for f in (path, path + ".out"):
-            if os.path.exists(f):
+        for f in (path, path + ".out", csv):
+            if f and os.path.exists(f):
                 os.remove(f)
     return info, rec
 
@@ -187,7 +201,12 @@ def bench_reference(args):
     else:
         cam, params, metric, workload, seed0 = stream_setup(args.config)
         ts, base, idx = make_stream(seed0, total, cam=cam)
-    info, rec = run_reference("/tmp", ts, base, idx, total, per * args.warmup, gpu_params=params)
+    imu = None
+    if args.config == 3:
+        from rebvo_b200 import synth
+        seq = synth.Sequence(w=cam["w"], h=cam["h"], seed=seed0, zf=cam["zfx"])
+        imu = synth.imu_samples_walk(seq, total, min(IMU_BASE_N, total))
+    info, rec = run_reference("/tmp", ts, base, idx, total, per * args.warmup, gpu_params=params, imu=imu)
     fps = info["fps"]
     ncpu = os.cpu_count() or 1
     out = {"metric": metric, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -219,6 +238,10 @@ def bench_ours(args):
     total = B * (K + W)
     cam, params, metric, workload, seed0 = stream_setup(args.config)
     ts, base, idx = make_stream(multi.stream_seed(rank) + (seed0 - 7), total, cam=cam)
+    imu = None
+    if args.config == 3:   # IMU samples of the walked camera path; every pipeline of this run gets them
+        seq = synth.Sequence(w=cam["w"], h=cam["h"], seed=multi.stream_seed(rank), zf=cam["zfx"])
+        imu = synth.imu_samples_walk(seq, total, min(IMU_BASE_N, total))
     h, w = cam["h"], cam["w"]
     fbytes = h * w * 3
     # host (pinned) and device copies of the whole stream, batch-contiguous
@@ -235,6 +258,8 @@ def bench_ours(args):
     sampler = ClockSampler(dev)
     # ---------------- value: frames resident in HBM ----------------------------------------------------
     pl = capi.Pipeline(params, max_batch=B, device=dev)
+    if imu is not None:
+        pl.set_imu(imu, capi.default_imu_params(InitBias=1, InitBiasFrameNum=5))
     navs = []
     for s in range(W):
         navs.append(pl.push_dev(devbuf[s * B].data_ptr(), ts[s * B:(s + 1) * B]))
@@ -260,6 +285,8 @@ def bench_ours(args):
     pl.close()
     # ---------------- e2e: host buffers through the C ABI ------------------------------------------------
     pl2 = capi.Pipeline(params, max_batch=B, device=dev)
+    if imu is not None:
+        pl2.set_imu(imu, capi.default_imu_params(InitBias=1, InitBiasFrameNum=5))
     navs2 = []
     for s in range(W):
         navs2.append(pl2.push(host[s * B].data_ptr(), ts[s * B:(s + 1) * B]))
@@ -274,7 +301,7 @@ def bench_ours(args):
     pl2.close()
     # ---------------- where the step goes: in-situ stage profile (eager launches, one stream, CUDA events) ---------
     stage_us = None
-    if rank == 0:
+    if rank == 0 and imu is None:   # (the IMU-mode frame loop is host-driven: no per-stage device profile)
         os.environ["REBVO_B200_STAGE_PROF"] = "1"
         try:
             pl3 = capi.Pipeline(params, max_batch=B, device=dev)
@@ -345,7 +372,7 @@ def bench_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         try:
             n = min(620, total)
-            info, rec = run_reference("/tmp", ts, base, idx, n, 20, gpu_params=params)
+            info, rec = run_reference("/tmp", ts, base, idx, n, 20, gpu_params=params, imu=imu)
             cpu = {"value": info["fps"], "unit": "frames/s", "cores": 3, "kind": "reference", "cpu_model": cpu_model(),
                    "sample": "first %d frames of the bench stream (20 warm-up) through the unmodified 3-thread REBVO "
                              "built from /root/reference sources; %d host cpus visible" % (n, os.cpu_count() or 1),
@@ -539,7 +566,7 @@ def bench_config4(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5], help="BASELINE.json configs index + 1 (2: 752x480 EuRoC-like replay, 4: 1280x960 multi-sequence, 5: 640x480 TUM desk parameters)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json configs index + 1 (2: 752x480 EuRoC-like replay, 3: the same with IMU fusion, 4: 1280x960 multi-sequence, 5: 640x480 TUM desk parameters)")
     ap.add_argument("--seqs", type=int, default=8, help="config 4: independent sequences per GPU")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)

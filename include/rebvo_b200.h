@@ -262,6 +262,22 @@ int rb_pipeline_bench_pass(rb_pipeline *pl, int pass_id, int nimg, int iters, fl
  * number.  k_prof is the depth scale the third thread passes (pbuf.K, rebvo_third_t.cpp:192). */
 int rb_map_pack_net_keylines(rb_map *m, double k_prof, void *dst, int capacity, int *n_out);
 
+/* IMU fusion (BASELINE configs[2], REBVOParameters ImuMode = 2: samples from a dataset file).  After this call every push runs
+ * the IMU branch of REBVO::SecondThread (rebvo_second_t.cpp:182-336: gyro pre-rotation, Minimizer_V, ExtRotVel, BiasCorrect,
+ * scale / gravity / bias filter of scaleestimator.cpp, filtered pose of :521-551) instead of Minimizer_RV.  samples: n rows
+ * {t [s], gyro xyz [rad/s], accel xyz [m/s^2]} as ImuGrabber::LoadDataSet reads them (imugrabber.cpp:80-132, time already scaled).
+ * Field names follow REBVOParameters (include/rebvo/rebvo.h:64-235). */
+typedef struct rb_imu_params {
+    double TimeDesinc;
+    int32_t InitBias, InitBiasFrameNum;
+    double BiasInitGuess[3];
+    double GiroMeasStdDev, GiroBiasStdDev, AcelMeasStdDev;
+    double g_module, g_module_uncer, g_uncert, VBiasStdDev, ScaleStdDevInit;
+    int32_t use_se3, pad;          /* CamImuSE3File given: Rc2i / Tc2i below (ImuGrabber::LoadCamImuSE3), else identity / zero */
+    double Rc2i[9], Tc2i[3];
+} rb_imu_params;
+int rb_pipeline_set_imu(rb_pipeline *pl, const rb_imu_params *ip, const double *samples, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -126,7 +126,9 @@ def build(level_b=True, force=False):
     a_srcs = [os.path.join(REF, "src/mtracklib", f + ".cpp") for f in
               ("sspace", "iigauss", "iimage", "edge_finder", "edge_tracker")]
     a_srcs += [os.path.join(REF, "src/UtilLib/ne10wrapper.cpp"), os.path.join(REF, "src/VideoLib/image_undistort.cpp"),
-               os.path.join(REF, "src/CommLib/net_keypoint.cpp"), os.path.join(HERE, "ref_shim.cpp")]
+               os.path.join(REF, "src/CommLib/net_keypoint.cpp"), os.path.join(REF, "src/mtracklib/scaleestimator.cpp"),
+               os.path.join(REF, "src/UtilLib/imugrabber.cpp"), os.path.join(REF, "src/UtilLib/configurator.cpp"),
+               os.path.join(HERE, "ref_shim.cpp")]
     b_names = ["rebvo/rebvo", "rebvo/rebvo_first_t", "rebvo/rebvo_second_t", "rebvo/rebvo_third_t",
                "mtracklib/sspace", "mtracklib/iigauss", "mtracklib/iimage", "mtracklib/edge_finder",
                "mtracklib/edge_tracker", "mtracklib/global_tracker", "UtilLib/ne10wrapper",

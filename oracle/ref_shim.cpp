@@ -324,3 +324,76 @@ void ref_bias_correct(double *X, double *Wx, double *Gb, double *Wb, const doubl
     M3out(wb, Wb);
 }
 }
+
+// ---- IMU-mode host filter chain (config 3): ScaleEstimator (src/mtracklib/scaleestimator.cpp) and ImuGrabber's dataset
+// integration (src/UtilLib/imugrabber.cpp), for tests/test_cpu_imu_filter.py -------------------------------------------------
+#include "mtracklib/scaleestimator.h"
+#include "UtilLib/imugrabber.h"
+extern "C" {
+void ref_est_acel_lsq4(const double *vel, double *acel, const double *R, double dt) {
+    Vector<3> v = makeVector(vel[0], vel[1], vel[2]), a = makeVector(acel[0], acel[1], acel[2]);
+    ScaleEstimator::EstAcelLsq4(v, a, M3(R), dt);
+    for (int i = 0; i < 3; i++) acel[i] = a[i];
+}
+void ref_mean_acel4(const double *s_acel, double *acel, const double *R) {
+    Vector<3> s = makeVector(s_acel[0], s_acel[1], s_acel[2]), a = Zeros;
+    ScaleEstimator::MeanAcel4(s, a, M3(R));
+    for (int i = 0; i < 3; i++) acel[i] = a[i];
+}
+static Matrix<3, 3> M3c(const double *m) { return M3(m); }
+double ref_est_ka_gmek_bias(const double *s_acel, const double *f_acel, double kP, const double *Rot, double *X, double *P,
+                            const double *Qg, const double *Qrot, const double *Qbias, double QKp, double Rg, const double *Rs,
+                            const double *Rf, double *g_est, double *b_est, const double *Wvw, double *Xvw, double g_gravit) {
+    Vector<3> sa = makeVector(s_acel[0], s_acel[1], s_acel[2]), fa = makeVector(f_acel[0], f_acel[1], f_acel[2]), ge = Zeros, be = Zeros;
+    Vector<7> x;
+    Matrix<7, 7> p;
+    for (int i = 0; i < 7; i++) {
+        x[i] = X[i];
+        for (int j = 0; j < 7; j++) p(i, j) = P[i * 7 + j];
+    }
+    Matrix<6, 6> wvw;
+    Vector<6> xvw;
+    for (int i = 0; i < 6; i++) {
+        xvw[i] = Xvw[i];
+        for (int j = 0; j < 6; j++) wvw(i, j) = Wvw[i * 6 + j];
+    }
+    const double k = ScaleEstimator::estKaGMEKBias(sa, fa, kP, M3c(Rot), x, p, M3c(Qg), M3c(Qrot), M3c(Qbias), QKp, Rg, M3c(Rs),
+                                                   M3c(Rf), ge, be, wvw, xvw, g_gravit);
+    for (int i = 0; i < 7; i++) {
+        X[i] = x[i];
+        for (int j = 0; j < 7; j++) P[i * 7 + j] = p(i, j);
+    }
+    for (int i = 0; i < 3; i++) {
+        g_est[i] = ge[i];
+        b_est[i] = be[i];
+    }
+    for (int i = 0; i < 6; i++) Xvw[i] = xvw[i];
+    return k;
+}
+int ref_imu_integrate(const double *samples, int n, const double *ts, int nf, double *out) {
+    std::vector<ImuData> v(n);
+    for (int i = 0; i < n; i++) {
+        v[i].tstamp = samples[i * 7];
+        v[i].giro = makeVector(samples[i * 7 + 1], samples[i * 7 + 2], samples[i * 7 + 3]);
+        v[i].acel = makeVector(samples[i * 7 + 4], samples[i * 7 + 5], samples[i * 7 + 6]);
+        v[i].comp = Zeros;
+    }
+    ImuGrabber g(v);
+    double t0 = 0;
+    for (int f = 0; f < nf; f++) {
+        IntegratedImuData d = g.GrabAndIntegrate(t0, ts[f]);
+        double *o = out + f * 20;
+        o[0] = d.n;
+        o[1] = d.dt;
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) o[2 + i * 3 + j] = d.Rot(i, j);
+        for (int k = 0; k < 3; k++) {
+            o[11 + k] = d.giro[k];
+            o[14 + k] = d.acel[k];
+            o[17 + k] = d.cacel[k];
+        }
+        t0 = ts[f];
+    }
+    return 0;
+}
+}

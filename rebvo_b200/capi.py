@@ -37,6 +37,25 @@ class Params(C.Structure):
                 ("DoReScaling", C.c_double), ("config_fps", C.c_double), ("kl_capacity", C.c_int32)]
 
 
+class ImuParams(C.Structure):
+    """rb_imu_params (include/rebvo_b200.h); defaults = the IMU block of app/rebvorun/GlobalConfig_EuRoC_2.txt"""
+    _fields_ = [("TimeDesinc", C.c_double), ("InitBias", C.c_int32), ("InitBiasFrameNum", C.c_int32),
+                ("BiasInitGuess", C.c_double * 3), ("GiroMeasStdDev", C.c_double), ("GiroBiasStdDev", C.c_double),
+                ("AcelMeasStdDev", C.c_double), ("g_module", C.c_double), ("g_module_uncer", C.c_double),
+                ("g_uncert", C.c_double), ("VBiasStdDev", C.c_double), ("ScaleStdDevInit", C.c_double),
+                ("use_se3", C.c_int32), ("pad", C.c_int32), ("Rc2i", C.c_double * 9), ("Tc2i", C.c_double * 3)]
+
+
+def default_imu_params(**over):
+    p = ImuParams()
+    p.TimeDesinc, p.InitBias, p.InitBiasFrameNum = 0.0, 0, 10
+    p.GiroMeasStdDev, p.GiroBiasStdDev, p.AcelMeasStdDev = 1.6968e-4, 1.9393e-5, 2e-3
+    p.g_module, p.g_module_uncer, p.g_uncert, p.VBiasStdDev, p.ScaleStdDevInit = 9.8, 100e3, 2e-3, 1e-7, 1.2e-3
+    for k, v in over.items():
+        setattr(p, k, v)
+    return p
+
+
 NAV = np.dtype([("t", "f8"), ("dt", "f8"), ("Rot", "f8", 9), ("RotLie", "f8", 3), ("Vel", "f8", 3),
                 ("Pose", "f8", 9), ("PoseLie", "f8", 3), ("Pos", "f8", 3), ("V", "f8", 3), ("W", "f8", 3),
                 ("K", "f8"), ("Kp", "f8"), ("RKp", "f8"), ("s_rho_p", "f8"), ("score", "f8"), ("kn", "i4"),
@@ -66,6 +85,7 @@ SYMBOLS = ["rb_ctx_create", "rb_ctx_destroy", "rb_last_error", "rb_ctx_sync", "r
            "rb_pipeline_last_error", "rb_pipeline_push", "rb_pipeline_push_dev", "rb_pipeline_reset",
            "rb_pipeline_map", "rb_pipeline_launch_count", "rb_pipeline_stage_ms", "rb_pipeline_stream",
            "rb_pipeline_event_record", "rb_pipeline_event_elapsed", "rb_pipeline_event_elapsed_between", "rb_pipeline_bench_pass",
+           "rb_pipeline_set_imu",
            "rb_pipeline_stage_profile",
            "rb_undistort_create", "rb_undistort_destroy", "rb_undistort_rgb", "rb_undistort_rgb_dev",
            "rb_try_vel", "rb_minimizer_v", "rb_ext_rot_vel", "rb_bias_correct", "rb_map_pack_net_keylines"]
@@ -394,6 +414,12 @@ class Pipeline:
             ptr = C.c_void_p(int(rgb))
         self.check(self.L.rb_pipeline_push(self.h_, ptr, _p(ts), n, _p(nav)))
         return nav
+
+    def set_imu(self, samples, imu_params=None):
+        """IMU mode (BASELINE configs[2]): samples = float64 [n, 7] rows {t, gyro xyz, accel xyz}."""
+        samples = np.ascontiguousarray(samples, np.float64)
+        ip = imu_params if imu_params is not None else default_imu_params()
+        self.check(self.L.rb_pipeline_set_imu(self.h_, C.byref(ip), _p(samples), len(samples)))
 
     def push_dev(self, dev_ptr, ts):
         ts = np.ascontiguousarray(ts, np.float64)

@@ -40,8 +40,10 @@ extern "C" int rb_debug_fetch_trace(unsigned long long *out, unsigned int *n) {
 #define RB_TRACE(stream, tag) do { } while (0)
 #endif
 
+struct ImuFlow;
 struct rb_pipeline {
     rb_ctx *c;
+    ImuFlow *imu;         // IMU mode (rb_pipeline_set_imu), nullptr otherwise
     rb_params p;
     int max_batch;
     DogWS ws;
@@ -86,6 +88,8 @@ struct rb_pipeline {
     long long pframes;
 };
 
+#include "imu_flow.cuh"
+
 enum { ST_H2D = 0, ST_GRAY, ST_DOG, ST_DETECT, ST_REEST, ST_FIELD, ST_MINIM, ST_FWD_ROT, ST_DMATCH, ST_REG_EKF, ST_RESCALE,
        ST_FINISH, ST_NAV };
 static inline void prof_mark(rb_pipeline *pl, int tag) {
@@ -95,6 +99,7 @@ static inline void prof_mark(rb_pipeline *pl, int tag) {
 }
 
 int rb_dog_single_pass(rb_ctx *c, DogWS *ws, int pass_id, int nimg, double *bytes);
+int rb_read_map_state(rb_map *m, MapState *host);
 
 static void set_eye(double *M, double v) {
     for (int i = 0; i < 9; i++) M[i] = 0;
@@ -149,6 +154,7 @@ static int pl_reset_state(rb_pipeline *pl) {
     RB_CUDA(cudaMemcpy(pl->chain, &ch, sizeof(ch), cudaMemcpyHostToDevice));
     for (int k = 0; k < RB_NMAPS; k++)
         if (pl->maps[k]) RB_CUDA(cudaMemset(&pl->maps[k]->ts_host.ctl->abort, 0, sizeof(int)));
+    if (pl->imu) imu_flow_reset(*pl->imu);
     pl->n_pushed = 0;
     pl->t_prev = 0;
     return RB_OK;
@@ -241,9 +247,29 @@ extern "C" int rb_pipeline_create(rb_pipeline **out, int device, const rb_params
     return RB_OK;
 }
 
+extern "C" int rb_pipeline_set_imu(rb_pipeline *pl, const rb_imu_params *ip, const double *samples, int n) {
+    if (!pl || !ip || !samples || n < 2) return RB_ERR_ARG;
+    if (!pl->imu) pl->imu = new (std::nothrow) ImuFlow();
+    if (!pl->imu) return RB_ERR_ARG;
+    ImuFlow &f = *pl->imu;
+    f.ip = *ip;
+    f.samples.resize(n);
+    for (int i = 0; i < n; i++) {
+        f.samples[i].t = samples[i * 7];
+        for (int k = 0; k < 3; k++) {
+            f.samples[i].giro[k] = samples[i * 7 + 1 + k];
+            f.samples[i].acel[k] = samples[i * 7 + 4 + k];
+        }
+    }
+    f.enabled = true;
+    imu_flow_reset(f);
+    return RB_OK;
+}
+
 extern "C" void rb_pipeline_destroy(rb_pipeline *pl) {
     if (!pl) return;
     rb_ctx *c = pl->c;
+    delete pl->imu;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (pl->det_stream) cudaStreamSynchronize(pl->det_stream);
@@ -434,6 +460,12 @@ static int push_impl(rb_pipeline *pl, const uint8_t *rgb, bool on_device, const 
     if (n < 1 || n > pl->max_batch || !rgb || !ts) return RB_ERR_ARG;
     RB_CUDA(cudaSetDevice(c->device));
     int r;
+    if (pl->imu) {   // IMU mode: host-driven frame loop (imu_flow.cuh)
+        if ((r = imu_push(pl, *pl->imu, rgb, on_device, ts, n, pl->nav_pin))) return r;
+        RB_CUDA(cudaStreamSynchronize(c->stream));
+        if (nav_out) memcpy(nav_out, pl->nav_pin, sizeof(rb_nav) * n);
+        return RB_OK;
+    }
     const long long first = pl->n_pushed;
     // per-frame scalars -> device (SecondThread :146-149 for dt; FrameCount of the reference's 8-slot ring:
     // frame fr is served by slot (fr+1)%8, whose global_tracker has run (fr-1)/8 minimisations before)

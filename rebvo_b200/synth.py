@@ -126,3 +126,24 @@ def write_imu_csv(path, samples):
         f.write("#timestamp,w_x,w_y,w_z,a_x,a_y,a_z\n")
         for r in samples:
             f.write(",".join("%.17g" % v for v in r) + "\n")
+
+
+def imu_samples_walk(seq, total, base_n, rate=200.0, gyro_bias=(0.02, -0.015, 0.01), gyro_noise=1.7e-4, acc_noise=2e-3, seed=0,
+                     g=9.8):
+    """IMU stream for a sequence whose `total` frames walk `base_n` rendered frames back and forth (bench.py): the camera
+    position at time t is cam_pos at the triangle-wave frame index."""
+    rng = np.random.default_rng(seed + 78)
+    period = max(1, 2 * (base_n - 1))
+    t = np.arange(-0.25, total / seq.fps + 0.25, 1.0 / rate)
+    h = 1e-3
+
+    def pos(tt):
+        x = (tt * seq.fps) % period
+        x = np.where(x < base_n - 1, x, period - x)
+        return np.stack([seq.cam_pos(v) for v in x])
+
+    acc = (pos(t + h) - 2 * pos(t) + pos(t - h)) / (h * h)
+    acc = np.clip(acc, -20, 20) - np.array([0.0, g, 0.0])
+    acc = acc + rng.normal(0, acc_noise, acc.shape)
+    gyro = np.array(gyro_bias)[None, :] + rng.normal(0, gyro_noise, (len(t), 3))
+    return np.concatenate([t[:, None], gyro, acc], axis=1)
