@@ -128,7 +128,8 @@ class ClockSampler:
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
 # (profiles/r1_summary.md section 3, 64-frame batch = the default bench batch)
-TRAFFIC = {"k_rowscan_ring<avg>": 3.19e8}   # 307-331 MB over the two launches of a 64-frame batch
+TRAFFIC = {"k_rowscan_ring<avg>": 3.19e8,   # 307-331 MB over the two launches of a 64-frame batch
+           "k_minimizer_cluster": 2.43e6}   # profiles/r2_summary.md section 3 (operands / residuals in shared memory, gathers in L1)
 
 
 def peak_gbs():

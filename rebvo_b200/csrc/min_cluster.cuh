@@ -788,12 +788,9 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
                         L.last_score = t;
                     } else if (PJ && lane < 27) {
                         if (lane < 21) {
-                            int a = 0, b = lane;
-                            while (b >= 6 - a) {
-                                b -= 6 - a;
-                                a++;
-                            }
-                            b += a;
+                            // upper-triangle index -> (row, column), branch-free
+                            const int a = lane < 6 ? 0 : lane < 11 ? 1 : lane < 15 ? 2 : lane < 18 ? 3 : lane < 20 ? 4 : 5;
+                            const int b = lane - (a == 0 ? 0 : a == 1 ? 6 : a == 2 ? 11 : a == 3 ? 15 : a == 4 ? 18 : 20) + a;
                             const bool neg = (a < 2 && (b == 2 || b == 3)) || ((a == 2 || a == 3) && b >= 4);
                             t = neg ? -t : t;
                             L.JtJn[a * 6 + b] = t;

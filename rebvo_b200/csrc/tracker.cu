@@ -388,7 +388,7 @@ __device__ void lm_finalize(LMState &s, MapState *fst) {   // :793-816; RVel / R
     if (fst) fst->frame_count = fst->frame_count + 1;   // FrameCount++ (one CTA of the cluster kernel does it)
 }
 
-__device__ __noinline__ void lm_step(LMState &s, int step, MapState *fst) {
+__device__ __forceinline__ void lm_step(LMState &s, int step, MapState *fst) {
     switch (step) {
         case STEP_INIT_FIRST_ZERO:
             lm_take_first(s);   // v = 2 from the declaration (:620)
