@@ -65,8 +65,10 @@ struct DogWS {           // batched scale-space workspace, B images of N floats 
     float *img0;         // B * N    blur 0
     float *dog;          // B * N    blur1 - blur0
     float *aux;          // 3 * N    on-demand planes (Img(1), dx, dy) for the test/debug accessor
-    void *tmaps;         // CUtensorMap[3] (host): I, img0, dog -- TMA-staged last box + DoG (dog.cu)
+    void *tmaps;         // CUtensorMap[] (host, dog.cu TM_*): TMA-staged row passes, last box + DoG
     bool tma_ok;
+    int tma_row_mask;
+    bool tma_row_ok;     // the row passes run on TMA tiles (k_rowscan_tma_*)
 };
 
 struct rb_ctx {

@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(BT_THREADS) k_blur_dog_tma(const __grid_consta
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                         const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static bool make_tmap3(CUtensorMap *tm, float *base, int w, int h, int nimg, int bw, int bh) {
+static bool make_tmap3(CUtensorMap *tm, float *base, int w, int h, int nimg, int bw, int bh, bool swizzle128 = false) {
     static PFN_tmapEncodeTiled enc = nullptr;
     if (!enc) {
         void *fn = nullptr;
@@ -339,26 +339,44 @@ static bool make_tmap3(CUtensorMap *tm, float *base, int w, int h, int nimg, int
     const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
     const cuuint32_t es[3] = {1, 1, 1};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+// tensor map slots of a workspace
+enum { TM_I_BLUR = 0, TM_IMG0, TM_DOG, TM_GRAY, TM_S, TM_I0_F0, TM_I0_F1, TM_I_F0, TM_I_F1, TM_COUNT };
 int rb_dog_make_tmaps(rb_ctx *c, DogWS *ws) {
     ws->tma_ok = false;
+    ws->tma_row_ok = false;
     const char *e = getenv("REBVO_B200_BLUR_TMA");
-    if (e && atoi(e) == 0) return RB_OK;
+    const char *er = getenv("REBVO_B200_ROW_TMA");
+    const bool want_blur = !(e && atoi(e) == 0), want_row = !(er && atoi(er) == 0);
+    if (!want_blur && !want_row) return RB_OK;
     if ((c->w * 4) % 16) return RB_OK;
-    CUtensorMap *t = new (std::nothrow) CUtensorMap[3];
+    CUtensorMap *t = new (std::nothrow) CUtensorMap[TM_COUNT];
     if (!t) return RB_OK;
-    bool ok = make_tmap3(&t[0], ws->I, c->w, c->h, 2 * ws->B, BT_BW, BT_BH) &&
-              make_tmap3(&t[1], ws->img0, c->w, c->h, ws->B, BT_W, BT_H) &&
-              make_tmap3(&t[2], ws->dog, c->w, c->h, ws->B, BT_W, BT_H);
-    ok = ok && cudaFuncSetAttribute(k_blur_dog_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlurTmaSmem) + 128) == cudaSuccess;
-    if (!ok) {
-        cudaGetLastError();
-        delete[] t;
-        return RB_OK;
-    }
     ws->tmaps = t;
-    ws->tma_ok = true;
+    if (want_blur) {
+        bool ok = make_tmap3(&t[TM_I_BLUR], ws->I, c->w, c->h, 2 * ws->B, BT_BW, BT_BH) &&
+                  make_tmap3(&t[TM_IMG0], ws->img0, c->w, c->h, ws->B, BT_W, BT_H) &&
+                  make_tmap3(&t[TM_DOG], ws->dog, c->w, c->h, ws->B, BT_W, BT_H);
+        ok = ok && cudaFuncSetAttribute(k_blur_dog_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlurTmaSmem) + 128) == cudaSuccess;
+        if (!ok) cudaGetLastError();
+        ws->tma_ok = ok;
+    }
+    if (want_row) {
+        // row pass: 32 x 32 tiles, 128-byte swizzle on the tiles the sequential scan walks row-wise (gray in, S out); the
+        // box-average inputs are (32 + d) x 32 windows read column-wise (no swizzle)
+        const int (*d)[3] = c->plan.d;
+        bool ok = make_tmap3(&t[TM_GRAY], ws->gray, c->w, c->h, ws->B, 32, 32, true) &&
+                  make_tmap3(&t[TM_S], ws->S, c->w, c->h, 2 * ws->B, 32, 32, true) &&
+                  make_tmap3(&t[TM_I0_F0], ws->I0, c->w, c->h, ws->B, 32, 32 + d[0][0]) &&
+                  make_tmap3(&t[TM_I0_F1], ws->I0, c->w, c->h, ws->B, 32, 32 + d[1][0]) &&
+                  make_tmap3(&t[TM_I_F0], ws->I, c->w, c->h, 2 * ws->B, 32, 32 + d[0][1]) &&
+                  make_tmap3(&t[TM_I_F1], ws->I, c->w, c->h, 2 * ws->B, 32, 32 + d[1][1]);
+        if (!ok) cudaGetLastError();
+        ws->tma_row_ok = ok;
+        ws->tma_row_mask = er ? atoi(er) : 1;   // 1 = both row passes, 2 = plain only, 3 = box average only (diagnosis)
+    }
     return RB_OK;
 }
 
@@ -558,6 +576,235 @@ __global__ void __launch_bounds__(32 * RING_WARPS) k_rowscan_ring(const float *_
     cp_async_wait<0>();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Row pass on TMA tiles.  One warp = one 32-row band of one image (the sequential float add chain of iimage.cpp:56-60 runs
+// along x, one row per lane), one warp per CTA so that the CTAs spread evenly over the SMs.  The ncu profile of the cp.async
+// ring version showed a warp-latency-bound kernel (775 instructions per 32 x 32 chunk, 5 cycles per instruction, 10 % warps
+// active), not a memory-bound one; here a chunk costs ~80 (plain) / ~370 (box average) instructions:
+//   * one lane issues one cp.async.bulk.tensor load per chunk on an mbarrier ring, RT_NS - 1 chunks ahead;
+//   * the tile the scan walks row-wise lives in shared memory in the 128-byte swizzle of the tensor map, so that a lane reads
+//     and writes its row as eight conflict-free 16-byte accesses (unit k of row r sits at unit k ^ (r & 7));
+//   * the scanned tile leaves with one cp.async.bulk.tensor store; bounds are the tensor map's business (zero fill on the
+//     way in, clipping on the way out).
+// Same arithmetic and add order as k_rowscan (bit-identical output).
+#define RT_NS 4
+__device__ __forceinline__ unsigned int rt_s32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rt_load3(unsigned int dst, const CUtensorMap *tm, int x, int y, int z, unsigned int bar,
+                                         unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void rt_store3(const CUtensorMap *tm, int x, int y, int z, unsigned int src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tm), "r"(x), "r"(y),
+                 "r"(z), "r"(src)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ bool rt_wait(unsigned int bar, unsigned int parity, int *fail) {
+    unsigned int ok = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return true;
+        if (clock64() - t0 > (1ll << 28)) {   // a broken copy flags an error instead of hanging the device
+            *fail = 1;
+            return false;
+        }
+    }
+}
+// in-place scan of a swizzled 32 x 32 tile (shared-space address), lane = row
+__device__ __forceinline__ float rt_scan_tile(unsigned int tile_s, int lane, float carry) {
+    const unsigned int rowp = tile_s + (unsigned int)((lane * 128) ^ ((lane & 7) << 4));
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const unsigned int a = rowp ^ (unsigned int)(k << 4);
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+        carry = carry + v.x;   // I(x,y) = I(x-1,y) + in(x,y), iimage.cpp:56-60
+        v.x = carry;
+        carry = carry + v.y;
+        v.y = carry;
+        carry = carry + v.z;
+        v.z = carry;
+        carry = carry + v.w;
+        v.w = carry;
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
+    return carry;
+}
+
+__global__ void __launch_bounds__(32) k_rowscan_tma_plain(const __grid_constant__ CUtensorMap tm_in,
+                                                          const __grid_constant__ CUtensorMap tm_out, int w, int h,
+                                                          int zin0, int *fail) {
+    extern __shared__ unsigned char rt_raw[];
+    unsigned char *base = rt_raw + ((1024u - (rt_s32(rt_raw) & 1023u)) & 1023u);   // 1024-byte aligned (swizzle atom)
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(base + RT_NS * 4096);
+    const int lane = threadIdx.x;
+    const int bands = (h + 31) >> 5;
+    const int img = blockIdx.x / bands, band = blockIdx.x - img * bands;
+    const int y0 = band * 32;
+    const int nchunk = (w + 31) >> 5;
+    const unsigned int ring_s = rt_s32(base), full_s = rt_s32(full);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < RT_NS; k++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_s + 8 * k) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int ci = 0; ci < RT_NS - 1; ci++)
+            if (ci < nchunk) rt_load3(ring_s + ci * 4096, &tm_in, 32 * ci, y0, zin0 + img, full_s + 8 * ci, 4096);
+    }
+    __syncwarp();
+    float carry = 0.f;
+    for (int t = 0; t < nchunk; t++) {
+        const int slot = t % RT_NS;
+        if (!rt_wait(full_s + 8 * slot, (unsigned int)(t / RT_NS) & 1u, fail)) break;
+        carry = rt_scan_tile(ring_s + slot * 4096, lane, carry);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA unit
+        __syncwarp();
+        if (lane == 0) {
+            rt_store3(&tm_out, 32 * t, y0, img, ring_s + slot * 4096);
+            // the slot of chunk t-1 (its store has been read out) takes the chunk RT_NS-1 ahead
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            const int cn = t + RT_NS - 1;
+            if (cn < nchunk)
+                rt_load3(ring_s + (cn % RT_NS) * 4096, &tm_in, 32 * cn, y0, zin0 + img, full_s + 8 * (cn % RT_NS), 4096);
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// Box average + row scan: chunk c of the input holds the columns [32c - 16, 32c + 16), so that the taps of the output tile t
+// (columns [32t, 32t + 32), |offset| <= d2 + 1 <= 16) come from the chunks t and t+1 only: two chunks live, two in flight.
+// Windows are (32 + d) x 32, read column-wise (lane = column, dense rows, no swizzle); the output tile is written column-wise
+// into the swizzled layout and scanned in place.  (Output tiles shifted by 16 columns instead fault in the TMA store.)
+__global__ void __launch_bounds__(32) k_rowscan_tma_avg(const __grid_constant__ CUtensorMap tm_in0,
+                                                        const __grid_constant__ CUtensorMap tm_in1,
+                                                        const __grid_constant__ CUtensorMap tm_out, int w, int h,
+                                                        int in_mod, int nper, int d_f0, int d_f1,
+                                                        const float *__restrict__ tab_f0, const float *__restrict__ tab_f1,
+                                                        int rmax, int *fail) {
+    extern __shared__ unsigned char rt_raw[];
+    unsigned char *base = rt_raw + ((1024u - (rt_s32(rt_raw) & 1023u)) & 1023u);   // 1024-byte aligned (swizzle atom)
+    unsigned char *otile = base;                                        // [2][4096]
+    float *ring = reinterpret_cast<float *>(base + 2 * 4096);           // [RT_NS][rmax][32]
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(base + 2 * 4096 + (size_t)RT_NS * rmax * 128);
+    float *tab = reinterpret_cast<float *>(full + RT_NS);
+    const int lane = threadIdx.x;
+    const int bands = (h + 31) >> 5;
+    const int img = blockIdx.x / bands, band = blockIdx.x - img * bands;
+    const bool f1 = (img / nper) != 0;
+    const int d = f1 ? d_f1 : d_f0, d2 = d / 2;
+    const int y0 = band * 32, yb0 = y0 - d2 - 1;    // image row of window row 0
+    const int zin = img % in_mod;
+    const CUtensorMap *tm = f1 ? &tm_in1 : &tm_in0;
+    const unsigned int wbytes = (unsigned int)(32 + d) * 128u;
+    const int ntile = (w + 31) >> 5, nchunk = (w + 16 + 31) >> 5;
+    const unsigned int ring_s = rt_s32(ring), full_s = rt_s32(full), ot_s = rt_s32(otile);
+    const unsigned int slot_bytes = (unsigned int)rmax * 128u;
+    {
+        const float *__restrict__ tg = f1 ? tab_f1 : tab_f0;
+        tab[lane] = tg[lane];
+        tab[lane + 32] = tg[lane + 32];
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < RT_NS; k++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_s + 8 * k) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int ci = 0; ci < RT_NS - 1; ci++)
+            if (ci < nchunk) rt_load3(ring_s + ci * slot_bytes, tm, 32 * ci - 16, yb0, zin, full_s + 8 * ci, wbytes);
+    }
+    __syncwarp();
+    const bool band_interior = (y0 >= d2 + 1) && (y0 + 31 < h - d2);
+    // column-wise store offsets into the swizzled output tile: element (r, lane) at r * 128 + so[r & 7]
+    unsigned int so[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) so[j] = (unsigned int)((((lane >> 2) ^ j) << 4) | ((lane & 3) << 2));
+    float carry = 0.f;
+    bool ok = rt_wait(full_s, 0u, fail);   // chunk 0
+    for (int t = 0; ok && t < ntile; t++) {
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store of tile t-2 has left its buffer
+            const int cn = t + RT_NS - 1;                                     // the slot of chunk t-1 is free since tile t-1
+            if (cn < nchunk)
+                rt_load3(ring_s + (cn % RT_NS) * slot_bytes, tm, 32 * cn - 16, yb0, zin, full_s + 8 * (cn % RT_NS), wbytes);
+        }
+        if (t + 1 < nchunk && !rt_wait(full_s + 8 * ((t + 1) % RT_NS), (unsigned int)((t + 1) / RT_NS) & 1u, fail)) break;
+        __syncwarp();
+        unsigned char *ot = otile + (t & 1) * 4096;
+        const int x = t * 32 + lane;
+        if (band_interior && t * 32 >= d2 + 1 && t * 32 + 31 < w - d2) {
+            // centre region of iimage::average for the whole tile: constant tap offsets, no selects
+            const int xr = x + d2 + 16, xl = x - d2 - 1 + 16;   // (+16: chunk c starts at column 32c - 16)
+            const float *colr = ring + (size_t)((xr >> 5) % RT_NS) * rmax * 32 + (xr & 31);
+            const float *coll = ring + (size_t)((xl >> 5) % RT_NS) * rmax * 32 + (xl & 31);
+            const float *colr_b = colr + d * 32, *coll_b = coll + d * 32;   // bottom taps: window row r + d
+            const float a = tab[d2 * BOX_TAB_W + d2];
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                float v = colr_b[r * 32] - coll_b[r * 32];   // A - B
+                v = v - colr[r * 32];                        //   - C
+                v = v + coll[r * 32];                        //   + D
+                *reinterpret_cast<float *>(ot + r * 128 + so[r & 7]) = v * a;
+            }
+        } else {
+            const int xc = x < w ? x : w - 1;
+            const bool left = xc < d2 + 1, right = xc >= w - d2;
+            const int xr = (right ? w - 1 : xc + d2) + 16, xl = (left ? 0 : xc - d2 - 1) + 16;
+            const int cx = left ? xc + d2 + 1 : (right ? w - xc + d2 : d);
+            const float *colr = ring + (size_t)((xr >> 5) % RT_NS) * rmax * 32 + (xr & 31);
+            const float *coll = ring + (size_t)((xl >> 5) % RT_NS) * rmax * 32 + (xl & 31);
+            const float *tcol = tab + (cx - d2 - 1);
+#pragma unroll 8
+            for (int r = 0; r < 32; r++) {
+                const int y = y0 + r;
+                const int yc = y < h ? y : h - 1;
+                const bool top = yc < d2 + 1, bottom = yc >= h - d2;
+                const int jb = (bottom ? h - 1 : yc + d2) - yb0, jt = top ? 0 : yc - d2 - 1 - yb0;
+                const float A = colr[jb * 32], B = coll[jb * 32], C = colr[jt * 32], Dd = coll[jt * 32];
+                const float t1 = bottom ? C : B, t2 = bottom ? B : C;   // bottom band: A-C-B+D, elsewhere A-B-C+D
+                const bool h1 = bottom ? !top : !left, h2 = bottom ? !left : !top;
+                float v = A;
+                v = h1 ? v - t1 : v;
+                v = h2 ? v - t2 : v;
+                v = (!top && !left) ? v + Dd : v;
+                const int cy = top ? yc + d2 + 1 : (bottom ? h - yc + d2 : d);
+                v = v * tcol[(cy - d2 - 1) * BOX_TAB_W];
+                *reinterpret_cast<float *>(ot + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2))) =
+                    (y < h && x < w) ? v : 0.f;
+            }
+        }
+        __syncwarp();
+        carry = rt_scan_tile(ot_s + (t & 1) * 4096, lane, carry);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) rt_store3(&tm_out, 32 * t, y0, img, ot_s + (t & 1) * 4096);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+static int rowscan_tma(rb_ctx *c, DogWS *ws, int stage, const float *in, int nimg, int in_mod, int nper) {
+    const CUtensorMap *t = (const CUtensorMap *)ws->tmaps;
+    const int bands = (c->h + 31) / 32;
+    int *fail = (int *)((char *)c->dev_small + RB_DS_TMA_FAIL);
+    if (stage < 0) {
+        const int zin0 = (int)((in - ws->gray) / (ptrdiff_t)c->N);
+        k_rowscan_tma_plain<<<nimg * bands, 32, RT_NS * 4096 + 64 + 1024, c->stream>>>(t[TM_GRAY], t[TM_S], c->w, c->h, zin0, fail);
+    } else {
+        const int d0 = c->plan.d[0][stage], d1 = c->plan.d[1][stage];
+        const int rmax = 32 + (d0 > d1 ? d0 : d1);
+        const size_t smem = 2 * 4096 + (size_t)RT_NS * rmax * 128 + 64 + BOX_TAB_N * 4 + 1024;
+        k_rowscan_tma_avg<<<nimg * bands, 32, smem, c->stream>>>(
+            t[stage == 0 ? TM_I0_F0 : TM_I_F0], t[stage == 0 ? TM_I0_F1 : TM_I_F1], t[TM_S], c->w, c->h, in_mod, nper, d0, d1,
+            c->boxtab + (0 * 3 + stage) * BOX_TAB_N, c->boxtab + (1 * 3 + stage) * BOX_TAB_N, rmax, fail);
+    }
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
 // per-device opt-ins of this file's kernels (function attributes are per device: called from rb_ctx_create after
 // cudaSetDevice, so that contexts on several GPUs of one process all get them)
 int rb_dog_device_setup(rb_ctx *c) {
@@ -585,7 +832,10 @@ static int rowscan_ring(rb_ctx *c, int stage, const float *in, float *out, int n
 }
 
 // stage < 0: plain row scan of the input; stage 0..1: row scan of box `stage` of both filters
-static int rowscan(rb_ctx *c, int stage, const float *in, float *out, int nimg, int in_mod, int nper) {
+static int rowscan(rb_ctx *c, DogWS *ws, int stage, const float *in, float *out, int nimg, int in_mod, int nper) {
+    if (ws->tma_row_ok && out == ws->S && stage <= 1 && (ws->tma_row_mask == 1 || ws->tma_row_mask == (stage < 0 ? 2 : 3)) &&
+        (stage < 0 ? (in >= ws->gray && in < ws->gray + (size_t)ws->B * c->N) : in == (stage == 0 ? ws->I0 : ws->I)))
+        return rowscan_tma(c, ws, stage, in, nimg, in_mod, nper);
     if (c->rowscan_mode == 2) return rowscan_ring(c, stage, in, out, nimg, in_mod, nper);
     const int bands = (c->h + 31) / 32;
     const int warps = nimg * bands;
@@ -605,7 +855,7 @@ static int blur_dog(rb_ctx *c, DogWS *ws, int nimg, float *img1_opt, int out_slo
         const CUtensorMap *t = (const CUtensorMap *)ws->tmaps;
         dim3 tg(rb_div_up(c->w, BT_W), rb_div_up(c->h, BT_H), nimg);
         k_blur_dog_tma<<<tg, BT_THREADS, sizeof(BlurTmaSmem) + 128, c->stream>>>(
-            t[0], t[1], t[2], c->w, c->h, nimg, out_slot, c->plan.d[0][2], c->plan.d[1][2],
+            t[TM_I_BLUR], t[TM_IMG0], t[TM_DOG], c->w, c->h, nimg, out_slot, c->plan.d[0][2], c->plan.d[1][2],
             c->boxtab + (0 * 3 + 2) * BOX_TAB_N, c->boxtab + (1 * 3 + 2) * BOX_TAB_N, (int *)((char *)c->dev_small + RB_DS_TMA_FAIL));
         RB_LAUNCH_CHECK();
         return RB_OK;
@@ -664,13 +914,13 @@ int rb_dog_build_batch(rb_ctx *c, DogWS *ws, int nimg) {
     for (int s = 0; s < nimg; s += sub) {
         const int m = nimg - s < sub ? nimg - s : sub;
         // iimage::load(in): identical for both filters -> computed once
-        if ((r = rowscan(c, -1, ws->gray + s * N, ws->S, m, m, m))) return r;
+        if ((r = rowscan(c, ws, -1, ws->gray + s * N, ws->S, m, m, m))) return r;
         if ((r = colscan(c, ws->S, ws->I0, m))) return r;
         // box 0 of both filters reads the shared integral; image index = filter * m + b
-        if ((r = rowscan(c, 0, ws->I0, ws->S, 2 * m, m, m))) return r;
+        if ((r = rowscan(c, ws, 0, ws->I0, ws->S, 2 * m, m, m))) return r;
         if ((r = colscan(c, ws->S, ws->I, 2 * m))) return r;
         // box 1
-        if ((r = rowscan(c, 1, ws->I, ws->S, 2 * m, 2 * m, m))) return r;
+        if ((r = rowscan(c, ws, 1, ws->I, ws->S, 2 * m, 2 * m, m))) return r;
         if ((r = colscan(c, ws->S, ws->I, 2 * m))) return r;
         // box 2 + DoG.  Filter f of image b lives at I[(f*m + b)*N]
         if ((r = blur_dog(c, ws, m, nullptr, s))) return r;
@@ -697,10 +947,10 @@ int rb_dog_single_pass(rb_ctx *c, DogWS *ws, int pass_id, int nimg, double *byte
     switch (pass_id) {
         case 0:
             *bytes = 8.0 * N * nimg;   // read gray 4N, write S 4N
-            return rowscan(c, -1, ws->gray, ws->S, nimg, nimg, nimg);
+            return rowscan(c, ws, -1, ws->gray, ws->S, nimg, nimg, nimg);
         case 1:
             *bytes = 8.0 * N * 2 * nimg;   // read I 4N (each tap row is re-used from L1/L2), write S 4N
-            return rowscan(c, 1, ws->I, ws->S, 2 * nimg, 2 * nimg, nimg);
+            return rowscan(c, ws, 1, ws->I, ws->S, 2 * nimg, 2 * nimg, nimg);
         case 2:
             *bytes = 8.0 * N * 2 * nimg;   // read S 4N, write I 4N
             return colscan(c, ws->S, ws->I, 2 * nimg);
