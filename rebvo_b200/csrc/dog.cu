@@ -587,7 +587,6 @@ __global__ void __launch_bounds__(32 * RING_WARPS) k_rowscan_ring(const float *_
 //   * the scanned tile leaves with one cp.async.bulk.tensor store; bounds are the tensor map's business (zero fill on the
 //     way in, clipping on the way out).
 // Same arithmetic and add order as k_rowscan (bit-identical output).
-#define RT_NS 4
 __device__ __forceinline__ unsigned int rt_s32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void rt_load3(unsigned int dst, const CUtensorMap *tm, int x, int y, int z, unsigned int bar,
                                          unsigned int bytes) {
@@ -636,6 +635,7 @@ __device__ __forceinline__ float rt_scan_tile(unsigned int tile_s, int lane, flo
     return carry;
 }
 
+template <int RT_NS>
 __global__ void __launch_bounds__(32) k_rowscan_tma_plain(const __grid_constant__ CUtensorMap tm_in,
                                                           const __grid_constant__ CUtensorMap tm_out, int w, int h,
                                                           int zin0, int *fail) {
@@ -680,6 +680,7 @@ __global__ void __launch_bounds__(32) k_rowscan_tma_plain(const __grid_constant_
 // (columns [32t, 32t + 32), |offset| <= d2 + 1 <= 16) come from the chunks t and t+1 only: two chunks live, two in flight.
 // Windows are (32 + d) x 32, read column-wise (lane = column, dense rows, no swizzle); the output tile is written column-wise
 // into the swizzled layout and scanned in place.  (Output tiles shifted by 16 columns instead fault in the TMA store.)
+template <int RT_NS>
 __global__ void __launch_bounds__(32) k_rowscan_tma_avg(const __grid_constant__ CUtensorMap tm_in0,
                                                         const __grid_constant__ CUtensorMap tm_in1,
                                                         const __grid_constant__ CUtensorMap tm_out, int w, int h,
@@ -751,30 +752,31 @@ __global__ void __launch_bounds__(32) k_rowscan_tma_avg(const __grid_constant__ 
                 *reinterpret_cast<float *>(ot + r * 128 + so[r & 7]) = v * a;
             }
         } else {
-            const int xc = x < w ? x : w - 1;
-            const bool left = xc < d2 + 1, right = xc >= w - d2;
-            const int xr = (right ? w - 1 : xc + d2) + 16, xl = (left ? 0 : xc - d2 - 1) + 16;
-            const int cx = left ? xc + d2 + 1 : (right ? w - xc + d2 : d);
+            // border tiles.  The dropped terms of iimage::average (left: B and D, top: C and D) are the taps that fall on
+            // column / row -1, which the tensor map fills with +0: subtracting or adding +0 is the identity here (an
+            // integral value is never -0: the add chains start from +0), so only the clamps (right, bottom), the bottom
+            // band's term order and the clipped-area factor remain.
+            const int xr = (x + d2 < w - 1 ? x + d2 : w - 1) + 16, xl = x - d2 - 1 + 16;
+            const bool left = x < d2 + 1, right = x >= w - d2;
+            int cxi = (left ? x + d2 + 1 : (right ? w - x + d2 : d)) - d2 - 1;
+            cxi = cxi < 0 ? 0 : cxi;   // (columns >= w: clipped by the store)
             const float *colr = ring + (size_t)((xr >> 5) % RT_NS) * rmax * 32 + (xr & 31);
             const float *coll = ring + (size_t)((xl >> 5) % RT_NS) * rmax * 32 + (xl & 31);
-            const float *tcol = tab + (cx - d2 - 1);
-#pragma unroll 8
+            const float *tcol = tab + cxi;
+            const int jbmax = h - 1 - yb0;
+#pragma unroll
             for (int r = 0; r < 32; r++) {
-                const int y = y0 + r;
-                const int yc = y < h ? y : h - 1;
-                const bool top = yc < d2 + 1, bottom = yc >= h - d2;
-                const int jb = (bottom ? h - 1 : yc + d2) - yb0, jt = top ? 0 : yc - d2 - 1 - yb0;
-                const float A = colr[jb * 32], B = coll[jb * 32], C = colr[jt * 32], Dd = coll[jt * 32];
+                const int y = y0 + r;   // (warp-uniform row quantities)
+                const bool top = y < d2 + 1, bottom = y >= h - d2;
+                const int jb = r + d < jbmax ? r + d : jbmax;
+                int cyi = (top ? y + d2 + 1 : (bottom ? h - y + d2 : d)) - d2 - 1;
+                cyi = cyi < 0 ? 0 : cyi;   // (rows >= h: clipped by the store)
+                const float A = colr[jb * 32], B = coll[jb * 32], C = colr[r * 32], Dd = coll[r * 32];
                 const float t1 = bottom ? C : B, t2 = bottom ? B : C;   // bottom band: A-C-B+D, elsewhere A-B-C+D
-                const bool h1 = bottom ? !top : !left, h2 = bottom ? !left : !top;
-                float v = A;
-                v = h1 ? v - t1 : v;
-                v = h2 ? v - t2 : v;
-                v = (!top && !left) ? v + Dd : v;
-                const int cy = top ? yc + d2 + 1 : (bottom ? h - yc + d2 : d);
-                v = v * tcol[(cy - d2 - 1) * BOX_TAB_W];
-                *reinterpret_cast<float *>(ot + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2))) =
-                    (y < h && x < w) ? v : 0.f;
+                float v = A - t1;
+                v = v - t2;
+                v = v + Dd;
+                *reinterpret_cast<float *>(ot + r * 128 + so[r & 7]) = v * tcol[cyi * BOX_TAB_W];
             }
         }
         __syncwarp();
@@ -790,16 +792,28 @@ static int rowscan_tma(rb_ctx *c, DogWS *ws, int stage, const float *in, int nim
     const CUtensorMap *t = (const CUtensorMap *)ws->tmaps;
     const int bands = (c->h + 31) / 32;
     int *fail = (int *)((char *)c->dev_small + RB_DS_TMA_FAIL);
+    static const int ns_env = getenv("REBVO_B200_ROW_NS") ? atoi(getenv("REBVO_B200_ROW_NS")) : 0;
     if (stage < 0) {
         const int zin0 = (int)((in - ws->gray) / (ptrdiff_t)c->N);
-        k_rowscan_tma_plain<<<nimg * bands, 32, RT_NS * 4096 + 64 + 1024, c->stream>>>(t[TM_GRAY], t[TM_S], c->w, c->h, zin0, fail);
+        const int ns = ns_env ? ns_env : 4;
+#define RT_PLAIN(NS) k_rowscan_tma_plain<NS><<<nimg * bands, 32, NS * 4096 + 64 + 1024, c->stream>>>(t[TM_GRAY], t[TM_S], c->w, c->h, zin0, fail)
+        if (ns >= 8) RT_PLAIN(8);
+        else if (ns >= 6) RT_PLAIN(6);
+        else RT_PLAIN(4);
+#undef RT_PLAIN
     } else {
         const int d0 = c->plan.d[0][stage], d1 = c->plan.d[1][stage];
         const int rmax = 32 + (d0 > d1 ? d0 : d1);
-        const size_t smem = 2 * 4096 + (size_t)RT_NS * rmax * 128 + 64 + BOX_TAB_N * 4 + 1024;
-        k_rowscan_tma_avg<<<nimg * bands, 32, smem, c->stream>>>(
-            t[stage == 0 ? TM_I0_F0 : TM_I_F0], t[stage == 0 ? TM_I0_F1 : TM_I_F1], t[TM_S], c->w, c->h, in_mod, nper, d0, d1,
-            c->boxtab + (0 * 3 + stage) * BOX_TAB_N, c->boxtab + (1 * 3 + stage) * BOX_TAB_N, rmax, fail);
+        const int ns = ns_env ? ns_env : 4;
+#define RT_AVG(NS)                                                                                                              \
+    k_rowscan_tma_avg<NS><<<nimg * bands, 32, 2 * 4096 + (size_t)NS * rmax * 128 + 64 + BOX_TAB_N * 4 + 1024, c->stream>>>(     \
+        t[stage == 0 ? TM_I0_F0 : TM_I_F0], t[stage == 0 ? TM_I0_F1 : TM_I_F1], t[TM_S], c->w, c->h, in_mod, nper, d0, d1,       \
+        c->boxtab + (0 * 3 + stage) * BOX_TAB_N, c->boxtab + (1 * 3 + stage) * BOX_TAB_N, rmax, fail)
+        if (ns >= 6) RT_AVG(6);
+        else if (ns >= 5) RT_AVG(5);
+        else if (ns == 3) RT_AVG(3);
+        else RT_AVG(4);
+#undef RT_AVG
     }
     RB_LAUNCH_CHECK();
     return RB_OK;
@@ -808,6 +822,7 @@ static int rowscan_tma(rb_ctx *c, DogWS *ws, int stage, const float *in, int nim
 // per-device opt-ins of this file's kernels (function attributes are per device: called from rb_ctx_create after
 // cudaSetDevice, so that contexts on several GPUs of one process all get them)
 int rb_dog_device_setup(rb_ctx *c) {
+    RB_CUDA(cudaFuncSetAttribute(k_rowscan_tma_avg<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     RB_CUDA(cudaFuncSetAttribute(k_rowscan_ring<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     RB_CUDA(cudaFuncSetAttribute(k_rowscan_ring<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return RB_OK;
