@@ -128,7 +128,9 @@ class ClockSampler:
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
 # (profiles/r1_summary.md section 3, 64-frame batch = the default bench batch)
-TRAFFIC = {"k_rowscan_ring<avg>": 3.19e8,   # 307-331 MB over the two launches of a 64-frame batch
+TRAFFIC = {"k_rowscan_ring<avg>": 3.19e8,   # 307-331 MB over the two launches of a 64-frame batch (round 1)
+           "k_rowscan_tma_avg": 3.31e8,     # 188.9 MB read + 142.2 MB written (profiles/r2_summary.md section 4)
+           "k_rowscan_tma_plain": 1.385e8,  # 94.4 MB read + 44.1 MB written (the rest of the 92 MB written is still in L2)
            "k_minimizer_cluster": 2.43e6}   # profiles/r2_summary.md section 3 (operands / residuals in shared memory, gathers in L1)
 
 
@@ -278,11 +280,16 @@ def bench_ours(args):
     nav_dev = np.concatenate(navs)
     # ---------------- roofline of the scale-space passes (same workspace, same batch) --------------------
     passes = {}
+    # (names of the kernels the library dispatches to by default; the environment switches select the older versions)
+    row_tma = os.environ.get("REBVO_B200_ROW_TMA", "1") != "0" and w % 4 == 0
     rs = "k_rowscan_ring" if os.environ.get("REBVO_B200_ROWSCAN", "2") == "2" else "k_rowscan"
-    for pid, name in ((4, "k_rgb2gray"), (0, rs + "<plain>"), (1, rs + "<avg>"), (2, "k_colscan"),
-                      (3, "k_blur_dog")):
+    rs_plain, rs_avg = ("k_rowscan_tma_plain", "k_rowscan_tma_avg") if row_tma else (rs + "<plain>", rs + "<avg>")
+    blur = "k_blur_dog_tma" if os.environ.get("REBVO_B200_BLUR_TMA", "1") != "0" and w % 4 == 0 else "k_blur_dog"
+    peak_now = peak_gbs()
+    for pid, name in ((4, "k_rgb2gray"), (0, rs_plain), (1, rs_avg), (2, "k_colscan"), (3, blur)):
         ms, by = pl.bench_pass(pid, B, 20)
-        passes[name] = {"ms_per_launch": ms, "bytes_per_launch": by, "gbs": by / (ms * 1e-3) / 1e9}
+        passes[name] = {"ms_per_launch": ms, "bytes_per_launch": by, "gbs": by / (ms * 1e-3) / 1e9,
+                        "frac": by / (ms * 1e-3) / 1e9 / peak_now}
     pl.close()
     # ---------------- e2e: host buffers through the C ABI ------------------------------------------------
     pl2 = capi.Pipeline(params, max_batch=B, device=dev)
@@ -327,7 +334,7 @@ def bench_ours(args):
     # launches of each scale-space pass in one step (rb_dog_build_batch: gray, one plain row pass and one column pass over
     # B images, then per box stage an averaged row pass + a column pass over 2B images, then the blur/DoG pass); the
     # timed column pass is the 2B-image one, the B-image one counts half
-    per_step = {"k_rgb2gray": 1, rs + "<plain>": 1, rs + "<avg>": 2, "k_colscan": 2.5, "k_blur_dog": 1}
+    per_step = {"k_rgb2gray": 1, rs_plain: 1, rs_avg: 2, "k_colscan": 2.5, blur: 1}
     dog_ms = sum(passes[k]["ms_per_launch"] * n for k, n in per_step.items())
     # ---- roofline of the TIME-dominant kernel: Minimizer_RV (one launch per frame).  Algorithmic bytes per launch =
     # SURVEY.md 8(d) tryvelrot_bytes = E * (K0 * 104 + 224), E = TryVelRot evaluations (2*(init_iter+1) + 1 + iter), K0 = old
@@ -351,7 +358,7 @@ def bench_ours(args):
                                         "gbs": field_b / (stage_us["quantile+field"] * 1e-6) / 1e9},
                      "mapper": {"us": mapper_us, "algorithmic_bytes_lower_bound": mapper_b,
                                 "gbs": mapper_b / (mapper_us * 1e-6) / 1e9}}
-    dom = rs + "<avg>"
+    dom = min(passes, key=lambda k: passes[k]["gbs"])   # the scale-space pass furthest from the roofline
     roof = {"bound": "hbm", "kernel": "k_minimizer_cluster (Minimizer_RV, one launch per frame)",
             "achieved": min_gbs, "peak": peak, "unit": "GB/s", "frac": (min_gbs / peak) if min_gbs else None,
             "traffic": TRAFFIC.get("k_minimizer_cluster"), "peak_source": peak_src,

@@ -228,24 +228,6 @@ struct BlurTmaSmem {       // measured: 64 x 32 tiles (99 us per 64-frame launch
     alignas(8) unsigned long long bar;
     float tab[2][BOX_TAB_N];
 };
-__device__ __forceinline__ float box_avg_win(const float (*W)[BT_BW], int wx0, int wy0, int x, int y, int w, int h, int d, int d2,
-                                             const float *__restrict__ tab) {
-    // box_avg with the taps read from the staged window (window origin = image (wx0, wy0)); same selects, same order
-    const bool left = x < d2 + 1, right = x >= w - d2;
-    const bool top = y < d2 + 1, bottom = y >= h - d2;
-    const int xr = (right ? w - 1 : x + d2) - wx0, yb = (bottom ? h - 1 : y + d2) - wy0;
-    const int xl = (left ? 0 : x - d2 - 1) - wx0, yt = (top ? 0 : y - d2 - 1) - wy0;
-    const float A = W[yb][xr], B = W[yb][xl], C = W[yt][xr], D = W[yt][xl];
-    const float t1 = bottom ? C : B, t2 = bottom ? B : C;
-    const bool h1 = bottom ? !top : !left, h2 = bottom ? !left : !top;
-    float r = A;
-    r = h1 ? r - t1 : r;
-    r = h2 ? r - t2 : r;
-    r = (!top && !left) ? r + D : r;
-    const int cx = left ? x + d2 + 1 : (right ? w - x + d2 : d);
-    const int cy = top ? y + d2 + 1 : (bottom ? h - y + d2 : d);
-    return r * tab[(cy - d2 - 1) * BOX_TAB_W + (cx - d2 - 1)];
-}
 __global__ void __launch_bounds__(BT_THREADS) k_blur_dog_tma(const __grid_constant__ CUtensorMap tm_in,
                                                              const __grid_constant__ CUtensorMap tm_img0,
                                                              const __grid_constant__ CUtensorMap tm_dog, int w, int h,
@@ -295,15 +277,65 @@ __global__ void __launch_bounds__(BT_THREADS) k_blur_dog_tma(const __grid_consta
     }
     // 64 x 32 pixels, 256 threads: thread = column (tid & 63), rows (tid >> 6) + 4k
     const int lx = tid & 63, ly0 = tid >> 6;
-    const int x = min(x0 + lx, w - 1);
-#pragma unroll 4
-    for (int k = 0; k < BT_H / 4; k++) {
-        const int ly = ly0 + 4 * k;
-        const int y = min(y0 + ly, h - 1);
-        const float v0 = box_avg_win(sm.win0, wx0[0], wy0[0], x, y, w, h, d0, d20, sm.tab[0]);
-        const float v1 = box_avg_win(sm.win1, wx0[1], wy0[1], x, y, w, h, d1, d21, sm.tab[1]);
-        sm.o0[ly][lx] = v0;
-        sm.o1[ly][lx] = v1 - v0;
+    const int x = x0 + lx;
+    const int dm = d20 > d21 ? d20 : d21;
+    if (x0 >= dm + 1 && x0 + BT_W - 1 < w - dm && y0 >= dm + 1 && y0 + BT_H - 1 < h - dm) {
+        // centre region of iimage::average for the whole tile and both filters: constant tap offsets, no selects
+        const float a0 = sm.tab[0][d20 * BOX_TAB_W + d20], a1 = sm.tab[1][d21 * BOX_TAB_W + d21];
+        const float *r0 = &sm.win0[0][lx + 8 + d20], *l0 = &sm.win0[0][lx + 8 - d20 - 1];
+        const float *r1 = &sm.win1[0][lx + 8 + d21], *l1 = &sm.win1[0][lx + 8 - d21 - 1];
+#pragma unroll
+        for (int k = 0; k < BT_H / 4; k++) {
+            const int ly = ly0 + 4 * k;
+            float v0 = r0[(ly + d0) * BT_BW] - l0[(ly + d0) * BT_BW];   // A - B
+            v0 = v0 - r0[ly * BT_BW];                                   //   - C
+            v0 = v0 + l0[ly * BT_BW];                                   //   + D
+            float v1 = r1[(ly + d1) * BT_BW] - l1[(ly + d1) * BT_BW];
+            v1 = v1 - r1[ly * BT_BW];
+            v1 = v1 + l1[ly * BT_BW];
+            v0 *= a0;
+            v1 *= a1;
+            sm.o0[ly][lx] = v0;
+            sm.o1[ly][lx] = v1 - v0;
+        }
+    } else {
+        // border tiles: the dropped terms are the taps on column / row -1, zero-filled by the tensor map (see k_rowscan_tma_avg)
+        const float *rr[2], *ll[2], *tc[2];
+        int jbmax[2];
+#pragma unroll
+        for (int f = 0; f < 2; f++) {
+            const int d = f ? d1 : d0, d2 = f ? d21 : d20;
+            const float(*W)[BT_BW] = f ? sm.win1 : sm.win0;
+            const int xr = (x + d2 < w - 1 ? x + d2 : w - 1) - wx0[f], xl = x - d2 - 1 - wx0[f];
+            const bool left = x < d2 + 1, right = x >= w - d2;
+            int cxi = (left ? x + d2 + 1 : (right ? w - x + d2 : d)) - d2 - 1;
+            cxi = cxi < 0 ? 0 : cxi;   // (columns >= w: clipped by the store)
+            rr[f] = &W[0][xr];
+            ll[f] = &W[0][xl];
+            tc[f] = sm.tab[f] + cxi;
+            jbmax[f] = h - 1 - wy0[f];
+        }
+#pragma unroll 2
+        for (int k = 0; k < BT_H / 4; k++) {
+            const int ly = ly0 + 4 * k, y = y0 + ly;
+            float v[2];
+#pragma unroll
+            for (int f = 0; f < 2; f++) {
+                const int d = f ? d1 : d0, d2 = f ? d21 : d20;
+                const bool top = y < d2 + 1, bottom = y >= h - d2;
+                const int jb = ly + d < jbmax[f] ? ly + d : jbmax[f];
+                int cyi = (top ? y + d2 + 1 : (bottom ? h - y + d2 : d)) - d2 - 1;
+                cyi = cyi < 0 ? 0 : cyi;   // (rows >= h: clipped by the store)
+                const float A = rr[f][jb * BT_BW], B = ll[f][jb * BT_BW], C = rr[f][ly * BT_BW], D = ll[f][ly * BT_BW];
+                const float t1 = bottom ? C : B, t2 = bottom ? B : C;   // bottom band: A-C-B+D, elsewhere A-B-C+D
+                float r = A - t1;
+                r = r - t2;
+                r = r + D;
+                v[f] = r * tc[f][cyi * BOX_TAB_W];
+            }
+            sm.o0[ly][lx] = v[0];
+            sm.o1[ly][lx] = v[1] - v[0];
+        }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA unit
     __syncthreads();
