@@ -286,7 +286,7 @@ def bench_ours(args):
     rs_plain, rs_avg = ("k_rowscan_tma_plain", "k_rowscan_tma_avg") if row_tma else (rs + "<plain>", rs + "<avg>")
     blur = "k_blur_dog_tma" if os.environ.get("REBVO_B200_BLUR_TMA", "1") != "0" and w % 4 == 0 else "k_blur_dog"
     peak_now = peak_gbs()
-    for pid, name in ((4, "k_rgb2gray"), (0, rs_plain), (1, rs_avg), (2, "k_colscan"), (3, blur)):
+    for pid, name in ((4, "k_rgb2gray"), (0, rs_plain), (1, rs_avg), (2, "k_colscan_pipe"), (3, blur)):
         ms, by = pl.bench_pass(pid, B, 20)
         passes[name] = {"ms_per_launch": ms, "bytes_per_launch": by, "gbs": by / (ms * 1e-3) / 1e9,
                         "frac": by / (ms * 1e-3) / 1e9 / peak_now}
@@ -334,7 +334,7 @@ def bench_ours(args):
     # launches of each scale-space pass in one step (rb_dog_build_batch: gray, one plain row pass and one column pass over
     # B images, then per box stage an averaged row pass + a column pass over 2B images, then the blur/DoG pass); the
     # timed column pass is the 2B-image one, the B-image one counts half
-    per_step = {"k_rgb2gray": 1, rs_plain: 1, rs_avg: 2, "k_colscan": 2.5, blur: 1}
+    per_step = {"k_rgb2gray": 1, rs_plain: 1, rs_avg: 2, "k_colscan_pipe": 2.5, blur: 1}
     dog_ms = sum(passes[k]["ms_per_launch"] * n for k, n in per_step.items())
     # ---- roofline of the TIME-dominant kernel: Minimizer_RV (one launch per frame).  Algorithmic bytes per launch =
     # SURVEY.md 8(d) tryvelrot_bytes = E * (K0 * 104 + 224), E = TryVelRot evaluations (2*(init_iter+1) + 1 + iter), K0 = old

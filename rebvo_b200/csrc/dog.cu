@@ -167,6 +167,48 @@ __global__ void __launch_bounds__(64) k_colscan(const float4 *__restrict__ in, f
     }
 }
 
+// Column pass, software-pipelined: VW adjacent columns per thread, the next U rows are in flight while the current U are added
+// and stored (the add chain per column is the reference's: top to bottom, one float add per row)
+template <int VW> struct ColVec;
+template <> struct ColVec<4> { typedef float4 T; };
+__device__ __forceinline__ void col_acc(float4 &a, const float4 &v) { a.x = v.x + a.x; a.y = v.y + a.y; a.z = v.z + a.z; a.w = v.w + a.w; }
+template <int VW, int U>
+__global__ void __launch_bounds__(64) k_colscan_pipe(const typename ColVec<VW>::T *__restrict__ in,
+                                                     typename ColVec<VW>::T *__restrict__ out, int wv, int h, int nimg) {
+    typedef typename ColVec<VW>::T V;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int img = idx / wv, cx = idx - img * wv;
+    if (img >= nimg) return;
+    const V *__restrict__ I = in + (size_t)img * wv * h + cx;
+    V *__restrict__ O = out + (size_t)img * wv * h + cx;
+    V acc;
+    memset(&acc, 0, sizeof(acc));
+    V a[U], b[U];
+#pragma unroll
+    for (int k = 0; k < U; k++)
+        if (k < h) a[k] = __ldcs(&I[(size_t)k * wv]);
+    for (int y = 0; y < h; y += 2 * U) {
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            if (y + U + k < h) b[k] = __ldcs(&I[(size_t)(y + U + k) * wv]);
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            if (y + k < h) {
+                col_acc(acc, a[k]);
+                O[(size_t)(y + k) * wv] = acc;
+            }
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            if (y + 2 * U + k < h) a[k] = __ldcs(&I[(size_t)(y + 2 * U + k) * wv]);
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            if (y + U + k < h) {
+                col_acc(acc, b[k]);
+                O[(size_t)(y + U + k) * wv] = acc;
+            }
+    }
+}
+
 // Last box of both filters + sspace::build_dog (sspace.cpp:63-70): img0, dog = img1 - img0
 #define BLUR_RY 4
 __global__ void __launch_bounds__(256) k_blur_dog(const float *__restrict__ I, float *__restrict__ img0,
@@ -941,10 +983,19 @@ int rb_dog_make_tables(rb_ctx *c) {
 }
 
 static int colscan(rb_ctx *c, const float *in, float *out, int nimg) {
-    const int w4 = c->w / 4;
-    const int threads = nimg * w4;
-    k_colscan<<<rb_div_up(threads, 64), 64, 0, c->stream>>>((const float4 *)in, (float4 *)out, w4, c->h,
-                                                           nimg);
+    // measured per 64-frame launch (128 images): float4 x 16 rows pipelined 69 us, float2 x 16 70 us, float x 16 73 us,
+    // float4 x 8 82 us, the unpipelined float4 x 16 loop (REBVO_B200_COLSCAN=1) 78 us
+    static const int mode = getenv("REBVO_B200_COLSCAN") ? atoi(getenv("REBVO_B200_COLSCAN")) : 0;
+#define COL_PIPE(VW, U)                                                                                                \
+    k_colscan_pipe<VW, U><<<rb_div_up(nimg * (c->w / VW), 64), 64, 0, c->stream>>>(                                      \
+        (const ColVec<VW>::T *)in, (ColVec<VW>::T *)out, c->w / VW, c->h, nimg)
+    if (mode != 1) COL_PIPE(4, 16);
+    else {
+        const int w4 = c->w / 4;
+        const int threads = nimg * w4;
+        k_colscan<<<rb_div_up(threads, 64), 64, 0, c->stream>>>((const float4 *)in, (float4 *)out, w4, c->h, nimg);
+    }
+#undef COL_PIPE
     RB_LAUNCH_CHECK();
     return RB_OK;
 }
