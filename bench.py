@@ -307,6 +307,41 @@ def bench_ours(args):
     t_e2e_ms = pl2.event_elapsed(0, 1)
     nav_e2e = np.concatenate(navs2)
     pl2.close()
+    # ---------------- e2e with the per-frame host mirror (the 168-byte KeyLine AoS D2H, reported separately) ----
+    mirror = None
+    if rank == 0 and imu is None:
+        mirror = {}
+        # raw D2H rate of this box (one 256 MB pinned copy): what bounds the 168-byte mirror
+        hb = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
+        db = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        hb.copy_(db, non_blocking=True)
+        torch.cuda.synchronize()
+        e0.record()
+        hb.copy_(db, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        d2h_gbs = (256 << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        del hb, db
+        for mode, key, rec in ((1, "keyline_168B", capi.KEYLINE.itemsize), (2, "net_keyline_15B", 15)):
+            pl4 = capi.Pipeline(params, max_batch=B, device=dev)
+            pl4.set_mirror(mode)
+            for s in range(W):
+                pl4.push(host[s * B].data_ptr(), ts[s * B:(s + 1) * B])
+            pl4.event_record(0)
+            mbytes = 0
+            for s in range(W, W + K):
+                navm = pl4.push(host[s * B].data_ptr(), ts[s * B:(s + 1) * B])
+                mbytes += int(navm["kn"].sum()) * rec
+            pl4.event_record(1)
+            t_m = pl4.event_elapsed(0, 1)
+            pl4.close()
+            mirror[key] = {"value": K * B / (t_m * 1e-3), "unit": "frames/s", "ms_per_step": t_m / K,
+                           "d2h_mirror_bytes_per_step": mbytes / K, "d2h_gbs": mbytes / (t_m * 1e-3) / 1e9}
+        mirror["d2h_copy_peak_gbs"] = d2h_gbs
+        mirror["what"] = ("e2e plus every frame's edge map in pinned host memory (rb_pipeline_set_mirror: packed after the "
+                          "frame's map update, written to mapped host memory while the next frames are tracked): as the reference's 168-byte KeyLine array, and as the "
+                          "15-byte net_keyline records its third thread sends")
     # ---------------- where the step goes: in-situ stage profile (eager launches, one stream, CUDA events) ---------
     stage_us = None
     if rank == 0 and imu is None:   # (the IMU-mode frame loop is host-driven: no per-stage device profile)
@@ -403,6 +438,7 @@ def bench_ours(args):
            "clocks": clocks,
            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * fbytes,
                    "d2h_bytes_per_step": B * capi.NAV.itemsize, "ms_per_step": t_e2e_max / K},
+           "e2e_with_mirror": mirror,
            "gpu_launches": int(launches), "gpu_launches_per_frame": launches / (K * B),
            "parity": parity, "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(out))

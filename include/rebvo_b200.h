@@ -233,6 +233,15 @@ int rb_pipeline_push_dev(rb_pipeline *pl, const uint8_t *rgb_dev, const double *
 int rb_pipeline_reset(rb_pipeline *pl);
 /* newest / previous edge map of the ring (valid until the next push) */
 rb_map *rb_pipeline_map(rb_pipeline *pl, int age);
+/* Per-frame host mirror of the edge map: the reference hands every frame's KeyLine array (edge_finder::operator[],
+ * include/mtracklib/keyline.h) to its consumers (third thread: net_keypoint.cpp, keyframes).  With the mirror on, each frame's
+ * keylines are packed right after its map update and written into pinned host memory while the following frames are tracked
+ * (part of the batch: no extra calls).  mode 1: the 168-byte KeyLine records (rb_keyline); mode 2: the 15-byte net_keyline
+ * wire records the third thread builds from them (copy_net_keyline + copy_net_keyline_nextid with pbuf.K,
+ * rebvo_third_t.cpp:192-197); mode 0: off.  rb_pipeline_mirror(i) = the records of frame i of the last push, valid from the
+ * return of that push until the next one.  Not available in IMU mode. */
+int rb_pipeline_set_mirror(rb_pipeline *pl, int mode);
+int rb_pipeline_mirror(rb_pipeline *pl, int i, const void **records, int *n);
 int64_t rb_pipeline_launch_count(const rb_pipeline *pl);
 /* CUDA-event time (ms) of the last push split by stage: [0] h2d+gray, [1] DoG, [2] detect,
  * [3] tracker (field + minimiser), [4] mapper, [5] total */

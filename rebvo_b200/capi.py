@@ -85,7 +85,7 @@ SYMBOLS = ["rb_ctx_create", "rb_ctx_destroy", "rb_last_error", "rb_ctx_sync", "r
            "rb_pipeline_last_error", "rb_pipeline_push", "rb_pipeline_push_dev", "rb_pipeline_reset",
            "rb_pipeline_map", "rb_pipeline_launch_count", "rb_pipeline_stage_ms", "rb_pipeline_stream",
            "rb_pipeline_event_record", "rb_pipeline_event_elapsed", "rb_pipeline_event_elapsed_between", "rb_pipeline_bench_pass",
-           "rb_pipeline_set_imu",
+           "rb_pipeline_set_imu", "rb_pipeline_set_mirror", "rb_pipeline_mirror",
            "rb_pipeline_stage_profile",
            "rb_undistort_create", "rb_undistort_destroy", "rb_undistort_rgb", "rb_undistort_rgb_dev",
            "rb_try_vel", "rb_minimizer_v", "rb_ext_rot_vel", "rb_bias_correct", "rb_map_pack_net_keylines"]
@@ -467,6 +467,26 @@ class Pipeline:
         ms, by = C.c_float(0), C.c_double(0)
         self.check(self.L.rb_pipeline_bench_pass(self.h_, pass_id, nimg, iters, C.byref(ms), C.byref(by)))
         return ms.value, by.value
+
+    def set_mirror(self, mode=1):
+        """Per-frame host mirror of the edge map, written while the following frames are tracked: mode 1 = the reference's 168-byte KeyLine
+        records, 2 = its 15-byte net_keyline wire records, 0 = off."""
+        self.check(self.L.rb_pipeline_set_mirror(self.h_, int(mode)))
+        self._mirror_mode = int(mode)
+
+    def mirror(self, i):
+        """View (no copy) of the records of frame `i` of the last push: KEYLINE[n] (mode 1) or uint8[n, 15] (mode 2); valid until
+        the next push."""
+        p, kn = C.c_void_p(0), C.c_int(0)
+        self.check(self.L.rb_pipeline_mirror(self.h_, i, C.byref(p), C.byref(kn)))
+        net = getattr(self, "_mirror_mode", 1) == 2
+        if kn.value == 0:
+            return np.zeros((0, 15), np.uint8) if net else np.zeros(0, KEYLINE)
+        rec = 15 if net else KEYLINE.itemsize
+        buf = (C.c_char * (kn.value * rec)).from_address(p.value)
+        if net:
+            return np.frombuffer(buf, dtype=np.uint8).reshape(kn.value, 15)
+        return np.frombuffer(buf, dtype=KEYLINE, count=kn.value)
 
     def map(self, age=0):
         """Edge map of the ring: age 0 = newest.  Returns a Map view bound to a throw-away context facade."""

@@ -66,9 +66,7 @@ static void plane_fit_pinv(double pinv[3][25]) {
 }
 
 // ---- AoS <-> SoA ----------------------------------------------------------------------------------
-__global__ void k_pack_aos(KLSoA kl, const MapState *st, rb_keyline *out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= st->kn) return;
+__device__ __forceinline__ void pack_one(const KLSoA &kl, int i, rb_keyline *dst) {
     rb_keyline k;
     k.p_inx = kl.p_inx[i];
     float2 v = kl.m_m[i];
@@ -103,7 +101,35 @@ __global__ void k_pack_aos(KLSoA kl, const MapState *st, rb_keyline *out) {
     k.stereo_m_id = -1;
     k.stereo_rho = RB_RHO_INIT;
     k.stereo_s_rho = RB_RHO_MAX;
-    out[i] = k;
+    *dst = k;
+}
+__global__ void k_pack_aos(KLSoA kl, const MapState *st, rb_keyline *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st->kn) return;
+    pack_one(kl, i, out + i);
+}
+
+// pipeline mirror: the destination comes through a device pointer, so that one captured graph serves every staging buffer.
+// The records of a block are assembled in shared memory and leave as contiguous 8-byte stores (a thread writing its own
+// 168-byte record straight to global memory scatters 42 four-byte stores per lane).
+__global__ void __launch_bounds__(128) k_pack_aos_ind(KLSoA kl, const MapState *st, unsigned char *const *base, size_t offset) {
+    __shared__ __align__(16) rb_keyline rec[128];
+    const int kn = st->kn;
+    const int i0 = blockIdx.x * 128;
+    if (i0 >= kn) return;
+    const int i = i0 + threadIdx.x;
+    if (i < kn) pack_one(kl, i, &rec[threadIdx.x]);
+    __syncthreads();
+    const int nrec = kn - i0 < 128 ? kn - i0 : 128;
+    const int n8 = nrec * (int)(sizeof(rb_keyline) / 8);   // 168 = 21 x 8
+    uint2 *dst = reinterpret_cast<uint2 *>(*base + offset) + (size_t)i0 * (sizeof(rb_keyline) / 8);
+    const uint2 *src = reinterpret_cast<const uint2 *>(rec);
+    for (int k = threadIdx.x; k < n8; k += 128) dst[k] = src[k];
+}
+int rb_map_pack_aos_enqueue(rb_ctx *c, rb_map *m, unsigned char *const *base, size_t offset) {
+    k_pack_aos_ind<<<rb_div_up(c->kcap, 128), 128, 0, c->stream>>>(m->kl, m->st, base, offset);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
 }
 
 __global__ void k_unpack_aos(KLSoA kl, MapState *st, const rb_keyline *in, int kn) {

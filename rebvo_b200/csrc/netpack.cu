@@ -19,13 +19,7 @@ __device__ __forceinline__ unsigned char d_clamp_uchar(float f) {     // util.h:
     return (unsigned char)r;
 }
 
-__global__ void __launch_bounds__(256) k_pack_net(KLSoA kl, const MapState *__restrict__ st, unsigned char *__restrict__ out,
-                                                  int capacity, double k_prof, int *n_out) {
-    const int kn = st->kn;
-    const int n = kn < capacity ? kn : capacity;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j == 0) *n_out = n;
-    if (j >= n) return;
+__device__ __forceinline__ void pack_net_one(const KLSoA &kl, int j, int n, double k_prof, unsigned char *__restrict__ out) {
     const float2 cp = kl.c_p[j], pm = kl.p_m[j], pm0 = kl.p_m_0[j];
     const unsigned short qx = (unsigned short)round((double)cp.x), qy = (unsigned short)round((double)cp.y);
     unsigned short rho = d_clamp_ushort((float)(NET_RHO_SCALING * kl.rho[j] / k_prof));
@@ -55,6 +49,30 @@ __global__ void __launch_bounds__(256) k_pack_net(KLSoA kl, const MapState *__re
     o[12] = m_num;
     o[13] = fx;
     o[14] = fy;
+}
+
+__global__ void __launch_bounds__(256) k_pack_net(KLSoA kl, const MapState *__restrict__ st, unsigned char *__restrict__ out,
+                                                  int capacity, double k_prof, int *n_out) {
+    const int kn = st->kn;
+    const int n = kn < capacity ? kn : capacity;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0) *n_out = n;
+    if (j >= n) return;
+    pack_net_one(kl, j, n, k_prof, out);
+}
+
+// pipeline mirror (rb_pipeline_set_mirror mode 2): destination through a device pointer, K from the frame's nav record
+__global__ void __launch_bounds__(256) k_pack_net_ind(KLSoA kl, const MapState *__restrict__ st, unsigned char *const *base,
+                                                      size_t offset, const double *__restrict__ k_prof) {
+    const int n = st->kn;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    pack_net_one(kl, j, n, *k_prof, *base + offset);
+}
+int rb_map_pack_net_enqueue(rb_ctx *c, rb_map *m, unsigned char *const *base, size_t offset, const double *k_prof) {
+    k_pack_net_ind<<<rb_div_up(c->kcap, 256), 256, 0, c->stream>>>(m->kl, m->st, base, offset, k_prof);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
 }
 
 extern "C" int rb_map_pack_net_keylines(rb_map *m, double k_prof, void *dst, int capacity, int *n_out) {

@@ -86,6 +86,17 @@ struct rb_pipeline {
     int pcap, pn;
     double pacc[16];
     long long pframes;
+    // optional per-frame host mirror of the edge map (rb_pipeline_set_mirror): every frame's keylines are packed into a device
+    // staging slot right after its map update (tracker stream), then a small kernel on mirror_stream writes exactly kn records
+    // into mapped pinned host memory while the next frames are tracked; both are part of the captured batch
+    int mirror_on;                                // 0 off, 1 = 168-byte KeyLine records, 2 = 15-byte net_keyline records
+    size_t mirror_rec, mirror_stride;             // bytes per record / per frame slot (multiple of 256)
+    unsigned char *mirror_dev, *mirror_host;      // [max_batch * mirror_stride]: device staging, mapped pinned host memory
+    unsigned char **mirror_base_dev;              // device: {staging, host} address of frame 0 of the sub-batch being processed
+    unsigned char **mirror_base_pin;              // pinned: one pair per sub-batch of the current push
+    cudaStream_t mirror_stream;
+    cudaEvent_t *ev_mpack, ev_mjoin;
+    int mirror_n;                                 // frames of the last push
 };
 
 #include "imu_flow.cuh"
@@ -99,6 +110,19 @@ static inline void prof_mark(rb_pipeline *pl, int tag) {
 }
 
 int rb_dog_single_pass(rb_ctx *c, DogWS *ws, int pass_id, int nimg, double *bytes);
+int rb_map_pack_aos_enqueue(rb_ctx *c, rb_map *m, unsigned char *const *base, size_t offset_bytes);
+int rb_map_pack_net_enqueue(rb_ctx *c, rb_map *m, unsigned char *const *base, size_t offset_bytes, const double *k_prof);
+
+// staging slot -> mapped pinned host memory: exactly kn records, 16-byte stores (posted writes over PCIe)
+__global__ void __launch_bounds__(256) k_mirror_to_host(unsigned char *const *bases, size_t offset, const int *kn_p, int rec) {
+    const size_t nbytes = (size_t)(*kn_p > 0 ? *kn_p : 0) * rec;
+    const uint4 *src = reinterpret_cast<const uint4 *>(bases[0] + offset);
+    uint4 *dst = reinterpret_cast<uint4 *>(bases[1] + offset);
+    const size_t n16 = nbytes >> 4;
+    for (size_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n16; k += (size_t)gridDim.x * blockDim.x) dst[k] = src[k];
+    if (blockIdx.x == 0 && threadIdx.x < (nbytes & 15))
+        bases[1][offset + (n16 << 4) + threadIdx.x] = bases[0][offset + (n16 << 4) + threadIdx.x];
+}
 int rb_read_map_state(rb_map *m, MapState *host);
 
 static void set_eye(double *M, double v) {
@@ -292,6 +316,18 @@ extern "C" void rb_pipeline_destroy(rb_pipeline *pl) {
     delete[] pl->ev_copy;
     cudaFree(pl->rgb_src_dev);
     if (pl->rgb_src_pin) cudaFreeHost(pl->rgb_src_pin);
+    if (pl->mirror_stream) {
+        cudaStreamSynchronize(pl->mirror_stream);
+        cudaStreamDestroy(pl->mirror_stream);
+    }
+    cudaFree(pl->mirror_dev);
+    if (pl->mirror_host) cudaFreeHost(pl->mirror_host);
+    for (int i = 0; i < pl->max_batch; i++)
+        if (pl->ev_mpack && pl->ev_mpack[i]) cudaEventDestroy(pl->ev_mpack[i]);
+    delete[] pl->ev_mpack;
+    if (pl->ev_mjoin) cudaEventDestroy(pl->ev_mjoin);
+    cudaFree(pl->mirror_base_dev);
+    if (pl->mirror_base_pin) cudaFreeHost(pl->mirror_base_pin);
     rb_dogws_free(&pl->ws);
     cudaFree(pl->chain);
     cudaFree(pl->fs);
@@ -449,7 +485,23 @@ static int enqueue_batch(rb_pipeline *pl, int n, long long first_frame, bool wit
         } else {
             if ((r = track_frame(pl, neu, old, pl->fa_dev + i, pl->nav_dev + i))) return r;
         }
+        if (pl->mirror_on) {   // the frame's edge map as the reference's records, before the next frame touches it
+            const size_t ofs = (size_t)i * pl->mirror_stride;
+            if (pl->mirror_on == 1)
+                r = rb_map_pack_aos_enqueue(c, neu, pl->mirror_base_dev, ofs);
+            else   // copy_net_keyline(..., pbuf.K) of the third thread (rebvo_third_t.cpp:192-197): K of this frame's nav record
+                r = rb_map_pack_net_enqueue(c, neu, pl->mirror_base_dev, ofs, &(pl->nav_dev + i)->K);
+            if (r) return r;
+            RB_CUDA(cudaEventRecord(pl->ev_mpack[i], main_stream));
+            RB_CUDA(cudaStreamWaitEvent(pl->mirror_stream, pl->ev_mpack[i], 0));
+            k_mirror_to_host<<<8, 256, 0, pl->mirror_stream>>>(pl->mirror_base_dev, ofs, &(pl->nav_dev + i)->kn, (int)pl->mirror_rec);
+            RB_LAUNCH_CHECK();
+        }
         if (ov && i + 2 < n) RB_CUDA(cudaEventRecord(pl->ev_trk[i], main_stream));
+    }
+    if (pl->mirror_on) {   // the batch is complete when its last map has reached the host
+        RB_CUDA(cudaEventRecord(pl->ev_mjoin, pl->mirror_stream));
+        RB_CUDA(cudaStreamWaitEvent(main_stream, pl->ev_mjoin, 0));
     }
     return RB_OK;
 }
@@ -506,6 +558,12 @@ static int push_impl(rb_pipeline *pl, const uint8_t *rgb, bool on_device, const 
         if (!on_device && nsub > 1) RB_CUDA(cudaStreamWaitEvent(c->stream, pl->ev_copy[j], 0));
         RB_CUDA(cudaMemcpyAsync(pl->fa_dev, pl->fa_pin + off, sizeof(FrameArgs) * nj, cudaMemcpyHostToDevice, c->stream));
         RB_CUDA(cudaMemcpyAsync(pl->rgb_src_dev, pl->rgb_src_pin + j, sizeof(void *), cudaMemcpyHostToDevice, c->stream));
+        if (pl->mirror_on) {
+            pl->mirror_base_pin[2 * j] = pl->mirror_dev + (size_t)off * pl->mirror_stride;
+            pl->mirror_base_pin[2 * j + 1] = pl->mirror_host + (size_t)off * pl->mirror_stride;
+            RB_CUDA(cudaMemcpyAsync(pl->mirror_base_dev, pl->mirror_base_pin + 2 * j, 2 * sizeof(void *), cudaMemcpyHostToDevice,
+                                    c->stream));
+        }
         const bool graph_ok = pl->use_graph && first_j > 0;
         if (!graph_ok) {
             if ((r = enqueue_batch(pl, nj, first_j, j == 0))) return r;
@@ -564,6 +622,7 @@ static int push_impl(rb_pipeline *pl, const uint8_t *rgb, bool on_device, const 
         pl->pframes += n;
     }
     if (nav_out) memcpy(nav_out, pl->nav_pin, sizeof(rb_nav) * n);
+    pl->mirror_n = pl->mirror_on ? n : 0;
     {   // did a minimiser of this push abort (an exchange between its CTAs timed out)?  Checked on every push.
         bool aborted = false;
         for (int k = 0; k < RB_NMAPS; k++) aborted = aborted || pl->abort_pin[k] != 0;
@@ -583,6 +642,51 @@ static int push_impl(rb_pipeline *pl, const uint8_t *rgb, bool on_device, const 
     pl->stage_ms[3] = pl->stage_ms[4] = 0;
     cudaEventElapsedTime(&ms, pl->ev[0], pl->ev[3]);
     pl->stage_ms[5] = ms;
+    return RB_OK;
+}
+
+extern "C" int rb_pipeline_set_mirror(rb_pipeline *pl, int on) {
+    if (!pl || on < 0 || on > 2) return RB_ERR_ARG;
+    rb_ctx *c = pl->c;
+    RB_ENTER(c);
+    RB_CUDA(cudaSetDevice(c->device));
+    if (pl->imu) {
+        snprintf(c->err, sizeof(c->err), "set_mirror: not available in IMU mode");
+        return RB_ERR_ARG;
+    }
+    RB_CUDA(cudaStreamSynchronize(c->stream));
+    const size_t stride = ((size_t)c->kcap * sizeof(rb_keyline) + 255) & ~(size_t)255;   // (sized for the larger record)
+    if (on && !pl->mirror_dev) {
+        const size_t bytes = (size_t)pl->max_batch * stride;
+        RB_CUDA(cudaMalloc(&pl->mirror_dev, bytes));
+        RB_CUDA(cudaHostAlloc(&pl->mirror_host, bytes, cudaHostAllocMapped));
+        RB_CUDA(cudaMalloc(&pl->mirror_base_dev, 2 * sizeof(void *)));
+        RB_CUDA(cudaMallocHost(&pl->mirror_base_pin, 4 * sizeof(void *)));
+        RB_CUDA(cudaStreamCreateWithFlags(&pl->mirror_stream, cudaStreamNonBlocking));
+        pl->ev_mpack = new (std::nothrow) cudaEvent_t[pl->max_batch];
+        if (!pl->ev_mpack) return RB_ERR_ARG;
+        memset(pl->ev_mpack, 0, sizeof(cudaEvent_t) * pl->max_batch);
+        for (int i = 0; i < pl->max_batch; i++) RB_CUDA(cudaEventCreateWithFlags(&pl->ev_mpack[i], cudaEventDisableTiming));
+        RB_CUDA(cudaEventCreateWithFlags(&pl->ev_mjoin, cudaEventDisableTiming));
+    }
+    if (on != pl->mirror_on) {   // the captured batches contain (or not) the pack kernels: drop them
+        for (int i = 0; i < RB_NMAPS * (pl->max_batch + 1); i++)
+            if (pl->gexec[i]) {
+                cudaGraphExecDestroy(pl->gexec[i]);
+                pl->gexec[i] = nullptr;
+            }
+    }
+    pl->mirror_on = on;
+    pl->mirror_rec = on == 2 ? 15 : sizeof(rb_keyline);
+    pl->mirror_stride = stride;
+    pl->mirror_n = 0;
+    return RB_OK;
+}
+extern "C" int rb_pipeline_mirror(rb_pipeline *pl, int i, const void **records, int *n) {
+    if (!pl || !pl->mirror_on || !records || !n) return RB_ERR_ARG;
+    if (i < 0 || i >= pl->mirror_n) return RB_ERR_ARG;
+    *records = pl->mirror_host + (size_t)i * pl->mirror_stride;
+    *n = pl->nav_pin[i].kn;
     return RB_OK;
 }
 

@@ -147,3 +147,40 @@ def test_keyline_mirror_matches_reference_layout(built, stream):
     assert (kl["m_id"] >= 0).sum() == nav["matches"][3] or (kl["m_id"] >= 0).sum() >= nav["matches"][3]
     assert np.all(kl["rho"] > 0) and np.all(kl["s_rho"] > 0)
     pl.close()
+
+
+def test_host_mirror(built, stream):
+    """rb_pipeline_set_mirror: the per-frame records written to host memory during the push equal, for every frame, what the stage calls
+    return when the same stream is pushed one frame at a time (so that every frame is once the newest map): mode 1 =
+    KeyLine AoS vs rb_map_sync_host_keylines field by field, mode 2 = net_keyline records vs rb_map_pack_net_keylines with
+    the frame's K (itself bit-exact against the reference's packer, test_gpu_netpack.py).  The poses do not change."""
+    from rebvo_b200 import capi, synth
+    ts, fr = stream
+    got = {}
+    for mode in (1, 2):
+        pl = capi.Pipeline(capi.default_params(synth.EUROC), max_batch=20)
+        pl.set_mirror(mode)
+        navs, mirrors = [], []
+        for s in range(0, NF, 20):
+            nav = pl.push(fr[s:s + 20], ts[s:s + 20])
+            navs.append(nav)
+            for i in range(len(nav)):
+                m = pl.mirror(i)
+                assert len(m) == nav["kn"][i]
+                mirrors.append(m.copy())
+        pl.close()
+        got[mode] = (np.concatenate(navs), mirrors)
+    nav, aos = got[1]
+    assert np.array_equal(got[2][0]["Pos"], nav["Pos"])
+    one = capi.Pipeline(capi.default_params(synth.EUROC), max_batch=1)
+    for f in range(NF):
+        nav1 = one.push(fr[f:f + 1], ts[f:f + 1])
+        assert np.array_equal(nav1["Pos"][0], nav["Pos"][f])
+        kl = one.map(0).keylines()
+        assert len(kl) == len(aos[f])
+        for name in capi.KEYLINE.names:
+            assert np.array_equal(kl[name], aos[f][name], equal_nan=True), "frame %d field %s" % (f, name)
+        net = one.map(0).pack_net(k_prof=float(nav1["K"][0]))
+        assert len(net) == len(kl) and np.array_equal(net, got[2][1][f]), "frame %d net records" % f
+    one.close()
+    assert int((aos[30]["m_id"] >= 0).sum()) > 1000 and float(np.abs(aos[30]["rho"] - aos[30]["rho0"]).max()) > 0
