@@ -424,6 +424,22 @@ def bench_ours(args):
             parity = refapi.trajectory_parity(rec, nav_dev)
             parity["vs"] = "reference CPU build, same %d frames of the bench stream, same parameters" % n
             parity["e2e_arm"] = refapi.trajectory_parity(rec, nav_e2e)
+            # level A: the reference's functions, one thread, stage by stage, on a frame pair of this stream,
+            # beside this library's per-frame stage times of the same run (CUDA events, eager launches)
+            from oracle import level_a
+            la_cfg = level_a.TUM if args.config == 5 else level_a.EUROC
+            try:   # (the reference keeps O(27 * 8 * K) bytes of VLAs on the caller's stack)
+                import resource
+                resource.setrlimit(resource.RLIMIT_STACK, (min(1 << 30, resource.getrlimit(resource.RLIMIT_STACK)[1])
+                                                           if resource.getrlimit(resource.RLIMIT_STACK)[1] != resource.RLIM_INFINITY
+                                                           else 1 << 30, resource.getrlimit(resource.RLIMIT_STACK)[1]))
+            except (ImportError, ValueError, OSError):
+                pass
+            la = level_a.stage_table(la_cfg, np.ascontiguousarray(base[idx[10]]), np.ascontiguousarray(base[idx[11]]), reps=5)
+            cpu["level_a"] = {"threads": 1, "config": la_cfg["name"], "ms_per_frame": la,
+                              "what": "unmodified reference functions (oracle/_ref/libref_mtrack.so), median of 5 runs of the "
+                                      "per-frame chain on frames 10/11 of the bench stream, old map seeded with rho = 1",
+                              "gpu_us_per_frame_eager": stage_us}
         except Exception as e:  # the oracle is test infrastructure; its absence must not break the bench
             cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (e,)}
     ok = nav_dev["estimation_ok"]
