@@ -105,6 +105,16 @@ typedef struct rb_nav {
     float retuned_thresh;
 } rb_nav;
 
+/* On-disk formats of the third thread (host code, no device work).  rb_nav_format_trajectory: the lines of the reference's
+ * TrayFile (rebvo_third_t.cpp:311: t / ImuTimeScale, Pos, util::LieRot2Quaternion(PoseLie), std::scientific with 18 digits,
+ * TooN vector streaming), one per record.  rb_nav_format_log: the pose / map records of its m-file LogFile
+ * (rebvo_third_t.cpp:265-281: Kp, RKp, Rot, Vel, t, dt, i, Pose, Pos, K, KLN), a_log_inx counted from first_index, p_id from
+ * frame_id0.  Both write at most cap bytes (no terminator) and report the length needed in *written; RB_ERR_ARG if it did
+ * not fit. */
+int rb_nav_format_trajectory(const rb_nav *nav, int n, double time_scale, char *buf, size_t cap, size_t *written);
+int rb_nav_format_log(const rb_nav *nav, int n, long long first_index, long long frame_id0, char *buf, size_t cap,
+                      size_t *written);
+
 /* ---- context ---------------------------------------------------------------------------------- */
 int rb_ctx_create(rb_ctx **out, int device, const rb_camera *cam, double sigma0, double ksigma,
                   int kl_capacity);

@@ -28,7 +28,8 @@ using namespace rebvo;
 struct OutRec {
     double t, Pos[3], PoseLie[3], Pose[9], Vel[3], RotLie[3];
     double dtp0, dtp1, K, Kp, s_rho_p;
-    int kn, matches, est_ok, pad;
+    int kn, matches, est_ok, p_id;
+    double Rot[9], RKp, dt;
 };
 static std::vector<OutRec> g_out;
 static volatile int g_ncb = 0;
@@ -52,6 +53,11 @@ static bool callback(PipeBuffer &pb) {
     r.kn = pb.ef->KNum();
     r.matches = pb.ef->NumMatches();
     r.est_ok = pb.EstimationOK;
+    r.p_id = pb.p_id;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) r.Rot[i * 3 + j] = pb.nav.Rot(i, j);
+    r.RKp = pb.RKp;
+    r.dt = pb.dt;
     g_out.push_back(r);
     g_ncb++;
     return true;
@@ -104,9 +110,9 @@ int main(int argc, char **argv) {
     p.encoder_type = 0;
     p.encoder_dev = "";
     p.EdgeMapDelay = 0;
-    p.SaveLog = false;
-    p.LogFile = "/tmp/ref_log.m";
-    p.TrayFile = "/tmp/ref_tray.txt";
+    p.SaveLog = get("SaveLog", 0) != 0;
+    p.LogFile = gets("LogFile").empty() ? std::string("/tmp/ref_log.m") : gets("LogFile");
+    p.TrayFile = gets("TrayFile").empty() ? std::string("/tmp/ref_tray.txt") : gets("TrayFile");
     p.TrackKeyFrames = false;
     p.KFSavePercent = 0.7;
     p.StereoAvaiable = false;

@@ -271,7 +271,8 @@ def so3_ln(R):
 
 OUTREC = np.dtype([("t", "f8"), ("Pos", "f8", 3), ("PoseLie", "f8", 3), ("Pose", "f8", 9), ("Vel", "f8", 3),
                    ("RotLie", "f8", 3), ("dtp0", "f8"), ("dtp1", "f8"), ("K", "f8"), ("Kp", "f8"),
-                   ("s_rho_p", "f8"), ("kn", "i4"), ("matches", "i4"), ("est_ok", "i4"), ("pad", "i4")])
+                   ("s_rho_p", "f8"), ("kn", "i4"), ("matches", "i4"), ("est_ok", "i4"), ("p_id", "i4"),
+                   ("Rot", "f8", 9), ("RKp", "f8"), ("dt", "f8")])
 
 
 def run_full_rebvo(frames_file, out_file, params=None, timeout=600, exe=None):

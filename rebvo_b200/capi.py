@@ -88,9 +88,31 @@ SYMBOLS = ["rb_ctx_create", "rb_ctx_destroy", "rb_last_error", "rb_ctx_sync", "r
            "rb_pipeline_set_imu", "rb_pipeline_set_mirror", "rb_pipeline_mirror",
            "rb_pipeline_stage_profile",
            "rb_undistort_create", "rb_undistort_destroy", "rb_undistort_rgb", "rb_undistort_rgb_dev",
-           "rb_try_vel", "rb_minimizer_v", "rb_ext_rot_vel", "rb_bias_correct", "rb_map_pack_net_keylines"]
+           "rb_try_vel", "rb_minimizer_v", "rb_ext_rot_vel", "rb_bias_correct", "rb_map_pack_net_keylines",
+           "rb_nav_format_trajectory", "rb_nav_format_log"]
 
 _lib = None
+
+
+def _format_nav(fn, nav, *args):
+    nav = np.ascontiguousarray(nav, NAV)
+    need = C.c_size_t(0)
+    getattr(lib(), fn)(_p(nav), len(nav), *args, None, C.c_size_t(0), C.byref(need))
+    buf = C.create_string_buffer(max(need.value, 1))
+    r = getattr(lib(), fn)(_p(nav), len(nav), *args, buf, C.c_size_t(need.value), C.byref(need))
+    if r:
+        raise RbError("%s failed (%d)" % (fn, r))
+    return buf.raw[:need.value].decode()
+
+
+def format_trajectory(nav, time_scale=1.0):
+    """Text of the reference's trajectory file (TrayFile, rebvo_third_t.cpp:311) for these NAV records."""
+    return _format_nav("rb_nav_format_trajectory", nav, C.c_double(time_scale))
+
+
+def format_log(nav, first_index=1, frame_id0=0):
+    """Pose / map records of the reference's m-file log (LogFile, rebvo_third_t.cpp:265-281) for these NAV records."""
+    return _format_nav("rb_nav_format_log", nav, C.c_longlong(first_index), C.c_longlong(frame_id0))
 
 
 def lib():
