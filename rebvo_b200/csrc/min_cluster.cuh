@@ -537,8 +537,13 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
                         McPlan plan, MinSetup su, FrameState *post_fs, int kpc_cap, ResPtrs gres,
                         unsigned long long *ll, MinCtl *ctl) {
     MC_STAMP(15, 0);
-    pdl_wait();
-    pdl_launch();
+    // early_operands (set by the per-frame pipeline, whose previous kernel on this stream -- EstimateQuantile -- writes no
+    // keyline array): the old map's operands are staged into shared memory BEFORE waiting for that kernel, i.e. while it runs
+    const bool early = su.early_operands != 0 && su.a.match_num_thresh <= 255u;
+    if (!early) {
+        pdl_wait();
+        pdl_launch();
+    }
     MC_STAMP(15, 1);
     extern __shared__ __align__(16) unsigned char mc_dyn[];
     __shared__ McSmem sm;
@@ -549,6 +554,10 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
     const unsigned int seq0 = G > 1 ? __ldcg(&ctl->gen) : 0u;   // sequence numbers of this minimisation: seq0 + 1 + round
     const int K0 = old_st->kn;
     if (K0 <= 0) {   // "if(klist.KNum()<=0) return 0;" (:601): Vel / W0 / RVel / RW0 stay what the caller passed, no FrameCount++
+        if (early) {
+            pdl_wait();
+            pdl_launch();
+        }
         if (first_cta && tid == 0) {
             lm_out->no_keylines = 1;
             lm_out->score = 0;
@@ -587,8 +596,10 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
     tc.max_r = su.max_r;
     tc.match_thresh = su.a.match_thresh;
     tc.k_huber = su.a.reweight_distance;
-    tc.s_rho_min = su.s_rho_from_state ? old_st->s_rho_q : su.max_s_rho;
-    {
+    tc.s_rho_min = 0;
+    tc.mnt = 0;
+    if (!early) {
+        tc.s_rho_min = su.s_rho_from_state ? old_st->s_rho_q : su.max_s_rho;
         const unsigned int fc = su.fc_from_state ? f_st->frame_count : su.frame_count;
         tc.mnt = su.a.match_num_thresh < fc ? su.a.match_num_thresh : fc;
     }
@@ -600,11 +611,21 @@ __global__ void __cluster_dims__(MC_C, 1, 1) __launch_bounds__(MC_T, 1)
             v.y0[li] = o.y0;
             v.z0[li] = o.z0;
             v.s_rho[li] = o.s_rho;
-            v.flag[li] = (unsigned int)o.m_num < tc.mnt ? 1 : 0;
+            const unsigned int mn = (unsigned int)o.m_num;
+            v.flag[li] = early ? (unsigned char)(mn < 255u ? mn : 255u) : (unsigned char)(mn < tc.mnt ? 1 : 0);
             v.res[0][li] = 0.0;   // for (auto &r : Residual) r = 0   (:625)
         } else {
             v.gres[0][v.base + li] = 0.0;
         }
+    }
+    if (early) {   // now the quantile and the frame counter of the previous kernel are needed
+        pdl_wait();
+        pdl_launch();
+        tc.s_rho_min = su.s_rho_from_state ? old_st->s_rho_q : su.max_s_rho;
+        const unsigned int fc = su.fc_from_state ? f_st->frame_count : su.frame_count;
+        tc.mnt = su.a.match_num_thresh < fc ? su.a.match_num_thresh : fc;   // (<= 255)
+        const int ns = v.cnt < v.S ? v.cnt : v.S;
+        for (int li = tid; li < ns; li += MC_T) v.flag[li] = (unsigned int)v.flag[li] < tc.mnt ? 1 : 0;   // (own bytes)
     }
     const bool fused = plan.merge_round >= 0;
     if (tid == 0) {

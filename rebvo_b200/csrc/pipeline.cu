@@ -393,7 +393,12 @@ static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, const FrameArg
     // FrameCount comes from fa (written into neu->st by the folded loop-body start)
     RB_TRACE(c->stream, 2);
     bool folded = false;
-    if ((r = rb_minimizer_enqueue(c, neu, old, pl->fs->VW, &a, 0.0, true, 0, true, pl->fs, &folded))) return r;
+    // (since the old map's update only EstimateQuantile -- and build_field of the NEW map without the second stream -- ran
+    // on this stream: the minimiser may stage the old map's operands while that kernel is still running)
+    c->min_early = getenv("REBVO_B200_MIN_EARLY") ? atoi(getenv("REBVO_B200_MIN_EARLY")) != 0 : true;
+    r = rb_minimizer_enqueue(c, neu, old, pl->fs->VW, &a, 0.0, true, 0, true, pl->fs, &folded);
+    c->min_early = false;
+    if (r) return r;
     RB_TRACE(c->stream, 3);
     prof_mark(pl, ST_MINIM);
     if (!folded) {

@@ -991,6 +991,7 @@ struct MinSetup {
     unsigned int frame_count;
     int s_rho_from_state, fc_from_state;
     int debug_abort;
+    int early_operands;   // the kernel before this one on the stream writes no keyline array of the old map (see k_minimizer_cluster)
 };
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
@@ -1196,6 +1197,7 @@ int rb_minimizer_enqueue(rb_ctx *c, rb_map *fmap, rb_map *old, const double *VW_
         su.s_rho_from_state = s_rho_from_state ? 1 : 0;
         su.fc_from_state = fc_from_state ? 1 : 0;
         su.debug_abort = c->min_debug_abort;
+        su.early_operands = c->min_early ? 1 : 0;
         if ((r = launch_minimizer_cluster(c, fmap, old, plan, su, post_fs))) return r;
         if (post_folded) *post_folded = post_fs != nullptr;
         return RB_OK;
