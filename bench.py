@@ -31,8 +31,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "frames/sec @752x480 EuRoC replay (synthetic stand-in), detect+track+map; pose ATE vs reference in `parity`"
-WORKLOAD = ("configs[1]: EuRoC MH_01-like 752x480 full replay, 1xB200 per sequence, IMU off (pure edge VO); "
-            "synthetic two-layer parallax stream seed 7")
+WORKLOAD = ("configs[1]: EuRoC MH_01-like 752x480 full replay, 1xB200 per sequence, IMU off (pure edge VO), UseUndistort=1 with "
+            "the EuRoC rad-tan coefficients in both arms; synthetic two-layer parallax stream seed 7")
 
 
 def rank_info():
@@ -49,8 +49,17 @@ WORKLOAD5 = ("configs[4]: TUM fr2_desk-like 640x480 replay, app/rebvorun/GlobalC
 METRIC3 = ("frames/sec @752x480 EuRoC replay with IMU fusion (ImuMode=2, synthetic stand-in), detect+track+map+scale filter; "
            "pose ATE vs reference in `parity`")
 WORKLOAD3 = ("configs[2]: EuRoC V1_02-like 752x480 replay with ImuGrabber csv fusion (IMUMode=2), 1xB200; synthetic two-layer "
-             "parallax stream seed 7 + synthetic 200 Hz IMU (gyro bias 0.02 rad/s, noise 1.7e-4)")
+             "parallax stream seed 7 + synthetic 200 Hz IMU (gyro bias 0.02 rad/s, noise 1.7e-4); UseUndistort=1 in both arms")
 IMU_BASE_N = 160
+
+
+# GlobalConfig_EuRoC_2.txt:64-68,73: the EuRoC configurations run UseUndistort=1 with these rad-tan coefficients
+EUROC_KC = (-0.28340811, 0.07395907, 0.0, 0.00019359, 1.76187114e-05)
+
+
+def undistort_of(config):
+    """distortion coefficients both arms undistort with (None: UseUndistort=0, the desk / synthetic configurations)"""
+    return EUROC_KC if config in (2, 3) else None
 
 
 def stream_setup(config):
@@ -158,7 +167,7 @@ def cpu_model():
     return "unknown"
 
 
-def run_reference(frames_file_dir, ts, base, idx, n_frames, warm_frames, affinity=True, gpu_params=None, imu=None):
+def run_reference(frames_file_dir, ts, base, idx, n_frames, warm_frames, affinity=True, gpu_params=None, imu=None, kc=None):
     """The reference's own CPU implementation (3 pipeline threads) on n_frames of the stream."""
     from oracle import refapi
     from rebvo_b200 import synth
@@ -172,6 +181,8 @@ def run_reference(frames_file_dir, ts, base, idx, n_frames, warm_frames, affinit
         csv = path + ".imu.csv"
         synth.write_imu_csv(csv, imu)
         params.update(ImuMode=2, ImuFile=csv, ImuTimeScale=1, InitBias=1, InitBiasFrameNum=5)
+    if kc is not None:
+        params.update(UseUndistort=1, KcR2=kc[0], KcR4=kc[1], KcR6=kc[2], KcP1=kc[3], KcP2=kc[4])
     if affinity and ncpu >= 3:
         params.update(SetAffinity=1, CPU0=0, CPU1=1, CPU2=2)
     try:
@@ -209,7 +220,8 @@ def bench_reference(args):
         from rebvo_b200 import synth
         seq = synth.Sequence(w=cam["w"], h=cam["h"], seed=seed0, zf=cam["zfx"])
         imu = synth.imu_samples_walk(seq, total, min(IMU_BASE_N, total))
-    info, rec = run_reference("/tmp", ts, base, idx, total, per * args.warmup, gpu_params=params, imu=imu)
+    info, rec = run_reference("/tmp", ts, base, idx, total, per * args.warmup, gpu_params=params, imu=imu,
+                              kc=undistort_of(args.config))
     fps = info["fps"]
     ncpu = os.cpu_count() or 1
     out = {"metric": metric, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -260,7 +272,14 @@ def bench_ours(args):
 
     sampler = ClockSampler(dev)
     # ---------------- value: frames resident in HBM ----------------------------------------------------
-    pl = capi.Pipeline(params, max_batch=B, device=dev)
+    kc = undistort_of(args.config)
+
+    def new_pipeline():
+        q = capi.Pipeline(params, max_batch=B, device=dev)
+        if kc is not None:
+            q.set_undistort(kc)
+        return q
+    pl = new_pipeline()
     if imu is not None:
         pl.set_imu(imu, capi.default_imu_params(InitBias=1, InitBiasFrameNum=5))
     navs = []
@@ -286,13 +305,14 @@ def bench_ours(args):
     rs_plain, rs_avg = ("k_rowscan_tma_plain", "k_rowscan_tma_avg") if row_tma else (rs + "<plain>", rs + "<avg>")
     blur = "k_blur_dog_tma" if os.environ.get("REBVO_B200_BLUR_TMA", "1") != "0" and w % 4 == 0 else "k_blur_dog"
     peak_now = peak_gbs()
-    for pid, name in ((4, "k_rgb2gray"), (0, rs_plain), (1, rs_avg), (2, "k_colscan_pipe"), (3, blur)):
+    gray = "k_undistort_gray" if kc is not None else "k_rgb2gray"
+    for pid, name in ((5 if kc is not None else 4, gray), (0, rs_plain), (1, rs_avg), (2, "k_colscan_pipe"), (3, blur)):
         ms, by = pl.bench_pass(pid, B, 20)
         passes[name] = {"ms_per_launch": ms, "bytes_per_launch": by, "gbs": by / (ms * 1e-3) / 1e9,
                         "frac": by / (ms * 1e-3) / 1e9 / peak_now}
     pl.close()
     # ---------------- e2e: host buffers through the C ABI ------------------------------------------------
-    pl2 = capi.Pipeline(params, max_batch=B, device=dev)
+    pl2 = new_pipeline()
     if imu is not None:
         pl2.set_imu(imu, capi.default_imu_params(InitBias=1, InitBiasFrameNum=5))
     navs2 = []
@@ -324,7 +344,7 @@ def bench_ours(args):
         d2h_gbs = (256 << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9
         del hb, db
         for mode, key, rec in ((1, "keyline_168B", capi.KEYLINE.itemsize), (2, "net_keyline_15B", 15)):
-            pl4 = capi.Pipeline(params, max_batch=B, device=dev)
+            pl4 = new_pipeline()
             pl4.set_mirror(mode)
             for s in range(W):
                 pl4.push(host[s * B].data_ptr(), ts[s * B:(s + 1) * B])
@@ -347,7 +367,7 @@ def bench_ours(args):
     if rank == 0 and imu is None:   # (the IMU-mode frame loop is host-driven: no per-stage device profile)
         os.environ["REBVO_B200_STAGE_PROF"] = "1"
         try:
-            pl3 = capi.Pipeline(params, max_batch=B, device=dev)
+            pl3 = new_pipeline()
             for s in range(min(3, K + W)):
                 pl3.push_dev(devbuf[s * B].data_ptr(), ts[s * B:(s + 1) * B])
             stage_us, _ = pl3.stage_profile()
@@ -369,7 +389,7 @@ def bench_ours(args):
     # launches of each scale-space pass in one step (rb_dog_build_batch: gray, one plain row pass and one column pass over
     # B images, then per box stage an averaged row pass + a column pass over 2B images, then the blur/DoG pass); the
     # timed column pass is the 2B-image one, the B-image one counts half
-    per_step = {"k_rgb2gray": 1, rs_plain: 1, rs_avg: 2, "k_colscan_pipe": 2.5, blur: 1}
+    per_step = {gray: 1, rs_plain: 1, rs_avg: 2, "k_colscan_pipe": 2.5, blur: 1}
     dog_ms = sum(passes[k]["ms_per_launch"] * n for k, n in per_step.items())
     # ---- roofline of the TIME-dominant kernel: Minimizer_RV (one launch per frame).  Algorithmic bytes per launch =
     # SURVEY.md 8(d) tryvelrot_bytes = E * (K0 * 104 + 224), E = TryVelRot evaluations (2*(init_iter+1) + 1 + iter), K0 = old
@@ -415,7 +435,7 @@ def bench_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         try:
             n = min(620, total)
-            info, rec = run_reference("/tmp", ts, base, idx, n, 20, gpu_params=params, imu=imu)
+            info, rec = run_reference("/tmp", ts, base, idx, n, 20, gpu_params=params, imu=imu, kc=undistort_of(args.config))
             cpu = {"value": info["fps"], "unit": "frames/s", "cores": 3, "kind": "reference", "cpu_model": cpu_model(),
                    "sample": "first %d frames of the bench stream (20 warm-up) through the unmodified 3-thread REBVO "
                              "built from /root/reference sources; %d host cpus visible" % (n, os.cpu_count() or 1),

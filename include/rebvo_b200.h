@@ -126,6 +126,10 @@ int rb_ctx_sync(rb_ctx *c);
 int rb_ctx_box_plan(const rb_ctx *c, int *out_d, double *out_sigma_r);
 /* kernels launched on this context so far (bench.py's gpu_launches) */
 int64_t rb_ctx_launch_count(const rb_ctx *c);
+/* which scale-space kernels a map's own workspace dispatches to, valid after its first rb_map_dog_build: bit 0 = row passes on
+ * TMA tiles, bit 1 = last box + DoG on TMA tiles (0 = the pre-TMA kernels: width not a multiple of 4, environment switch, or
+ * tensor-map creation failed) */
+int rb_map_scale_space_path(const rb_map *m);
 
 /* ---- edge map (ring slot) ---------------------------------------------------------------------- */
 int rb_map_create(rb_ctx *c, rb_map **out);
@@ -251,6 +255,10 @@ rb_map *rb_pipeline_map(rb_pipeline *pl, int age);
  * rebvo_third_t.cpp:192-197); mode 0: off.  rb_pipeline_mirror(i) = the records of frame i of the last push, valid from the
  * return of that push until the next one.  Not available in IMU mode. */
 int rb_pipeline_set_mirror(rb_pipeline *pl, int mode);
+/* UseUndistort=1 (rebvo_first_t.cpp:211-231: image_undistort::undistort<true> on every captured frame before the scale
+ * space): with a non-zero kc = {KcR2, KcR4, KcR6, KcP1, KcP2} every pushed frame is undistorted with the reference's
+ * fixed-point bilinear map, fused into the RGB -> BW pass.  kc == NULL or all zero: off. */
+int rb_pipeline_set_undistort(rb_pipeline *pl, const double kc[5]);
 int rb_pipeline_mirror(rb_pipeline *pl, int i, const void **records, int *n);
 int64_t rb_pipeline_launch_count(const rb_pipeline *pl);
 /* CUDA-event time (ms) of the last push split by stage: [0] h2d+gray, [1] DoG, [2] detect,

@@ -123,10 +123,10 @@ int main(int argc, char **argv) {
     p.z_f_y = get("ZfY", 457.296);
     p.pp_x = get("PPx", 367.215);
     p.pp_y = get("PPy", 248.375);
-    p.kc = {0, 0, 0, 0, 0};
+    p.kc = {get("KcR2", 0), get("KcR4", 0), get("KcR6", 0), get("KcP1", 0), get("KcP2", 0)};
     p.config_fps = get("FPS", 20);
     p.soft_fps = get("SoftFPS", 1e6);
-    p.useUndistort = false;
+    p.useUndistort = get("UseUndistort", 0) != 0;
     p.rotatedCam = false;
     p.CameraDevice = "";
     p.z_f_x_stereo = p.z_f_x;

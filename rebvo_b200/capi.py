@@ -85,11 +85,11 @@ SYMBOLS = ["rb_ctx_create", "rb_ctx_destroy", "rb_last_error", "rb_ctx_sync", "r
            "rb_pipeline_last_error", "rb_pipeline_push", "rb_pipeline_push_dev", "rb_pipeline_reset",
            "rb_pipeline_map", "rb_pipeline_launch_count", "rb_pipeline_stage_ms", "rb_pipeline_stream",
            "rb_pipeline_event_record", "rb_pipeline_event_elapsed", "rb_pipeline_event_elapsed_between", "rb_pipeline_bench_pass",
-           "rb_pipeline_set_imu", "rb_pipeline_set_mirror", "rb_pipeline_mirror",
+           "rb_pipeline_set_imu", "rb_pipeline_set_mirror", "rb_pipeline_mirror", "rb_pipeline_set_undistort",
            "rb_pipeline_stage_profile",
            "rb_undistort_create", "rb_undistort_destroy", "rb_undistort_rgb", "rb_undistort_rgb_dev",
            "rb_try_vel", "rb_minimizer_v", "rb_ext_rot_vel", "rb_bias_correct", "rb_map_pack_net_keylines",
-           "rb_nav_format_trajectory", "rb_nav_format_log"]
+           "rb_nav_format_trajectory", "rb_nav_format_log", "rb_map_scale_space_path"]
 
 _lib = None
 
@@ -287,6 +287,10 @@ class Map:
         k = C.c_int(0)
         self.ctx.check(self.L.rb_map_sync_host_keylines(self.h_, _p(out), len(out), C.byref(k)))
         return out[:kn]
+
+    def scale_space_path(self):
+        """bit 0: row passes on TMA tiles, bit 1: last box + DoG on TMA tiles (after dog_build)."""
+        return int(self.L.rb_map_scale_space_path(self.h_))
 
     def pack_net(self, k_prof=1.0, capacity=None):
         """15-byte net_keyline records (uint8 array [n, 15]) packed on the device."""
@@ -489,6 +493,15 @@ class Pipeline:
         ms, by = C.c_float(0), C.c_double(0)
         self.check(self.L.rb_pipeline_bench_pass(self.h_, pass_id, nimg, iters, C.byref(ms), C.byref(by)))
         return ms.value, by.value
+
+    def set_undistort(self, kc):
+        """UseUndistort=1 with kc = (KcR2, KcR4, KcR6, KcP1, KcP2); None / zeros = off."""
+        if kc is None:
+            self.check(self.L.rb_pipeline_set_undistort(self.h_, None))
+        else:
+            a = np.ascontiguousarray(kc, np.float64)
+            assert a.shape == (5,)
+            self.check(self.L.rb_pipeline_set_undistort(self.h_, _p(a)))
 
     def set_mirror(self, mode=1):
         """Per-frame host mirror of the edge map, written while the following frames are tracked: mode 1 = the reference's 168-byte KeyLine

@@ -202,7 +202,9 @@ extern "C" int rb_ctx_create(rb_ctx **out, int device, const rb_camera *cam, dou
         const char *mc = getenv("REBVO_B200_MIN_CLUSTER");
         c->min_cluster = !(mc && atoi(mc) == 0);
         const char *rs = getenv("REBVO_B200_ROWSCAN");
-        c->rowscan_mode = rs ? atoi(rs) : 2;   // cp.async ring measured 1.85x faster than register prefetch
+        c->rowscan_mode = rs ? atoi(rs) : 2;
+        c->row_ns = getenv("REBVO_B200_ROW_NS") ? atoi(getenv("REBVO_B200_ROW_NS")) : 0;
+        c->colscan_mode = getenv("REBVO_B200_COLSCAN") ? atoi(getenv("REBVO_B200_COLSCAN")) : 0;   // cp.async ring measured 1.85x faster than register prefetch
     }
     // sspace::sspace (sspace.cpp:36-46): filter1 sigma = filter0.sigma_r * k_sigma
     box_plan_one(sigma0, 3, c->plan.d[0], &c->plan.sigma_r[0]);
@@ -528,6 +530,13 @@ extern "C" int rb_map_knum(rb_map *m, int *kn) {
     if (r) return r;
     *kn = s.kn;
     return RB_OK;
+}
+
+/* which scale-space kernels this map's workspace dispatches to (after the first rb_map_dog_build): bit 0 = TMA row passes,
+ * bit 1 = TMA last box + DoG; 0 before the workspace exists */
+extern "C" int rb_map_scale_space_path(const rb_map *m) {
+    if (!m || !m->ws.gray) return 0;
+    return (m->ws.tma_row_ok ? 1 : 0) | (m->ws.tma_ok ? 2 : 0);
 }
 
 extern "C" int rb_map_sync_host_keylines(rb_map *m, rb_keyline *dst, int capacity, int *kn) {

@@ -109,6 +109,8 @@ struct rb_ctx {
     int min_debug_abort;
     bool min_early;      // set by rb_pipeline around its Minimizer_RV launch: operands may be staged before the PDL wait  // test hook (env REBVO_B200_MIN_FORCE_ABORT=1): the kernel raises its abort flag at once
     int min_cluster_xchg; // 1: st.async + mbarrier exchange, 0: DSMEM stores + barrier.cluster (env REBVO_B200_MIN_XCHG)
+    int row_ns;          // env REBVO_B200_ROW_NS: depth of the TMA tile ring of the row passes (0 = default 4)
+    int colscan_mode;    // env REBVO_B200_COLSCAN: 1 = unpipelined column pass
     int rowscan_mode;    // env REBVO_B200_ROWSCAN: 1 = register-prefetch kernel, 2 = cp.async shared-memory ring
 };
 // layout of rb_ctx::dev_small / pinned (byte offsets)

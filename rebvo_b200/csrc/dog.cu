@@ -866,7 +866,7 @@ static int rowscan_tma(rb_ctx *c, DogWS *ws, int stage, const float *in, int nim
     const CUtensorMap *t = (const CUtensorMap *)ws->tmaps;
     const int bands = (c->h + 31) / 32;
     int *fail = (int *)((char *)c->dev_small + RB_DS_TMA_FAIL);
-    static const int ns_env = getenv("REBVO_B200_ROW_NS") ? atoi(getenv("REBVO_B200_ROW_NS")) : 0;
+    const int ns_env = c->row_ns;
     if (stage < 0) {
         const int zin0 = (int)((in - ws->gray) / (ptrdiff_t)c->N);
         const int ns = ns_env ? ns_env : 4;
@@ -985,7 +985,7 @@ int rb_dog_make_tables(rb_ctx *c) {
 static int colscan(rb_ctx *c, const float *in, float *out, int nimg) {
     // measured per 64-frame launch (128 images): float4 x 16 rows pipelined 69 us, float2 x 16 70 us, float x 16 73 us,
     // float4 x 8 82 us, the unpipelined float4 x 16 loop (REBVO_B200_COLSCAN=1) 78 us
-    static const int mode = getenv("REBVO_B200_COLSCAN") ? atoi(getenv("REBVO_B200_COLSCAN")) : 0;
+    const int mode = c->colscan_mode;
 #define COL_PIPE(VW, U)                                                                                                \
     k_colscan_pipe<VW, U><<<rb_div_up(nimg * (c->w / VW), 64), 64, 0, c->stream>>>(                                      \
         (const ColVec<VW>::T *)in, (ColVec<VW>::T *)out, c->w / VW, c->h, nimg)

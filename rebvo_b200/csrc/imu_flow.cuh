@@ -276,7 +276,9 @@ static int imu_push(rb_pipeline *pl, ImuFlow &f, const uint8_t *rgb, bool on_dev
     const void *src = on_device ? (const void *)rgb : (const void *)pl->ws.rgb;
     RB_CUDA(cudaMemcpyAsync(pl->rgb_src_dev, &src, sizeof(void *), cudaMemcpyHostToDevice, c->stream));
     RB_CUDA(cudaStreamSynchronize(c->stream));   // (&src is a stack variable)
-    if ((r = rb_dog_gray(c, &pl->ws, n, pl->rgb_src_dev))) return r;
+    if (pl->und) r = rb_undistort_gray_enqueue(pl->und, pl->rgb_src_dev, pl->ws.gray, n);
+    else r = rb_dog_gray(c, &pl->ws, n, pl->rgb_src_dev);
+    if (r) return r;
     if ((r = rb_dog_build_batch(c, &pl->ws, n))) return r;
     for (int i = 0; i < n; i++) {
         const long long fr = pl->n_pushed + i;

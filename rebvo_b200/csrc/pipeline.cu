@@ -97,8 +97,10 @@ struct rb_pipeline {
     cudaStream_t mirror_stream;
     cudaEvent_t *ev_mpack, ev_mjoin;
     int mirror_n;                                 // frames of the last push
+    rb_undistort *und;                            // UseUndistort=1 (rb_pipeline_set_undistort): fused into the gray pass
 };
 
+int rb_undistort_gray_enqueue(rb_undistort *u, const void *const *src_pp, float *gray, int nimg);
 #include "imu_flow.cuh"
 
 enum { ST_H2D = 0, ST_GRAY, ST_DOG, ST_DETECT, ST_REEST, ST_FIELD, ST_MINIM, ST_FWD_ROT, ST_DMATCH, ST_REG_EKF, ST_RESCALE,
@@ -320,6 +322,7 @@ extern "C" void rb_pipeline_destroy(rb_pipeline *pl) {
         cudaStreamSynchronize(pl->mirror_stream);
         cudaStreamDestroy(pl->mirror_stream);
     }
+    if (pl->und) rb_undistort_destroy(pl->und);
     cudaFree(pl->mirror_dev);
     if (pl->mirror_host) cudaFreeHost(pl->mirror_host);
     for (int i = 0; i < pl->max_batch; i++)
@@ -444,7 +447,9 @@ static int enqueue_batch(rb_pipeline *pl, int n, long long first_frame, bool wit
     const rb_params &p = pl->p;
     int r;
     prof_mark(pl, ST_H2D);
-    if ((r = rb_dog_gray(c, &pl->ws, n, pl->rgb_src_dev))) return r;
+    if (pl->und) r = rb_undistort_gray_enqueue(pl->und, pl->rgb_src_dev, pl->ws.gray, n);   // rebvo_first_t.cpp:231 + RGB -> BW
+    else r = rb_dog_gray(c, &pl->ws, n, pl->rgb_src_dev);
+    if (r) return r;
     prof_mark(pl, ST_GRAY);
     if (with_events) RB_CUDA(cudaEventRecord(pl->ev[1], c->stream));
     if ((r = rb_dog_build_batch(c, &pl->ws, n))) return r;
@@ -650,6 +655,33 @@ static int push_impl(rb_pipeline *pl, const uint8_t *rgb, bool on_device, const 
     return RB_OK;
 }
 
+extern "C" int rb_pipeline_set_undistort(rb_pipeline *pl, const double kc[5]) {
+    if (!pl) return RB_ERR_ARG;
+    rb_ctx *c = pl->c;
+    RB_ENTER(c);
+    RB_CUDA(cudaSetDevice(c->device));
+    RB_CUDA(cudaStreamSynchronize(c->stream));
+    if (pl->und) {
+        rb_undistort_destroy(pl->und);
+        pl->und = nullptr;
+    }
+    bool any = false;
+    for (int i = 0; kc && i < 5; i++) any = any || kc[i] != 0.0;
+    if (any) {
+        int r = rb_undistort_create(c, kc, &pl->und);
+        if (r) {
+            if (pl->und) rb_undistort_destroy(pl->und);
+            pl->und = nullptr;
+            return r;
+        }
+    }
+    for (int i = 0; i < RB_NMAPS * (pl->max_batch + 1); i++)   // the captured batches contain the other gray kernel
+        if (pl->gexec[i]) {
+            cudaGraphExecDestroy(pl->gexec[i]);
+            pl->gexec[i] = nullptr;
+        }
+    return RB_OK;
+}
 extern "C" int rb_pipeline_set_mirror(rb_pipeline *pl, int on) {
     if (!pl || on < 0 || on > 2) return RB_ERR_ARG;
     rb_ctx *c = pl->c;
@@ -730,11 +762,23 @@ extern "C" int rb_pipeline_bench_pass(rb_pipeline *pl, int pass_id, int nimg, in
     if (nimg < 1 || nimg > pl->max_batch || iters < 1) return RB_ERR_ARG;
     int r;
     double bytes = 0;
+    // pass 5: the gray pass with the undistortion fused in (needs rb_pipeline_set_undistort; source = the workspace's RGB);
+    // algorithmic bytes: 3N in + 4N out per frame + the 32N-byte map once per launch
+    auto one = [&]() -> int {
+        if (pass_id != 5) return rb_dog_single_pass(c, &pl->ws, pass_id, nimg, &bytes);
+        if (!pl->und) return RB_ERR_STATE;
+        bytes = 7.0 * c->N * nimg + 32.0 * c->N;
+        return rb_undistort_gray_enqueue(pl->und, pl->rgb_src_dev, pl->ws.gray, nimg);
+    };
+    if (pass_id == 5) {
+        const void *src = pl->ws.rgb;
+        RB_CUDA(cudaMemcpyAsync(pl->rgb_src_dev, &src, sizeof(void *), cudaMemcpyHostToDevice, c->stream));
+    }
     for (int i = 0; i < 3; i++)
-        if ((r = rb_dog_single_pass(c, &pl->ws, pass_id, nimg, &bytes))) return r;
+        if ((r = one())) return r;
     RB_CUDA(cudaEventRecord(pl->user_ev[6], c->stream));
     for (int i = 0; i < iters; i++)
-        if ((r = rb_dog_single_pass(c, &pl->ws, pass_id, nimg, &bytes))) return r;
+        if ((r = one())) return r;
     RB_CUDA(cudaEventRecord(pl->user_ev[7], c->stream));
     RB_CUDA(cudaEventSynchronize(pl->user_ev[7]));
     float ms = 0;

@@ -49,6 +49,44 @@ __global__ void __launch_bounds__(256) k_undistort_rgb(const uint8_t *__restrict
     o[2] = (uint8_t)(b >> 16);
 }
 
+// Fused with Image<float>::ConvertRGB2BW for the per-frame pipeline (rebvo_first_t.cpp:231 then sspace::build's first
+// step): gray = float(r + g + b) of the undistorted pixel, whose channels are the integer bilinear sums >> 16.  The
+// undistorted colour image itself is only consumed by the encoder / viewer (out of scope), so it is never materialised: per
+// frame 3N bytes of RGB in, 4N of gray out, the 32N-byte map stays L2-resident across the batch.  The RGB source is read
+// through a device-resident pointer like k_rgb2gray.
+#define UG_IMGS 1   // images per thread.  Measured per 64-frame launch: 1 -> 123 us, 8 (map entry loaded once for 8 frames) -> 133 us:
+                    // the pass is bound by its twelve byte gathers per pixel, not by the L2-resident map
+__global__ void __launch_bounds__(256) k_undistort_gray(const uint8_t *const *__restrict__ src_pp, float *__restrict__ gray,
+                                                        const int4 *__restrict__ inx, const int4 *__restrict__ iw, int N,
+                                                        int nimg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int img0 = blockIdx.y * UG_IMGS;
+    const int4 ix = inx[i], w = iw[i];
+    const int o0 = 3 * ix.x, o1 = 3 * ix.y, o2 = 3 * ix.z, o3 = 3 * ix.w;
+    const uint8_t *src = *src_pp + (size_t)img0 * 3 * N;
+    float *dst = gray + (size_t)img0 * N + i;
+#pragma unroll 4
+    for (int k = 0; k < UG_IMGS; k++) {
+        if (img0 + k >= nimg) break;
+        const uint8_t *p0 = src + o0, *p1 = src + o1, *p2 = src + o2, *p3 = src + o3;
+        const int r = w.x * (int)p0[0] + w.y * (int)p1[0] + w.z * (int)p2[0] + w.w * (int)p3[0];
+        const int g = w.x * (int)p0[1] + w.y * (int)p1[1] + w.z * (int)p2[1] + w.w * (int)p3[1];
+        const int b = w.x * (int)p0[2] + w.y * (int)p1[2] + w.z * (int)p2[2] + w.w * (int)p3[2];
+        const unsigned int sum = (unsigned int)((uint8_t)(r >> 16)) + (unsigned int)((uint8_t)(g >> 16)) + (unsigned int)((uint8_t)(b >> 16));
+        *dst = (float)sum;
+        src += (size_t)3 * N;
+        dst += N;
+    }
+}
+int rb_undistort_gray_enqueue(rb_undistort *u, const void *const *src_pp, float *gray, int nimg) {
+    rb_ctx *c = u->c;
+    dim3 grid(rb_div_up(c->N, 256), rb_div_up(nimg, UG_IMGS));
+    k_undistort_gray<<<grid, 256, 0, c->stream>>>((const uint8_t *const *)src_pp, gray, u->inx, u->iw, c->N, nimg);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
 static inline bool inx_valid_f(float fx, float fy, int w, int h) {
     // Image::isInxValid takes `const uint&`: the float is converted to unsigned (x86-64: through a 64-bit
     // truncation, so negatives wrap to huge values and fail the upper bound)

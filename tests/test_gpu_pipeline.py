@@ -184,3 +184,34 @@ def test_host_mirror(built, stream):
         assert len(net) == len(kl) and np.array_equal(net, got[2][1][f]), "frame %d net records" % f
     one.close()
     assert int((aos[30]["m_id"] >= 0).sum()) > 1000 and float(np.abs(aos[30]["rho"] - aos[30]["rho0"]).max()) > 0
+
+
+EUROC_KC = (-0.28340811, 0.07395907, 0.0, 0.00019359, 1.76187114e-05)   # GlobalConfig_EuRoC_2.txt:64-68, UseUndistort=1
+
+
+def test_undistort_in_the_flow(built, stream, tmp_path):
+    """UseUndistort=1 (every EuRoC configuration of the reference): rb_pipeline_set_undistort against the unmodified reference
+    run with the same distortion coefficients.  The undistortion is integer arithmetic on a host-built map, so the keyline
+    counts stay identical and the trajectory stays at round-off distance; and it does change the input (other counts than
+    without it)."""
+    from oracle import refapi
+    from rebvo_b200 import capi, synth
+    if not os.path.exists(refapi.EXE):
+        pytest.skip("oracle/_ref/ref_rebvo not built")
+    ts, fr = stream
+    n = 40
+    path = str(tmp_path / "frames.bin")
+    synth.write_frames_file(path, ts[:n], fr[:n])
+    kv = dict(UseUndistort=1, KcR2=EUROC_KC[0], KcR4=EUROC_KC[1], KcR6=EUROC_KC[2], KcP1=EUROC_KC[3], KcP2=EUROC_KC[4])
+    info, rec = refapi.run_full_rebvo(path, str(tmp_path / "out.bin"), kv)
+    os.remove(path)
+    pl = capi.Pipeline(capi.default_params(synth.EUROC), max_batch=20)
+    pl.set_undistort(EUROC_KC)
+    nav = np.concatenate([pl.push(fr[s:s + 20], ts[s:s + 20]) for s in range(0, n, 20)])
+    pl.set_undistort(None)   # switching it off again drops the captured batches
+    pl.close()
+    plain, _ = _gpu_run(stream, 20)
+    par = refapi.trajectory_parity(rec, nav)
+    print(par)
+    assert par["kn_equal"] and par["matches_equal"] and par["ate_m"] < 1e-9
+    assert not np.array_equal(nav["kn"][:n], plain["kn"][:n])
