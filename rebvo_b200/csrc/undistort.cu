@@ -54,35 +54,88 @@ __global__ void __launch_bounds__(256) k_undistort_rgb(const uint8_t *__restrict
 // undistorted colour image itself is only consumed by the encoder / viewer (out of scope), so it is never materialised: per
 // frame 3N bytes of RGB in, 4N of gray out, the 32N-byte map stays L2-resident across the batch.  The RGB source is read
 // through a device-resident pointer like k_rgb2gray.
-#define UG_IMGS 1   // images per thread.  Measured per 64-frame launch: 1 -> 123 us, 8 (map entry loaded once for 8 frames) -> 133 us:
-                    // the pass is bound by its twelve byte gathers per pixel, not by the L2-resident map
+// The taps are gathered as aligned 32-bit words (a pixel's three bytes start at any byte offset: two neighbouring words and a
+// funnel shift; the two taps of a row are adjacent pixels almost everywhere, so three words serve both) instead of twelve
+// byte loads per pixel, which bound the first version (123 us per 64-frame launch, ~4.5 cycles per byte gather per SM;
+// loading the 32-byte map entry once for 8 frames did not help: 133 us).
+__device__ __forceinline__ unsigned int ug_px(const unsigned int *__restrict__ W, int byte_ofs, int last_word) {
+    const int wi = byte_ofs >> 2;
+    const unsigned int lo = __ldg(W + wi), hi = __ldg(W + (wi + 1 <= last_word ? wi + 1 : last_word));
+    return __funnelshift_r(lo, hi, (byte_ofs & 3) * 8);   // bytes byte_ofs .. byte_ofs + 3
+}
+__device__ __forceinline__ void ug_acc(unsigned int v, int w, int &r, int &g, int &b) {
+    r += w * (int)(v & 0xffu);
+    g += w * (int)((v >> 8) & 0xffu);
+    b += w * (int)((v >> 16) & 0xffu);
+}
+__device__ __forceinline__ float ug_pixel(const uint8_t *__restrict__ src, const int4 ix, const int4 w, int N) {
+    int r = 0, g = 0, b = 0;
+    if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+        const unsigned int *W = reinterpret_cast<const unsigned int *>(src);
+        const int last_word = (3 * N - 1) >> 2;
+        if (ix.y == ix.x + 1 && ix.w == ix.z + 1) {   // two runs of two adjacent pixels: 6 bytes each, three words
+#pragma unroll
+            for (int row = 0; row < 2; row++) {
+                const int ofs = 3 * (row ? ix.z : ix.x), wi = ofs >> 2, sh = (ofs & 3) * 8;
+                const unsigned int w0 = __ldg(W + wi), w1 = __ldg(W + (wi + 1 <= last_word ? wi + 1 : last_word)),
+                                   w2 = __ldg(W + (wi + 2 <= last_word ? wi + 2 : last_word));
+                const unsigned int lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);   // bytes ofs..+3, ofs+4..+7
+                ug_acc(lo, row ? w.z : w.x, r, g, b);
+                ug_acc(__funnelshift_r(lo, hi, 24), row ? w.w : w.y, r, g, b);                            // bytes ofs+3..+6
+            }
+        } else {
+            ug_acc(ug_px(W, 3 * ix.x, last_word), w.x, r, g, b);
+            ug_acc(ug_px(W, 3 * ix.y, last_word), w.y, r, g, b);
+            ug_acc(ug_px(W, 3 * ix.z, last_word), w.z, r, g, b);
+            ug_acc(ug_px(W, 3 * ix.w, last_word), w.w, r, g, b);
+        }
+    } else {   // (a caller's device buffer that is not 4-byte aligned)
+#define TAP(IDX, WW)                         \
+    {                                        \
+        const uint8_t *p = src + 3 * (IDX);  \
+        r += (WW) * (int)p[0];               \
+        g += (WW) * (int)p[1];               \
+        b += (WW) * (int)p[2];               \
+    }
+        TAP(ix.x, w.x)
+        TAP(ix.y, w.y)
+        TAP(ix.z, w.z)
+        TAP(ix.w, w.w)
+#undef TAP
+    }
+    const unsigned int s = (unsigned int)((uint8_t)(r >> 16)) + (unsigned int)((uint8_t)(g >> 16)) + (unsigned int)((uint8_t)(b >> 16));
+    return (float)s;
+}
+// IMGS frames per thread: the 32-byte map entry of a pixel (L2-resident, but 739 MB of L2 reads per 64-frame launch when every
+// frame fetches it again) is loaded once for IMGS frames
+template <int IMGS>
 __global__ void __launch_bounds__(256) k_undistort_gray(const uint8_t *const *__restrict__ src_pp, float *__restrict__ gray,
                                                         const int4 *__restrict__ inx, const int4 *__restrict__ iw, int N,
                                                         int nimg) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int img0 = blockIdx.y * IMGS;
     if (i >= N) return;
-    const int img0 = blockIdx.y * UG_IMGS;
     const int4 ix = inx[i], w = iw[i];
-    const int o0 = 3 * ix.x, o1 = 3 * ix.y, o2 = 3 * ix.z, o3 = 3 * ix.w;
     const uint8_t *src = *src_pp + (size_t)img0 * 3 * N;
-    float *dst = gray + (size_t)img0 * N + i;
-#pragma unroll 4
-    for (int k = 0; k < UG_IMGS; k++) {
-        if (img0 + k >= nimg) break;
-        const uint8_t *p0 = src + o0, *p1 = src + o1, *p2 = src + o2, *p3 = src + o3;
-        const int r = w.x * (int)p0[0] + w.y * (int)p1[0] + w.z * (int)p2[0] + w.w * (int)p3[0];
-        const int g = w.x * (int)p0[1] + w.y * (int)p1[1] + w.z * (int)p2[1] + w.w * (int)p3[1];
-        const int b = w.x * (int)p0[2] + w.y * (int)p1[2] + w.z * (int)p2[2] + w.w * (int)p3[2];
-        const unsigned int sum = (unsigned int)((uint8_t)(r >> 16)) + (unsigned int)((uint8_t)(g >> 16)) + (unsigned int)((uint8_t)(b >> 16));
-        *dst = (float)sum;
-        src += (size_t)3 * N;
-        dst += N;
-    }
+    float v[IMGS];
+#pragma unroll
+    for (int k = 0; k < IMGS; k++) v[k] = img0 + k < nimg ? ug_pixel(src + (size_t)k * 3 * N, ix, w, N) : 0.f;
+#pragma unroll
+    for (int k = 0; k < IMGS; k++)
+        if (img0 + k < nimg) gray[(size_t)(img0 + k) * N + i] = v[k];
 }
 int rb_undistort_gray_enqueue(rb_undistort *u, const void *const *src_pp, float *gray, int nimg) {
     rb_ctx *c = u->c;
-    dim3 grid(rb_div_up(c->N, 256), rb_div_up(nimg, UG_IMGS));
-    k_undistort_gray<<<grid, 256, 0, c->stream>>>((const uint8_t *const *)src_pp, gray, u->inx, u->iw, c->N, nimg);
+    static const int imgs_env = getenv("REBVO_B200_UG_IMGS") ? atoi(getenv("REBVO_B200_UG_IMGS")) : 4;
+    const int imgs = nimg >= 4 ? imgs_env : 1;
+#define UG_LAUNCH(K)                                                                                                       \
+    k_undistort_gray<K><<<dim3(rb_div_up(c->N, 256), rb_div_up(nimg, K)), 256, 0, c->stream>>>((const uint8_t *const *)src_pp, \
+                                                                                           gray, u->inx, u->iw, c->N, nimg)
+    if (imgs >= 8) UG_LAUNCH(8);
+    else if (imgs >= 4) UG_LAUNCH(4);
+    else if (imgs >= 2) UG_LAUNCH(2);
+    else UG_LAUNCH(1);
+#undef UG_LAUNCH
     RB_LAUNCH_CHECK();
     return RB_OK;
 }
