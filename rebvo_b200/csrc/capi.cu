@@ -230,7 +230,13 @@ extern "C" int rb_ctx_create(rb_ctx **out, int device, const rb_camera *cam, dou
     c->sm_count = prop.multiProcessorCount;
     rb_minimizer_cluster_setup(c);
     if ((r = rb_dog_device_setup(c))) return fail(r);
-    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {   // the context's stream carries the latency-critical tracker chain: highest priority, so that its kernels get SM slots
+        // before the queued blocks of the detector / mirror streams (env REBVO_B200_PRIO=0: default priority)
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        const char *pe = getenv("REBVO_B200_PRIO");
+        CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, (pe && atoi(pe) == 0) ? lo : hi));
+    }
     c->nseg = c->h * rb_div_up(c->w, 32);
     CK(cudaMalloc(&c->seg_cnt, sizeof(int) * c->nseg));
     CK(cudaMalloc(&c->cand, sizeof(float4) * (size_t)c->N));

@@ -252,6 +252,7 @@ int rb_dogws_alloc(rb_ctx *c, DogWS *ws, int B);
 void rb_dogws_free(DogWS *ws);
 int rb_dog_gray(rb_ctx *c, DogWS *ws, int nimg, const void *const *src_pp = nullptr);   // rgb -> gray
 int rb_dog_build_batch(rb_ctx *c, DogWS *ws, int nimg);          // gray -> img0, dog
+int rb_dog_build_range(rb_ctx *c, DogWS *ws, int f0, int m);     // the same for the images [f0, f0 + m)
 int rb_dog_aux_planes(rb_ctx *c, DogWS *ws, int img);            // Img(1), dx, dy into ws->aux
 int rb_dog_make_tables(rb_ctx *c);
 int rb_dog_make_tmaps(rb_ctx *c, DogWS *ws);

@@ -1000,29 +1000,34 @@ static int colscan(rb_ctx *c, const float *in, float *out, int nimg) {
     return RB_OK;
 }
 
+// sspace::build for the m images [f0, f0 + m) of the workspace (gray already present): img0 / dog of those slots.  The
+// intermediate planes (S, I0, I) are scratch shared by all ranges: ranges must not run concurrently.
+int rb_dog_build_range(rb_ctx *c, DogWS *ws, int f0, int m) {
+    if (f0 < 0 || m < 1 || f0 + m > ws->B) return RB_ERR_ARG;
+    int r;
+    const size_t N = c->N;
+    // iimage::load(in): identical for both filters -> computed once
+    if ((r = rowscan(c, ws, -1, ws->gray + f0 * N, ws->S, m, m, m))) return r;
+    if ((r = colscan(c, ws->S, ws->I0, m))) return r;
+    // box 0 of both filters reads the shared integral; image index = filter * m + b
+    if ((r = rowscan(c, ws, 0, ws->I0, ws->S, 2 * m, m, m))) return r;
+    if ((r = colscan(c, ws->S, ws->I, 2 * m))) return r;
+    // box 1
+    if ((r = rowscan(c, ws, 1, ws->I, ws->S, 2 * m, 2 * m, m))) return r;
+    if ((r = colscan(c, ws->S, ws->I, 2 * m))) return r;
+    // box 2 + DoG.  Filter f of image b lives at I[(f*m + b)*N]
+    return blur_dog(c, ws, m, nullptr, f0);
+}
+
 // sspace::build for nimg images of the workspace (gray already present)
 int rb_dog_build_batch(rb_ctx *c, DogWS *ws, int nimg) {
     if (nimg < 1 || nimg > ws->B) return RB_ERR_ARG;
     int r;
-    // The batch is processed in sub-batches whose intermediate planes (S, I0, I: 20 N bytes per frame) fit in the
-    // 126 MB L2: what one pass writes is still on chip when the next pass reads it, so only gray in and img0/dog
-    // out stream through HBM.  The scratch planes of the first `sub` slots are reused by every sub-batch.
+    // REBVO_B200_DOG_SUB: sub-batches whose intermediate planes (S, I0, I: 20 N bytes per frame) fit in the 126 MB L2
+    // (measured: no gain, the passes are not capacity-bound); default: the whole batch in one go
     const int sub = c->dog_sub > 0 ? c->dog_sub : nimg;
-    const size_t N = c->N;
-    for (int s = 0; s < nimg; s += sub) {
-        const int m = nimg - s < sub ? nimg - s : sub;
-        // iimage::load(in): identical for both filters -> computed once
-        if ((r = rowscan(c, ws, -1, ws->gray + s * N, ws->S, m, m, m))) return r;
-        if ((r = colscan(c, ws->S, ws->I0, m))) return r;
-        // box 0 of both filters reads the shared integral; image index = filter * m + b
-        if ((r = rowscan(c, ws, 0, ws->I0, ws->S, 2 * m, m, m))) return r;
-        if ((r = colscan(c, ws->S, ws->I, 2 * m))) return r;
-        // box 1
-        if ((r = rowscan(c, ws, 1, ws->I, ws->S, 2 * m, 2 * m, m))) return r;
-        if ((r = colscan(c, ws->S, ws->I, 2 * m))) return r;
-        // box 2 + DoG.  Filter f of image b lives at I[(f*m + b)*N]
-        if ((r = blur_dog(c, ws, m, nullptr, s))) return r;
-    }
+    for (int s = 0; s < nimg; s += sub)
+        if ((r = rb_dog_build_range(c, ws, s, nimg - s < sub ? nimg - s : sub))) return r;
     return RB_OK;
 }
 

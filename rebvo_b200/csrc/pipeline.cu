@@ -53,6 +53,7 @@ struct rb_pipeline {
     cudaStream_t det_stream;
     cudaEvent_t ev_dog, *ev_det, *ev_trk;
     bool overlap;
+    int ss_sub;           // frames per scale-space sub-batch built on the detector stream (env REBVO_B200_SS_SUB, 0 = whole batch)
     bool fm_fused;        // FordwardMatch + rotate_keylines as one cluster kernel (env REBVO_B200_FM_FUSED)
     bool map_fused;       // gate + Regularize_1_iter + EKF inside the map-update cluster kernel (env REBVO_B200_MAP_FUSED)
     // host-input pushes are cut into a short head and the rest: the H2D copy of the rest (copy stream) runs beside the
@@ -244,6 +245,8 @@ extern "C" int rb_pipeline_create(rb_pipeline **out, int device, const rb_params
         pl->fm_fused = ff ? atoi(ff) != 0 : false;
         const char *ov = getenv("REBVO_B200_OVERLAP");
         pl->overlap = !(ov && ov[0] == '0') && !pl->prof_on;
+        pl->ss_sub = getenv("REBVO_B200_SS_SUB") ? atoi(getenv("REBVO_B200_SS_SUB")) : 0;
+        if (pl->ss_sub < 4) pl->ss_sub = 0;   // (a sub-batch must cover the frames the detector runs ahead)
         pl->ev_det = new (std::nothrow) cudaEvent_t[max_batch];
         pl->ev_trk = new (std::nothrow) cudaEvent_t[max_batch];
         if (!pl->ev_det || !pl->ev_trk) return RB_ERR_ARG;
@@ -452,7 +455,13 @@ static int enqueue_batch(rb_pipeline *pl, int n, long long first_frame, bool wit
     if (r) return r;
     prof_mark(pl, ST_GRAY);
     if (with_events) RB_CUDA(cudaEventRecord(pl->ev[1], c->stream));
-    if ((r = rb_dog_build_batch(c, &pl->ws, n))) return r;
+    // The scale space of a batch is a serial prefix of its first frame (0.57 ms per 64 frames = 7 % of the step).  With two
+    // streams only the first ss_sub frames are built here; the detector stream builds the next sub-batch while the
+    // tracker works on this one (it runs up to two frames ahead, more than a sub-batch costs).
+    const int SB = (pl->overlap && pl->ss_sub > 0 && pl->ss_sub < n) ? pl->ss_sub : n;
+    if (SB == n) r = rb_dog_build_batch(c, &pl->ws, n);
+    else r = rb_dog_build_range(c, &pl->ws, 0, SB);
+    if (r) return r;
     prof_mark(pl, ST_DOG);
     if (with_events) RB_CUDA(cudaEventRecord(pl->ev[2], c->stream));
     // Two streams, like the reference's first and second thread: the detector of frame f+1 only needs the scale space
@@ -474,6 +483,13 @@ static int enqueue_batch(rb_pipeline *pl, int n, long long first_frame, bool wit
             c->stream = pl->det_stream;
         }
         RB_TRACE(c->stream, 6);
+        if (SB < n && i % SB == 2 && i - 2 + SB < n) {   // (after the detector has its two frames of lead)
+            const int f0 = i - 2 + SB;
+            if ((r = rb_dog_build_range(c, &pl->ws, f0, n - f0 < SB ? n - f0 : SB))) {
+                c->stream = main_stream;
+                return r;
+            }
+        }
         r = rb_detect_enqueue(c, neu, img0, dog, &p.det, pl->chain);
         prof_mark(pl, ST_DETECT);
         if (!r) r = rb_reestimate_enqueue(c, neu, p.TrackPoints, p.QCutOffNumBins);
