@@ -19,7 +19,8 @@ using namespace TooN;
 struct OutRec {
     double t, Pos[3], PoseLie[3], Pose[9], Vel[3], RotLie[3];
     double dtp0, dtp1, K, Kp, s_rho_p;
-    int kn, matches, est_ok, pad;
+    int kn, matches, est_ok, p_id;
+    double Rot[9], RKp, dt;   // (layout of oracle/ref_driver.cpp's record; Rot / RKp stay zero here)
 };
 
 struct Slot {  // the hot-path members of PipeBuffer (include/rebvo/rebvo.h:312-351)
@@ -92,6 +93,7 @@ int main(int argc, char **argv) {
         memset(&r, 0, sizeof(r));
         r.t = t;
         r.K = K;
+        r.p_id = n;
         if (n == 0) {
             r.kn = pbuf.ef->KNum();
             out.push_back(r);
