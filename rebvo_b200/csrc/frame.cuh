@@ -30,12 +30,13 @@ __device__ __forceinline__ void d_eye(double *M, double v) {
 struct FrameArgs {
     double t, dt;
     unsigned int frame_count;   // global_tracker::FrameCount of the reference ring slot serving this frame
-    int pad;
+    unsigned int next_frame_count;   // ... and of the slot serving the NEXT frame (its loop-body start may be folded into this
+                                     // frame's last kernel, before the next push's arguments exist)
 };
 
 // start of the SecondThread loop body (:167-169) + minimiser priors
-__device__ __forceinline__ void d_frame_pre(FrameState *fs, const FrameArgs *fa, MapState *nst) {
-    nst->frame_count = fa->frame_count;
+__device__ __forceinline__ void d_frame_pre(FrameState *fs, unsigned int frame_count, MapState *nst) {
+    nst->frame_count = frame_count;
     nst->fwd_match = 0;   // counters of FordwardMatch / directed_matching / Regularize_1_iter
     nst->nmatch = 0;
     nst->reg_num = 0;

@@ -53,6 +53,7 @@ struct rb_pipeline {
     cudaStream_t det_stream;
     cudaEvent_t ev_dog, *ev_det, *ev_trk;
     bool overlap;
+    bool q_fold;          // EstimateQuantile + loop-body start of the next frame folded into this frame's map-update kernel
     int ss_sub;           // frames per scale-space sub-batch built on the detector stream (env REBVO_B200_SS_SUB, 0 = whole batch)
     bool fm_fused;        // FordwardMatch + rotate_keylines as one cluster kernel (env REBVO_B200_FM_FUSED)
     bool map_fused;       // gate + Regularize_1_iter + EKF inside the map-update cluster kernel (env REBVO_B200_MAP_FUSED)
@@ -133,7 +134,7 @@ static void set_eye(double *M, double v) {
     M[0] = M[4] = M[8] = v;
 }
 
-__global__ void k_frame_pre(FrameState *fs, const FrameArgs *fa, MapState *nst) { d_frame_pre(fs, fa, nst); }
+__global__ void k_frame_pre(FrameState *fs, const FrameArgs *fa, MapState *nst) { d_frame_pre(fs, fa->frame_count, nst); }
 __global__ void k_frame_post_min(FrameState *fs, const TrackState *ts) { d_frame_post_min(fs, ts->lm); }
 __global__ void k_frame_post_match(FrameState *fs, const MapState *nst, int match_threshold) {
     d_frame_post_match(fs, nst, match_threshold);
@@ -245,6 +246,10 @@ extern "C" int rb_pipeline_create(rb_pipeline **out, int device, const rb_params
         pl->fm_fused = ff ? atoi(ff) != 0 : false;
         const char *ov = getenv("REBVO_B200_OVERLAP");
         pl->overlap = !(ov && ov[0] == '0') && !pl->prof_on;
+        // (off by default: measured 7 480-7 490 frames/s against 7 560 -- the launch it saves was already hidden by programmatic
+        // dependent launch, and it costs the minimiser its early operand staging)
+        pl->q_fold = getenv("REBVO_B200_Q_FOLD") && atoi(getenv("REBVO_B200_Q_FOLD")) != 0 && p->QCutOffNumBins >= 1 &&
+                     p->QCutOffNumBins <= 128;
         pl->ss_sub = getenv("REBVO_B200_SS_SUB") ? atoi(getenv("REBVO_B200_SS_SUB")) : 0;
         if (pl->ss_sub < 4) pl->ss_sub = 0;   // (a sub-batch must cover the frames the detector runs ahead)
         pl->ev_det = new (std::nothrow) cudaEvent_t[max_batch];
@@ -375,15 +380,17 @@ extern "C" int rb_pipeline_reset(rb_pipeline *pl) {
 }
 
 // one frame of the tracker/mapper stage: new = maps[f % RB_NMAPS] (already detected), old = the map of frame f-1
-static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, const FrameArgs *fa, rb_nav *nav_slot) {
+static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, rb_map *next, const FrameArgs *fa, rb_nav *nav_slot) {
     rb_ctx *c = pl->c;
     const rb_params &p = pl->p;
     int r;
     RB_TRACE(c->stream, 1);
     // :167-169 loop-body start (folded into the quantile kernel) ; :172  s_rho_q = old_buf.ef->EstimateQuantile(...)
-    if ((r = rb_quantile_enqueue(c, old, RB_RHO_MIN, RB_RHO_MAX, p.QCutOffQuantile, p.QCutOffNumBins, pl->fs, fa,
-                                 neu->st)))
-        return r;
+    // (q_fold: both were done by the previous frame's map-update kernel, or after k_frame_first for frame 1)
+    if (!pl->q_fold)
+        if ((r = rb_quantile_enqueue(c, old, RB_RHO_MIN, RB_RHO_MAX, p.QCutOffQuantile, p.QCutOffNumBins, pl->fs,
+                                     &fa->frame_count, neu->st)))
+            return r;
     // :177  new_buf.gt->build_field(...) only needs the new edge map: enqueue_batch runs it on the detector stream
     if (!pl->overlap)
         if ((r = rb_build_field_enqueue(c, neu, p.SearchRange, 0.f, true))) return r;
@@ -401,7 +408,8 @@ static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, const FrameArg
     bool folded = false;
     // (since the old map's update only EstimateQuantile -- and build_field of the NEW map without the second stream -- ran
     // on this stream: the minimiser may stage the old map's operands while that kernel is still running)
-    c->min_early = getenv("REBVO_B200_MIN_EARLY") ? atoi(getenv("REBVO_B200_MIN_EARLY")) != 0 : true;
+    // (with q_fold the previous kernel is the old map's update itself: no early staging)
+    c->min_early = !pl->q_fold && (getenv("REBVO_B200_MIN_EARLY") ? atoi(getenv("REBVO_B200_MIN_EARLY")) != 0 : true);
     r = rb_minimizer_enqueue(c, neu, old, pl->fs->VW, &a, 0.0, true, 0, true, pl->fs, &folded);
     c->min_early = false;
     if (r) return r;
@@ -434,9 +442,10 @@ static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, const FrameArg
             return r;
     RB_TRACE(c->stream, 9);
     prof_mark(pl, ST_REG_EKF);
+    rb_quantile_fold qf = {pl->q_fold ? p.QCutOffNumBins : 0, RB_RHO_MIN, RB_RHO_MAX, p.QCutOffQuantile, next->st};
     if ((r = rb_map_update_enqueue(c, neu, p.RegularizeThresh, pl->fs->V, p.ReshapeQAbsolute, p.LocationUncertainty,
                                    RB_RHO_MAX, 1, p.DoReScaling > 0 ? 1 : 0, pl->fs, p.MatchThreshold, old->st,
-                                   nav_slot, fa, pl->map_fused)))
+                                   nav_slot, fa, pl->map_fused, &qf)))
         return r;
     prof_mark(pl, ST_RESCALE);   // rescaling + pose integration / nav record (folded)
     RB_TRACE(c->stream, 5);
@@ -508,8 +517,12 @@ static int enqueue_batch(rb_pipeline *pl, int n, long long first_frame, bool wit
         if (fr == 0) {
             k_frame_first<<<1, 1, 0, c->stream>>>(pl->fs, neu->st, pl->nav_dev + i, pl->fa_dev + i);
             RB_LAUNCH_CHECK();
+            if (pl->q_fold)   // what frame 1 starts with: EstimateQuantile of this map + its loop-body start
+                if ((r = rb_quantile_enqueue(c, neu, RB_RHO_MIN, RB_RHO_MAX, p.QCutOffQuantile, p.QCutOffNumBins, pl->fs,
+                                             &(pl->fa_dev + i)->next_frame_count, pl->maps[(fr + 1) % RB_NMAPS]->st)))
+                    return r;
         } else {
-            if ((r = track_frame(pl, neu, old, pl->fa_dev + i, pl->nav_dev + i))) return r;
+            if ((r = track_frame(pl, neu, old, pl->maps[(fr + 1) % RB_NMAPS], pl->fa_dev + i, pl->nav_dev + i))) return r;
         }
         if (pl->mirror_on) {   // the frame's edge map as the reference's records, before the next frame touches it
             const size_t ofs = (size_t)i * pl->mirror_stride;
@@ -554,7 +567,7 @@ static int push_impl(rb_pipeline *pl, const uint8_t *rgb, bool on_device, const 
         pl->fa_pin[i].t = ts[i];
         pl->fa_pin[i].dt = dt;
         pl->fa_pin[i].frame_count = fr > 0 ? (unsigned int)((fr - 1) / 8) : 0;
-        pl->fa_pin[i].pad = 0;
+        pl->fa_pin[i].next_frame_count = (unsigned int)(fr / 8);   // frame fr+1: ((fr+1)-1)/8
     }
     pl->pn = 0;
     prof_mark(pl, ST_NAV);   // origin of this push

@@ -99,11 +99,11 @@ void rb_track_state_free(rb_map *m) {
 __global__ void __launch_bounds__(256) k_quantile(const double *__restrict__ s_rho, MapState *st,
                                                   int *__restrict__ histo, unsigned int *ticket, double smin,
                                                   double smax, double perc, int n, FrameState *fs,
-                                                  const FrameArgs *fa, MapState *nst) {
+                                                  const unsigned int *frame_count, MapState *nst) {
     pdl_wait();
     pdl_launch();
     extern __shared__ int sh[];
-    if (fs && blockIdx.x == 0 && threadIdx.x == 0) d_frame_pre(fs, fa, nst);   // folded one-thread stage
+    if (fs && blockIdx.x == 0 && threadIdx.x == 0) d_frame_pre(fs, *frame_count, nst);   // folded one-thread stage
     const int kn = st->kn;
     for (int i = threadIdx.x; i < n; i += blockDim.x) sh[i] = 0;
     __syncthreads();
@@ -143,11 +143,11 @@ __global__ void __launch_bounds__(256) k_quantile(const double *__restrict__ s_r
 }
 
 int rb_quantile_enqueue(rb_ctx *c, rb_map *m, double smin, double smax, double perc, int nbins, FrameState *fs,
-                        const FrameArgs *fa, MapState *nst) {
+                        const unsigned int *frame_count_dev, MapState *nst) {
     if (nbins < 1 || nbins > 4096) return RB_ERR_ARG;
     int *histo = (int *)((char *)c->dev_small + RB_DS_QHISTO);  // zeroed at creation and by the kernel's tail
     RB_KLAUNCH(k_quantile, 64, 256, sizeof(int) * nbins, m->kl.s_rho, m->st, histo, c->ticket + 2, smin, smax, perc,
-               nbins, fs, fa, nst);
+               nbins, fs, frame_count_dev, nst);
     return RB_OK;
 }
 
@@ -1751,6 +1751,7 @@ int rb_regularize_ekf_enqueue(rb_ctx *c, rb_map *m, double thresh, FrameState *f
 namespace cg = cooperative_groups;
 #define MU_T 512
 #define MU_C 16   // (non-portable cluster size, like the minimiser's)
+#define MU_QBINS 128   // largest QCutOffNumBins the folded EstimateQuantile takes
 #define MU_KJ 2   // keylines per thread whose rescaling operands stay in registers (kn <= MU_KJ*MU_C*MU_T = 16384)
 
 struct MapUpdArgs {
@@ -1767,6 +1768,11 @@ struct MapUpdArgs {
     const LMState *lm;
     rb_nav *nav;
     const FrameArgs *fa;
+    // EstimateQuantile of THIS map (what the next frame's loop body starts with, rebvo_second_t.cpp:172) and that loop-body
+    // start, folded into the tail: q_bins > 0 enables it
+    int q_bins;
+    double q_min, q_max, q_perc;
+    MapState *nst_next;
 };
 
 __device__ __forceinline__ void mu_block_sum2(double &a, double &b, double (*sw)[2], int tid) {
@@ -1802,8 +1808,12 @@ __global__ void __cluster_dims__(MU_C, 1, 1) __launch_bounds__(MU_T) k_map_updat
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ double sw[MU_T / 32][2];
     __shared__ double slots[2][MU_C][2];   // [iteration parity][rank][sum]
+    __shared__ int qh[MU_QBINS];           // EstimateQuantile histogram of this CTA's keylines (rank 0, later: the cluster's)
+    __shared__ int qtab[MU_C][MU_QBINS];   // rank 0: every CTA's histogram (plain DSMEM stores: no initialisation to order)
     const int tid = threadIdx.x, rank = (int)cluster.block_rank();
     const int kn = st->kn;
+    if (a.q_bins > 0)
+        for (int b = tid; b < a.q_bins; b += MU_T) qh[b] = 0;   // (complete before anybody adds: cluster barriers below)
     bool en;
     if (a.fs && a.gate_post_match) {   // "after directed_matching" gate (rebvo_second_t.cpp:410-423) folded in
         en = a.fs->do_match && st->nmatch >= a.match_threshold;
@@ -1909,8 +1919,45 @@ __global__ void __cluster_dims__(MU_C, 1, 1) __launch_bounds__(MU_T) k_map_updat
             }
         }
     }
+    if (a.q_bins > 0) {   // EstimateQuantile (edge_finder.cpp: histogram of s_rho over all keylines) on the final s_rho of this map
+        __syncthreads();   // (qh zeroed; this thread's own s_rho writes are visible to it)
+        const double range = a.q_max - a.q_min;
+        for (int i = i0; i < kn; i += stride) {
+            int b = (int)((double)a.q_bins * (kl.s_rho[i] - a.q_min) / range);
+            b = b > a.q_bins - 1 ? a.q_bins - 1 : b;
+            b = b < 0 ? 0 : b;
+            atomicAdd(&qh[b], 1);
+        }
+        __syncthreads();
+        int *t0 = cluster.map_shared_rank(&qtab[rank][0], 0);
+        for (int b = tid; b < a.q_bins; b += MU_T) t0[b] = qh[b];
+    }
     cluster.sync();   // no CTA may exit while a peer can still store into its shared memory
-    if (a.fs && a.nav && rank == 0 && tid == 0) d_frame_finish(a.fs, st, a.ost, a.lm->score, a.nav, a.fa);
+    if (rank == 0 && a.q_bins > 0) {
+        for (int b = tid; b < a.q_bins; b += MU_T) {
+            int t = 0;
+#pragma unroll
+            for (int r = 0; r < MU_C; r++) t += qtab[r][b];
+            qh[b] = t;
+        }
+        __syncthreads();
+    }
+    if (rank == 0 && tid == 0) {
+        if (a.fs && a.nav) d_frame_finish(a.fs, st, a.ost, a.lm->score, a.nav, a.fa);
+        if (a.q_bins > 0) {
+            const double range = a.q_max - a.q_min;
+            double q = 1e3;
+            for (int i = 0, acc = 0; i < a.q_bins; i++) {
+                if ((double)acc > a.q_perc * (double)kn) {
+                    q = (double)i * range / (double)a.q_bins + a.q_min;
+                    break;
+                }
+                acc += qh[i];
+            }
+            st->s_rho_q = q;
+            if (a.fs && a.nst_next) d_frame_pre(a.fs, a.fa->next_frame_count, a.nst_next);   // loop-body start of the next frame
+        }
+    }
 }
 
 static int launch_map_update(rb_ctx *c, rb_map *m, const MapUpdArgs &a) {
@@ -1932,7 +1979,8 @@ static int launch_map_update(rb_ctx *c, rb_map *m, const MapUpdArgs &a) {
 // the pipeline's whole map update (gate, smoothing, EKF, rescaling, pose integration / nav record)
 int rb_map_update_enqueue(rb_ctx *c, rb_map *m, double reg_thresh, const double *vel_dev, double q_abs, double loc_unc,
                           double s_rho_min, unsigned int match_num_min, int re_escale, FrameState *fs,
-                          int match_threshold, const MapState *ost, rb_nav *nav, const FrameArgs *fa, bool fused) {
+                          int match_threshold, const MapState *ost, rb_nav *nav, const FrameArgs *fa, bool fused,
+                          const rb_quantile_fold *qf) {
     MapUpdArgs a;
     memset(&a, 0, sizeof(a));
     // fused: the match-count gate, Regularize_1_iter and the EKF run inside this cluster kernel too (one launch instead of
@@ -1955,6 +2003,13 @@ int rb_map_update_enqueue(rb_ctx *c, rb_map *m, double reg_thresh, const double 
     a.lm = &m->ts->lm;
     a.nav = nav;
     a.fa = fa;
+    if (qf && qf->nbins > 0 && qf->nbins <= MU_QBINS) {
+        a.q_bins = qf->nbins;
+        a.q_min = qf->smin;
+        a.q_max = qf->smax;
+        a.q_perc = qf->perc;
+        a.nst_next = qf->nst_next;
+    }
     return launch_map_update(c, m, a);
 }
 

@@ -118,6 +118,23 @@ def test_graph_replay_equals_eager_launches(built, stream, monkeypatch):
         assert np.array_equal(a[f], b[f]), f
 
 
+@pytest.mark.parametrize("env", [{"REBVO_B200_Q_FOLD": "1"}, {"REBVO_B200_SS_SUB": "16"}, {"REBVO_B200_MIN_EARLY": "0"},
+                                 {"REBVO_B200_PRIO": "0"}])
+def test_schedule_variants_do_not_change_the_result(built, stream, monkeypatch, env):
+    """Switches that only move work between kernels / streams (EstimateQuantile folded into the previous frame's map update,
+    scale space in sub-batches on the detector stream, operand staging after the PDL wait, stream priorities): same
+    arithmetic in the same order, hence the same bits -- also across a batch boundary and a graph replay."""
+    a, _ = _gpu_run(stream, 20)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    b, lb = _gpu_run(stream, 20)
+    for f in ("Pos", "Pose", "kn", "matches", "Kp", "score", "s_rho_p"):
+        assert np.array_equal(a[f], b[f]), (env, f)
+    monkeypatch.setenv("REBVO_B200_NO_GRAPH", "1")
+    c, lc = _gpu_run(stream, 7)   # other batch size, eager
+    assert np.array_equal(a["Pos"], c["Pos"]) and np.array_equal(a["s_rho_p"], c["s_rho_p"])
+
+
 def test_fallback_paths_agree(built, stream, monkeypatch):
     """The switches in DESIGN.md section 5 select the slower formulations of the same stages (one launch per TryVelRot
     evaluation, detector on the tracker stream, plain stream order): same keylines and matches, poses equal to the
