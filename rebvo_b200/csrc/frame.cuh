@@ -17,7 +17,8 @@ struct FrameState {
     int do_match, do_map, est_ok;
     int klm_num;
     int n_frame;
-    int pad;
+    int pose_done;      // d_frame_pose already integrated this frame's pose (cleared by d_frame_finish)
+    double RotLie[3], PoseLie[3];   // its logarithms for the nav record
 };
 
 __device__ __forceinline__ void d_eye(double *M, double v) {
@@ -112,13 +113,10 @@ __device__ __forceinline__ void d_frame_post_match(FrameState *fs, const MapStat
 }
 
 // pose integration + NavData (:545-585)
-__device__ __forceinline__ void d_frame_finish(FrameState *fs, const MapState *nst, const MapState *ost,
-                                               double lm_score, rb_nav *nav, const FrameArgs *fa) {
-    const double t = fa->t, dt_frame = fa->dt;
-    if (fs->do_map) {
-        fs->Kp = nst->Kp;      // Kp=EstimateReScalingOpt(P_Kp,...)
-        fs->P_Kp = nst->RKp;
-    }
+// pose integration of the frame (:545-551: Pose=Pose*R, Pos+=-Pose*V*K) and the two matrix logarithms of the nav record: the
+// serial part of d_frame_finish that needs nothing of the map update.  The pipeline runs it in a spare thread of the
+// regularise / EKF kernel (after the match-count gate has fixed V), so that the map-update kernel's one-thread tail is short.
+__device__ __forceinline__ void d_frame_pose(FrameState *fs) {
     const double K = fs->K;
     double Pose[9];
     mat3_mul(fs->Pose, fs->R, Pose);          // Pose=Pose*R
@@ -127,6 +125,21 @@ __device__ __forceinline__ void d_frame_finish(FrameState *fs, const MapState *n
     for (int i = 0; i < 9; i++) nP[i] = -Pose[i];
     mat3_vec(nP, fs->V, pv);                  // Pos+=-Pose*V*K
     for (int i = 0; i < 3; i++) fs->Pos[i] = fs->Pos[i] + pv[i] * K;
+    so3_ln_of_matrix(fs->R, fs->RotLie);
+    so3_ln_of_matrix(fs->Pose, fs->PoseLie);
+    fs->pose_done = 1;
+}
+
+__device__ __forceinline__ void d_frame_finish(FrameState *fs, const MapState *nst, const MapState *ost,
+                                               double lm_score, rb_nav *nav, const FrameArgs *fa) {
+    const double t = fa->t, dt_frame = fa->dt;
+    if (fs->do_map) {
+        fs->Kp = nst->Kp;      // Kp=EstimateReScalingOpt(P_Kp,...)
+        fs->P_Kp = nst->RKp;
+    }
+    const double K = fs->K;
+    if (!fs->pose_done) d_frame_pose(fs);
+    fs->pose_done = 0;
     rb_nav o;
     o.t = t;
     o.dt = dt_frame;
@@ -134,9 +147,9 @@ __device__ __forceinline__ void d_frame_finish(FrameState *fs, const MapState *n
         o.Rot[i] = fs->R[i];
         o.Pose[i] = fs->Pose[i];
     }
-    so3_ln_of_matrix(fs->R, o.RotLie);
-    so3_ln_of_matrix(fs->Pose, o.PoseLie);
     for (int i = 0; i < 3; i++) {
+        o.RotLie[i] = fs->RotLie[i];
+        o.PoseLie[i] = fs->PoseLie[i];
         o.Vel[i] = (-fs->V[i]) * K / dt_frame;
         o.Pos[i] = fs->Pos[i];
         o.V[i] = fs->V[i];

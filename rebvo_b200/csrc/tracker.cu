@@ -1702,9 +1702,12 @@ __global__ void __launch_bounds__(256) k_regb_ekf(KLSoA kl, const MapState *st, 
                                                   const double *__restrict__ s,
                                                   const unsigned char *__restrict__ set,
                                                   const double *__restrict__ velp, double zf, double q_abs,
-                                                  double loc_unc, const int *enable) {
+                                                  double loc_unc, const int *enable, FrameState *pose_fs) {
     pdl_wait();
     pdl_launch();
+    // the frame's pose integration + matrix logarithms (one thread, ~2.5 us) beside the EKF instead of in the map-update
+    // kernel's tail: V and R are final since the gate of the previous kernel.  The last block of the grid has no keylines.
+    if (pose_fs && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) d_frame_pose(pose_fs);
     if (enable && !*enable) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= st->kn) return;
@@ -1727,7 +1730,7 @@ int rb_regularize_ekf_enqueue(rb_ctx *c, rb_map *m, double thresh, FrameState *f
     const int nb = rb_div_up(c->kcap, 256);
     RB_KLAUNCH(k_regularize_a_gate, nb, 256, 0, m->kl, m->st, t.reg_r, t.reg_s, t.reg_set, thresh, fs, match_threshold);
     RB_KLAUNCH(k_regb_ekf, nb, 256, 0, m->kl, (const MapState *)m->st, (const double *)t.reg_r, (const double *)t.reg_s,
-               (const unsigned char *)t.reg_set, vel_dev, c->zfm, q_abs, loc_unc, do_map_dev);
+               (const unsigned char *)t.reg_set, vel_dev, c->zfm, q_abs, loc_unc, do_map_dev, fs);
     return RB_OK;
 }
 
