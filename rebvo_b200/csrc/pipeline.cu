@@ -410,12 +410,16 @@ static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, rb_map *next, 
     // on this stream: the minimiser may stage the old map's operands while that kernel is still running)
     // (with q_fold the previous kernel is the old map's update itself: no early staging)
     c->min_early = !pl->q_fold && (getenv("REBVO_B200_MIN_EARLY") ? atoi(getenv("REBVO_B200_MIN_EARLY")) != 0 : true);
-    r = rb_minimizer_enqueue(c, neu, old, pl->fs->VW, &a, 0.0, true, 0, true, pl->fs, &folded);
+    // the one-thread stage after the minimiser rides in a spare thread of the first FordwardMatch kernel (post_in_fm) rather
+    // than in the minimiser's tail; with the fused FordwardMatch + rotate kernel it stays in the minimiser
+    static const bool post_fm_env = getenv("REBVO_B200_POST_IN_FM") ? atoi(getenv("REBVO_B200_POST_IN_FM")) != 0 : true;
+    const bool post_in_fm = post_fm_env && !(pl->fm_fused && pl->overlap);
+    r = rb_minimizer_enqueue(c, neu, old, pl->fs->VW, &a, 0.0, true, 0, true, post_in_fm ? nullptr : pl->fs, &folded);
     c->min_early = false;
     if (r) return r;
     RB_TRACE(c->stream, 3);
     prof_mark(pl, ST_MINIM);
-    if (!folded) {
+    if (!folded && !post_in_fm) {
         k_frame_post_min<<<1, 1, 0, c->stream>>>(pl->fs, neu->ts);
         RB_LAUNCH_CHECK();
     }
@@ -423,7 +427,7 @@ static int track_frame(rb_pipeline *pl, rb_map *neu, rb_map *old, rb_map *next, 
     if (pl->fm_fused && pl->overlap) {   // (the arg-max scratch of the new map was cleared on the detector stream)
         if ((r = rb_forward_match_rotate_enqueue(c, old, neu, pl->fs->R0))) return r;
     } else {
-        if ((r = rb_forward_match_enqueue(c, old, neu, pl->overlap))) return r;
+        if ((r = rb_forward_match_enqueue(c, old, neu, pl->overlap, pl->fs))) return r;
         if ((r = rb_rotate_enqueue(c, old, pl->fs->R0))) return r;
     }
     RB_TRACE(c->stream, 11);

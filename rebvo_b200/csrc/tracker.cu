@@ -128,7 +128,36 @@ __global__ void __launch_bounds__(256) k_quantile(const double *__restrict__ s_r
         histo[i] = 0;   // leave the scratch histogram zeroed for the next call
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    // "for i: if (a > perc * kn) {q = bin i; break;} a += histo[i]" = the first bin whose exclusive prefix sum exceeds the
+    // threshold: one warp, 4 bins per lane, shuffle scan (the serial loop cost ~1 us at the end of every frame's first kernel)
+    if (threadIdx.x < 32 && n <= 128) {
+        const int lane = threadIdx.x;
+        int b[4], tot = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            b[k] = 4 * lane + k < n ? sh[4 * lane + k] : 0;
+            tot += b[k];
+        }
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int a = incl - tot, hit = -1;   // exclusive prefix of this lane's first bin
+        const double thr = perc * (double)kn;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (hit < 0 && 4 * lane + k < n && (double)a > thr) hit = 4 * lane + k;
+            a += b[k];
+        }
+        const unsigned int m = __ballot_sync(0xffffffffu, hit >= 0);
+        const int first = m ? __shfl_sync(0xffffffffu, hit, __ffs(m) - 1) : -1;
+        if (lane == 0) {
+            st->s_rho_q = first >= 0 ? (double)first * range / (double)n + smin : 1e3;
+            *ticket = 0;
+        }
+    } else if (threadIdx.x == 0 && n > 128) {
         double q = 1e3;
         for (int i = 0, a = 0; i < n; i++) {
             if ((double)a > perc * (double)kn) {
@@ -1300,9 +1329,12 @@ __device__ __forceinline__ bool d_fm_apply(const KLSoA &old, const KLSoA &neu, i
     return true;
 }
 __global__ void __launch_bounds__(256) k_fm_pass1(KLSoA old, const MapState *ost, const MapState *nst,
-                                                  unsigned long long *best) {
+                                                  unsigned long long *best, FrameState *post_fs, const TrackState *ts) {
     pdl_wait();
     pdl_launch();
+    // the pipeline's one-thread stage after Minimizer_RV (outputs, R0 = exp(W), NaN guard, directed-matching arguments: nothing
+    // FordwardMatch reads) in a spare thread here instead of in the minimiser's tail: the last block has no keylines
+    if (post_fs && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) d_frame_post_min(post_fs, ts->lm);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ost->kn) return;
     d_fm_pass1(old, i, nst->kn, best);
@@ -1331,7 +1363,7 @@ int rb_forward_match_init_enqueue(rb_ctx *c, rb_map *neu) {
     RB_LAUNCH_CHECK();
     return RB_OK;
 }
-int rb_forward_match_enqueue(rb_ctx *c, rb_map *old, rb_map *neu, bool scratch_ready) {
+int rb_forward_match_enqueue(rb_ctx *c, rb_map *old, rb_map *neu, bool scratch_ready, FrameState *post_fs) {
     const int nb = rb_div_up(c->kcap, 256);
     TrackState &t = neu->ts_host;
     if (!c->counters_preset) {   // the per-frame pipeline zeroes the counters in k_frame_pre
@@ -1342,7 +1374,8 @@ int rb_forward_match_enqueue(rb_ctx *c, rb_map *old, rb_map *neu, bool scratch_r
         int r = rb_forward_match_init_enqueue(c, neu);
         if (r) return r;
     }
-    RB_KLAUNCH(k_fm_pass1, nb, 256, 0, old->kl, (const MapState *)old->st, (const MapState *)neu->st, t.fm_best);
+    RB_KLAUNCH(k_fm_pass1, nb, 256, 0, old->kl, (const MapState *)old->st, (const MapState *)neu->st, t.fm_best, post_fs,
+               (const TrackState *)neu->ts);
     RB_KLAUNCH(k_fm_pass2, nb, 256, 0, old->kl, (const MapState *)old->st, (const MapState *)neu->st,
                (const unsigned long long *)t.fm_best, t.fm_idx);
     RB_KLAUNCH(k_fm_apply, nb, 256, 0, old->kl, neu->kl, neu->st, (const int *)t.fm_idx);

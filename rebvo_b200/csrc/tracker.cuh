@@ -54,7 +54,7 @@ struct rb_quantile_fold {
 };
 int rb_build_field_enqueue(rb_ctx *c, rb_map *m, int radius, float min_mod, bool min_mod_from_state);
 int rb_forward_match_init_enqueue(rb_ctx *c, rb_map *neu);
-int rb_forward_match_enqueue(rb_ctx *c, rb_map *old, rb_map *neu, bool scratch_ready = false);
+int rb_forward_match_enqueue(rb_ctx *c, rb_map *old, rb_map *neu, bool scratch_ready = false, FrameState *post_fs = nullptr);
 int rb_rotate_enqueue(rb_ctx *c, rb_map *m, const double *R_dev);
 int rb_forward_match_rotate_enqueue(rb_ctx *c, rb_map *old, rb_map *neu, const double *R_dev);   // scratch cleared before
 struct DMatchArgs {       // device-resident arguments of directed_matching (after the back-rotation)
