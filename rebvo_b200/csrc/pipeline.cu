@@ -580,11 +580,26 @@ static int push_impl(rb_pipeline *pl, const uint8_t *rgb, bool on_device, const 
     // frames) and the rest: only the head's H2D copy is exposed, the rest of the frames are copied on the copy stream into
     // their own staging region while the head computes (a frame costs ~8x more to track than to copy), and the scale
     // space of the rest still runs as one large batch.
-    const int head = (on_device || pl->prof_on || n < 3 * pl->sub) ? n : pl->sub;
-    const int nsub = head < n ? 2 : 1;
+    // (REBVO_B200_SUB3=1: three stages -- sub/2, 3*sub/2, the rest -- expose half the copy, but the extra launch and the small
+    // scale-space batches cost more: e2e 6 990 against 7 150 frames/s)
+    static const bool three = getenv("REBVO_B200_SUB3") && atoi(getenv("REBVO_B200_SUB3")) != 0;
+    int soff[4] = {0, n, n, n}, nsub = 1;
+    if (!(on_device || pl->prof_on || n < 3 * pl->sub)) {
+        if (three && pl->sub >= 4) {
+            const int s0 = pl->sub / 2;
+            soff[1] = s0;
+            soff[2] = 4 * s0;
+            soff[3] = n;
+            nsub = 3;
+        } else {
+            soff[1] = pl->sub;
+            soff[2] = n;
+            nsub = 2;
+        }
+    }
     const size_t fbytes = (size_t)3 * c->N;
     for (int j = 0; j < nsub; j++) {
-        const int off = j == 0 ? 0 : head, nj = j == 0 ? head : n - head;
+        const int off = soff[j], nj = soff[j + 1] - soff[j];
         if (on_device) {
             pl->rgb_src_pin[j] = rgb;
         } else {
@@ -596,7 +611,7 @@ static int push_impl(rb_pipeline *pl, const uint8_t *rgb, bool on_device, const 
         }
     }
     for (int j = 0; j < nsub; j++) {
-        const int off = j == 0 ? 0 : head, nj = j == 0 ? head : n - head;
+        const int off = soff[j], nj = soff[j + 1] - soff[j];
         const long long first_j = first + (long long)off;
         if (!on_device && nsub > 1) RB_CUDA(cudaStreamWaitEvent(c->stream, pl->ev_copy[j], 0));
         RB_CUDA(cudaMemcpyAsync(pl->fa_dev, pl->fa_pin + off, sizeof(FrameArgs) * nj, cudaMemcpyHostToDevice, c->stream));
@@ -731,7 +746,7 @@ extern "C" int rb_pipeline_set_mirror(rb_pipeline *pl, int on) {
         RB_CUDA(cudaMalloc(&pl->mirror_dev, bytes));
         RB_CUDA(cudaHostAlloc(&pl->mirror_host, bytes, cudaHostAllocMapped));
         RB_CUDA(cudaMalloc(&pl->mirror_base_dev, 2 * sizeof(void *)));
-        RB_CUDA(cudaMallocHost(&pl->mirror_base_pin, 4 * sizeof(void *)));
+        RB_CUDA(cudaMallocHost(&pl->mirror_base_pin, 8 * sizeof(void *)));
         RB_CUDA(cudaStreamCreateWithFlags(&pl->mirror_stream, cudaStreamNonBlocking));
         pl->ev_mpack = new (std::nothrow) cudaEvent_t[pl->max_batch];
         if (!pl->ev_mpack) return RB_ERR_ARG;

@@ -1,0 +1,11 @@
+#!/bin/bash
+cd $GRAFT_REPO_ROOT && mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_gpu_pipeline.py -x -q 2>&1 | tail -3
+for q in 1 0 1 0; do
+REBVO_B200_SUB3=$q timeout 600 python bench.py --no-cpu-baseline --steps 8 > gpurun_out/bench_q.json 2>gpurun_out/bench_q.err; tail -c 300 gpurun_out/bench_q.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/bench_q.json').read().strip().splitlines()[-1])
+print('SUB3=$q value %.0f e2e %.0f mirror %.0f'%(d['value'], d['e2e']['value'], d['e2e_with_mirror']['keyline_168B']['value']))
+PY
+done
