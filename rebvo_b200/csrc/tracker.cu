@@ -1473,6 +1473,7 @@ int rb_rotate_enqueue(rb_ctx *c, rb_map *m, const double *R_dev) {
 // =====================================================================================================
 // directed_matching + search_match (edge_tracker.cpp:158-374)
 // =====================================================================================================
+#define DM_G 4   // lanes per keyline of the directed search (must divide 32, even)
 __global__ void __launch_bounds__(128) k_directed_match(KLSoA neu, MapState *nst, KLSoA old,
                                                         const int *__restrict__ omask, const DMatchArgs *__restrict__ ap,
                                                         CamC cam, double min_thr_mod, double cang_min_edge,
@@ -1480,15 +1481,25 @@ __global__ void __launch_bounds__(128) k_directed_match(KLSoA neu, MapState *nst
     pdl_wait();
     pdl_launch();
     if (enable && !*enable) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // DM_G lanes per keyline: the search along the epipolar segment probes up to 2 * t_steps pixels in a fixed order
+    // (t_i = 0, 1, ...; for each the near side, then the far side) and stops at the first accepted candidate.  Unmatched
+    // keylines walk the whole segment, a chain of ~80 dependent lookups; here probe number s = 2 t_i + dir belongs to lane
+    // s mod DM_G of the keyline's group, the lanes advance in lock step (DM_G probes per iteration) and the lowest lane with
+    // a hit in an iteration is the first hit of the sequential order.  tp / tn are still built by repeated +-1 (each lane
+    // takes DM_G / 2 steps per iteration), so every probe sees the same bits as the reference's.
+    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gi / DM_G, g = gi % DM_G, lane = threadIdx.x & 31;
     bool got = false;
-    if (i < nst->kn) {
+    int jm = -1;
+    {
+        const bool valid = i < nst->kn;
+        const int ic = valid ? i : 0;   // (lanes without a keyline run on keyline 0 and never probe)
         const double zf = cam.zfm;
         const double *BR = ap->BackRot, *Vel = ap->Vel, *RV = ap->RVel;
-        const float2 kpm = neu.p_m[i];
-        const double krho = neu.rho[i], ks_rho = neu.s_rho[i];
-        const float2 km = neu.m_m[i];
-        const float kn_m = neu.n_m[i];
+        const float2 kpm = neu.p_m[ic];
+        const double krho = neu.rho[ic], ks_rho = neu.s_rho[ic];
+        const float2 km = neu.m_m[ic];
+        const float kn_m = neu.n_m[ic];
         // p_m3 = BackRot*(p_m.x, p_m.y, zfm)
         const double a0 = (double)kpm.x, a1 = (double)kpm.y, a2 = zf;
         double p30 = 0, p31 = 0, p32 = 0;
@@ -1536,35 +1547,54 @@ __global__ void __launch_bounds__(128) k_directed_match(KLSoA neu, MapState *nst
         }
         const double norm_m = (double)kn_m;
         double tn = dq_rho, tp = dq_rho + 1;
-        int jm = -1;
-        for (int t_i = 0; t_i < t_steps && jm < 0; t_i++, tp += 1, tn -= 1) {
-#pragma unroll
-            for (int dir = 0; dir < 2; dir++) {
-                double t;
-                if (dir) {
-                    t = tp;
-                    if (t > dq_max) continue;
-                } else {
-                    t = tn;
-                    if (t < dq_min) continue;
-                }
-                const float fx = (float)(t_x * t + (double)pi0x), fy = (float)(t_y * t + (double)pi0y);
-                const int xi = (int)roundf(fx), yi = (int)roundf(fy);       // GetIndexRC
-                if (xi >= cam.w || yi >= cam.h || xi < 0 || yi < 0) continue;
-                const int j = omask[(size_t)yi * cam.w + xi];
-                if (j < 0) continue;
-                const double norm_m0 = (double)old.n_m[j];
-                const float2 om = old.m_m[j];
-                const double cang = (double)(om.x * km.x + om.y * km.y) / (norm_m0 * norm_m);
-                if (cang < cang_min_edge || fabs(norm_m0 / norm_m - 1) > min_thr_mod) continue;
-                const double s_rho = old.s_rho[j], rho = old.rho[j];
-                const double v_rho_dr = (loc_unc * loc_unc + s_rho * s_rho * norm_t * norm_t + sigma2_t * rho * rho);
-                const double e = t - norm_t * rho;
-                if (e * e > v_rho_dr) continue;
-                jm = j;
-                break;
-            }
+        int t_i = g >> 1;
+        const int dir = g & 1;
+        for (int k = 0; k < (g >> 1); k++) {   // this lane's first probe
+            tp += 1;
+            tn -= 1;
         }
+        bool active = valid;
+        while (true) {
+            int j_hit = -1;
+            if (active && t_i < t_steps) {
+                const double t = dir ? tp : tn;
+                const bool inside = dir ? !(t > dq_max) : !(t < dq_min);
+                if (inside) {
+                    const float fx = (float)(t_x * t + (double)pi0x), fy = (float)(t_y * t + (double)pi0y);
+                    const int xi = (int)roundf(fx), yi = (int)roundf(fy);       // GetIndexRC
+                    if (!(xi >= cam.w || yi >= cam.h || xi < 0 || yi < 0)) {
+                        const int j = omask[(size_t)yi * cam.w + xi];
+                        if (j >= 0) {
+                            const double norm_m0 = (double)old.n_m[j];
+                            const float2 om = old.m_m[j];
+                            const double cang = (double)(om.x * km.x + om.y * km.y) / (norm_m0 * norm_m);
+                            if (!(cang < cang_min_edge || fabs(norm_m0 / norm_m - 1) > min_thr_mod)) {
+                                const double s_rho = old.s_rho[j], rho = old.rho[j];
+                                const double v_rho_dr = (loc_unc * loc_unc + s_rho * s_rho * norm_t * norm_t + sigma2_t * rho * rho);
+                                const double e = t - norm_t * rho;
+                                if (!(e * e > v_rho_dr)) j_hit = j;
+                            }
+                        }
+                    }
+                }
+            }
+            const unsigned int bal = __ballot_sync(0xffffffffu, j_hit >= 0);
+            const unsigned int grp = (bal >> (lane & ~(DM_G - 1))) & ((1u << DM_G) - 1u);
+            const int src = grp ? (lane & ~(DM_G - 1)) + __ffs(grp) - 1 : lane;
+            const int jw = __shfl_sync(0xffffffffu, j_hit, src);
+            if (grp) {   // the lowest lane with a hit = the first accepted probe of the sequential order
+                jm = jw;
+                active = false;
+            }
+#pragma unroll
+            for (int k = 0; k < DM_G / 2; k++) {
+                tp += 1;
+                tn -= 1;
+            }
+            t_i += DM_G / 2;
+            if (!__any_sync(0xffffffffu, active && t_i < t_steps)) break;
+        }
+        if (g != 0) jm = -1;   // one lane of the group writes
         if (jm >= 0) {                                                     // :343-366
             neu.rho[i] = old.rho[jm];
             neu.s_rho[i] = old.s_rho[jm];
@@ -1587,7 +1617,7 @@ int rb_directed_matching_enqueue(rb_ctx *c, rb_map *neu, rb_map *old, const DMat
         k_set_int<<<1, 1, 0, c->stream>>>(&neu->st->nmatch, 0);
         RB_LAUNCH_CHECK();
     }
-    RB_KLAUNCH(k_directed_match, rb_div_up(c->kcap, 128), 128, 0, neu->kl, neu->st, old->kl, old->mask, args_dev,
+    RB_KLAUNCH(k_directed_match, rb_div_up(c->kcap * DM_G, 128), 128, 0, neu->kl, neu->st, old->kl, old->mask, args_dev,
                make_cam(c), min_thr_mod, cang_min_edge, max_radius, loc_uncertainty, enable_dev);
     return RB_OK;
 }
