@@ -1,6 +1,6 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT && mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_pipeline.py tests/test_gpu_branches.py -x -q 2>&1 | tail -4
+timeout 1200 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -2
 for q in 1 2; do
 timeout 600 python bench.py --no-cpu-baseline --steps 8 > gpurun_out/bench_q.json 2>gpurun_out/bench_q.err; tail -c 300 gpurun_out/bench_q.err
 python - <<PY
