@@ -203,6 +203,7 @@ extern "C" int rb_ctx_create(rb_ctx **out, int device, const rb_camera *cam, dou
         c->min_cluster = !(mc && atoi(mc) == 0);
         const char *rs = getenv("REBVO_B200_ROWSCAN");
         c->rowscan_mode = rs ? atoi(rs) : 2;
+        c->mu_xchg = !(getenv("REBVO_B200_MU_XCHG") && atoi(getenv("REBVO_B200_MU_XCHG")) == 0);
         c->row_ns = getenv("REBVO_B200_ROW_NS") ? atoi(getenv("REBVO_B200_ROW_NS")) : 0;
         c->colscan_mode = getenv("REBVO_B200_COLSCAN") ? atoi(getenv("REBVO_B200_COLSCAN")) : 0;   // cp.async ring measured 1.85x faster than register prefetch
     }

@@ -107,6 +107,7 @@ struct rb_ctx {
     int min_cluster_kpc_multi;
     size_t min_cluster_dyn_multi;
     int min_debug_abort;
+    bool mu_xchg;        // env REBVO_B200_MU_XCHG (default 1): st.async all-reduce in k_map_update's rescaling iterations
     bool min_early;      // set by rb_pipeline around its Minimizer_RV launch: operands may be staged before the PDL wait  // test hook (env REBVO_B200_MIN_FORCE_ABORT=1): the kernel raises its abort flag at once
     int min_cluster_xchg; // 1: st.async + mbarrier exchange, 0: DSMEM stores + barrier.cluster (env REBVO_B200_MIN_XCHG)
     int row_ns;          // env REBVO_B200_ROW_NS: depth of the TMA tile ring of the row passes (0 = default 4)

@@ -1839,6 +1839,7 @@ struct MapUpdArgs {
     int q_bins;
     double q_min, q_max, q_perc;
     MapState *nst_next;
+    int xchg;                // 1: st.async + mbarrier all-reduce inside the rescaling iterations, 0: barrier.cluster
 };
 
 __device__ __forceinline__ void mu_block_sum2(double &a, double &b, double (*sw)[2], int tid) {
@@ -1873,7 +1874,9 @@ __global__ void __cluster_dims__(MU_C, 1, 1) __launch_bounds__(MU_T) k_map_updat
     pdl_launch();
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ double sw[MU_T / 32][2];
-    __shared__ double slots[2][MU_C][2];   // [iteration parity][rank][sum]
+    __shared__ __align__(16) double slots[2][MU_C][2];   // [iteration parity][rank][sum]
+    __shared__ __align__(8) unsigned long long xbar[2];  // one mbarrier per iteration parity (st.async exchange)
+    __shared__ int xfail;
     __shared__ int qh[MU_QBINS];           // EstimateQuantile histogram of this CTA's keylines (rank 0, later: the cluster's)
     __shared__ int qtab[MU_C][MU_QBINS];   // rank 0: every CTA's histogram (plain DSMEM stores: no initialisation to order)
     const int tid = threadIdx.x, rank = (int)cluster.block_rank();
@@ -1936,8 +1939,22 @@ __global__ void __cluster_dims__(MU_C, 1, 1) __launch_bounds__(MU_T) k_map_updat
                     }
                 }
             }
+            // all-reduce of an iteration's two sums: every CTA sends its pair to every CTA with st.async, completion counted on the
+            // receiver's mbarrier (as in k_minimizer_cluster): no cluster barrier, no fence inside the five dependent iterations
+            // (a barrier.cluster per iteration cost ~1.5 us each).  REBVO_B200_MU_XCHG=0: the barrier version.
+            const bool xchg = a.xchg != 0;
+            if (xchg) {
+                if (tid == 0) {
+                    mc_mbar_init(&xbar[0], 1);
+                    mc_mbar_init(&xbar[1], 1);
+                    xfail = 0;
+                    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                }
+                cluster.sync();   // every CTA's barriers exist before anybody sends
+            }
             double Kp = 1.0, RKp = 0;
             for (int iter = 0; iter < 5; iter++) {
+                if (xchg && tid == 0) mc_mbar_expect_tx(&xbar[iter & 1], MU_C * 16u);
                 double sa = 0, sb = 0;
 #pragma unroll
                 for (int j = 0; j < MU_KJ; j++)
@@ -1957,12 +1974,27 @@ __global__ void __cluster_dims__(MU_C, 1, 1) __launch_bounds__(MU_T) k_map_updat
                     }
                 }
                 mu_block_sum2(sa, sb, sw, tid);
-                if (tid < MU_C) {   // this CTA's pair into every CTA's table
-                    double *dst = cluster.map_shared_rank(&slots[iter & 1][rank][0], tid);
-                    dst[0] = sa;
-                    dst[1] = sb;
+                if (xchg) {
+                    if (tid < MU_C)
+                        mc_st_async_v2(mc_mapa(mc_smem_u32(&slots[iter & 1][rank][0]), (unsigned int)tid), sa, sb,
+                                       mc_mapa(mc_smem_u32(&xbar[iter & 1]), (unsigned int)tid));
+                    if (tid < 32) {   // one warp waits for the 16 pairs, the block follows through the barrier below
+                        const long long t0 = clock64();
+                        while (!mc_mbar_try_wait(&xbar[iter & 1], (unsigned int)(iter >> 1) & 1u))
+                            if (clock64() - t0 > (1ll << 28)) {
+                                xfail = 1;
+                                break;
+                            }
+                    }
+                    __syncthreads();
+                } else {
+                    if (tid < MU_C) {   // this CTA's pair into every CTA's table
+                        double *dst = cluster.map_shared_rank(&slots[iter & 1][rank][0], tid);
+                        dst[0] = sa;
+                        dst[1] = sb;
+                    }
+                    cluster.sync();
                 }
-                cluster.sync();
                 double rTr = 0, rTr0 = 0;
 #pragma unroll
                 for (int k = 0; k < MU_C; k++) {
@@ -1974,6 +2006,7 @@ __global__ void __cluster_dims__(MU_C, 1, 1) __launch_bounds__(MU_T) k_map_updat
                     RKp = 1 / rTr0;
                 }
             }
+            if (xchg && xfail) Kp = RKp = __longlong_as_double(0x7FF8000000000000ll);   // (an exchange timed out: poison, do not hang)
             if (a.re_escale)
                 for (int i = i0; i < kn; i += stride) {
                     kl.rho[i] = kl.rho[i] / Kp;
@@ -2026,7 +2059,9 @@ __global__ void __cluster_dims__(MU_C, 1, 1) __launch_bounds__(MU_T) k_map_updat
     }
 }
 
-static int launch_map_update(rb_ctx *c, rb_map *m, const MapUpdArgs &a) {
+static int launch_map_update(rb_ctx *c, rb_map *m, const MapUpdArgs &a_in) {
+    MapUpdArgs a = a_in;
+    a.xchg = c->mu_xchg ? 1 : 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(MU_C);
     cfg.blockDim = dim3(MU_T);
